@@ -1,0 +1,62 @@
+"""Builds libxrvio.so (every CUDA kernel for sm_100a + the C ABI) in-tree with nvcc."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libxrvio.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
+# per-source extra flags: the front end mirrors OpenCV's non-FMA float arithmetic
+SOURCES = {
+    "frontend.cu": ["-fmad=false"],
+    "backend_preint.cu": [],
+    "backend_solve.cu": [],
+    "backend_marg.cu": [],
+    "capi_ops.cu": [],
+    "capi_session.cu": [],
+}
+
+
+def _newer(a, b):
+    return (not os.path.exists(b)) or os.path.getmtime(a) > os.path.getmtime(b)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))]
+    headers.append(os.path.join(HERE, "..", "include", "xrvio.h"))
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+    objs = []
+    procs = []
+    for src, extra in SOURCES.items():
+        sp = os.path.join(CSRC, src)
+        if not os.path.exists(sp):
+            continue
+        op = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(op)
+        if force or _newer(sp, op) or hdr_time > os.path.getmtime(op):
+            cmd = ["nvcc"] + ARCH + COMMON + extra + ["-c", sp, "-o", op]
+            if verbose:
+                print(" ".join(cmd))
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write("nvcc failed for %s:\n%s\n" % (src, out.decode()))
+    if failed:
+        raise RuntimeError("libxrvio.so build failed")
+    if force or procs or not os.path.exists(LIB):
+        cmd = ["nvcc"] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,394 @@
+// K7-K11 driver: the Ceres-1.14-style trust-region loop around solve_core.cuh (see there).
+#include "solve_core.cuh"
+
+namespace xvbe {
+using namespace xv;
+
+size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k) {
+    size_t M = (size_t)((n_lm_free + 31) / 32) * 32 + 32;
+    size_t n = (size_t)15 * marg_k;
+    return 8 * M + (size_t)n_active * 6 * M + HPACK + (size_t)n_pre * kPreScratch + 4 * (n + 32) + n * n + 64;
+}
+
+
+// q <- normalize(q * exp(d)) for free pose blocks, additive elsewhere (quaternion_parameterization.h:11-17)
+__device__ void make_candidate(const Prob &P, Smem &s, double c1, double c2) {
+    const int tid = threadIdx.x;
+    // delta_j = (-c1 * gs_j / D_j^2 - c2 * y_j) * scale_j
+    for (int f = tid; f < P.d.n_frames; f += ST) {
+        double *c = s.cs + f * 16;
+        const double *x = s.xs + f * 16;
+        for (int k = 0; k < 16; ++k) c[k] = x[k];
+        if (f < P.d.n_active) {
+            double dl[15];
+            for (int k = 0; k < 15; ++k) {
+                const int j = 15 * f + k;
+                dl[k] = s.col_free[j] ? (-c1 * s.g[j] / (s.D[j] * s.D[j]) - c2 * s.y[j]) * s.scale[j] : 0.0;
+            }
+            if (s.pose_free[f]) {
+                st4(c, qnormalized(qmul(ld4(x), expmap(v3(dl[0], dl[1], dl[2])))));
+                for (int k = 0; k < 3; ++k) c[4 + k] = x[4 + k] + dl[3 + k];
+            }
+            if (s.motion_free[f])
+                for (int k = 0; k < 9; ++k) c[7 + k] = x[7 + k] + dl[6 + k];
+        }
+    }
+    for (int l = tid; l < P.M; l += ST) {
+        const double d = (-c1 * P.g_l[l] / (P.D_l[l] * P.D_l[l]) - c2 * P.y_l[l]) * P.sc_l[l];
+        P.inv_c[l] = P.inv_x[l] + d;
+    }
+    __syncthreads();
+}
+
+__device__ double ambient_sq(const Prob &P, Smem &s, const double *A, const double *B, const double *ia, const double *ib) {
+    // squared norm of (A - B) over the free blocks (B == nullptr: norm of A)
+    double a = 0.0;
+    for (int f = threadIdx.x; f < P.d.n_active; f += ST) {
+        if (s.pose_free[f])
+            for (int k = 0; k < 7; ++k) { double d = A[f * 16 + k] - (B ? B[f * 16 + k] : 0.0); a += d * d; }
+        if (s.motion_free[f])
+            for (int k = 7; k < 16; ++k) { double d = A[f * 16 + k] - (B ? B[f * 16 + k] : 0.0); a += d * d; }
+    }
+    for (int l = threadIdx.x; l < P.M; l += ST) { double d = ia[l] - (ib ? ib[l] : 0.0); a += d * d; }
+    return block_sum(a, s);
+}
+
+// Gauss-Newton step: (Hs + mu D^2) y = gs via Schur complement on the landmark block + Cholesky.
+// Returns false when the factorisation fails (LINEAR_SOLVER_FAILURE).  H is consumed.
+__device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = P.NPc, M = P.M, na = P.d.n_active;
+    for (int c = tid; c < n; c += ST)
+        if (s.col_free[c]) s.H[hidx(c, c)] += mu * s.D[c] * s.D[c];
+    for (int l = tid; l < M; l += ST) P.ht_l[l] = P.h_ll[l] + mu * P.D_l[l] * P.D_l[l];
+    for (int c = tid; c < n; c += ST) s.bred[c] = s.g[c];
+    __syncthreads();
+    schur_landmarks(P, s, s.bred);
+    __syncthreads();
+    // in-place right-looking Cholesky on the packed lower triangle
+    if (tid == 0) s.flag = 1;
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        const double d = s.H[hidx(j, j)];
+        if (!(d > 0.0) || !isfinite(d)) {
+            if (tid == 0) s.flag = 0;
+            break;                                   // uniform: every thread reads the same d
+        }
+        const double inv = 1.0 / sqrt(d);
+        __syncthreads();
+        for (int i = j + tid; i < n; i += ST) s.H[hidx(i, j)] = (i == j) ? sqrt(d) : s.H[hidx(i, j)] * inv;
+        __syncthreads();
+        for (int i = j + 1 + warp; i < n; i += NW) {
+            const double lij = s.H[hidx(i, j)];
+            if (lij == 0.0) continue;
+            const int row = i * (i + 1) / 2;
+            for (int k = j + 1 + lane; k <= i; k += 32) s.H[row + k] -= lij * s.H[hidx(k, j)];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (!s.flag) return false;
+    // forward / backward substitution (L z = b, L^T y = z)
+    for (int c = tid; c < n; c += ST) s.y[c] = s.bred[c];
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) s.y[j] /= s.H[hidx(j, j)];
+        __syncthreads();
+        const double yj = s.y[j];
+        for (int i = j + 1 + tid; i < n; i += ST) s.y[i] -= s.H[hidx(i, j)] * yj;
+        __syncthreads();
+    }
+    for (int j = n - 1; j >= 0; --j) {
+        if (tid == 0) s.y[j] /= s.H[hidx(j, j)];
+        __syncthreads();
+        const double yj = s.y[j];
+        for (int i = tid; i < j; i += ST) s.y[i] -= s.H[hidx(j, i)] * yj;
+        __syncthreads();
+    }
+    bool ok = true;
+    for (int c = tid; c < n; c += ST) ok = ok && isfinite(s.y[c]);
+    // back-substitute the landmarks: y_l = (gs_l - w_l . y_p) / ht_l
+    for (int l = tid; l < M; l += ST) {
+        double a = P.g_l[l];
+        for (int f = 0; f < na; ++f) {
+            if (!s.pose_free[f]) continue;
+            for (int k = 0; k < 6; ++k) a -= P.W[(size_t)(f * 6 + k) * M + l] * s.y[15 * f + k];
+        }
+        a /= P.ht_l[l];
+        P.y_l[l] = a;
+        ok = ok && isfinite(a);
+    }
+    const int allok = __syncthreads_and(ok ? 1 : 0);
+    return allok != 0;
+}
+
+__global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigParams *__restrict__ rig_g) {
+    extern __shared__ unsigned char smem_raw[];
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    __shared__ RigParams rg;
+    const int tid = threadIdx.x;
+    if (tid == 0) rg = *rig_g;
+    Prob P;
+    P.d = b.desc[blockIdx.x];
+    P.states_g = b.states + (size_t)P.d.frame_off * 16;
+    P.flags_g = b.frame_flags + P.d.frame_off;
+    P.invd_user = b.inv_depth + P.d.lm_off;
+    P.rpe = b.rpe; P.rot = b.rot; P.pre = b.pre; P.pre_blocks = b.pre_blocks; P.marg_frames = b.marg_frames;
+    P.M = P.d.n_lm_free;
+    P.NPc = 15 * P.d.n_active;
+    P.marg_n = 15 * P.d.marg_k;
+    {
+        const double *m = b.marg + P.d.marg_off;
+        const size_t n = P.marg_n;
+        P.marg_lin = m; P.marg_S = m + 16 * P.d.marg_k; P.marg_info = P.marg_S + n * n; P.marg_A0 = P.marg_info + n;
+        double *sc = b.scratch + P.d.scratch_off;
+        const size_t Mp = (size_t)((P.M + 31) / 32) * 32 + 32;
+        P.inv_x = sc; sc += Mp; P.inv_c = sc; sc += Mp; P.h_ll = sc; sc += Mp; P.g_l = sc; sc += Mp;
+        P.sc_l = sc; sc += Mp; P.D_l = sc; sc += Mp; P.y_l = sc; sc += Mp; P.ht_l = sc; sc += Mp;
+        P.W = sc; sc += (size_t)P.d.n_active * 6 * Mp;
+        P.Hcopy = sc; sc += HPACK;
+        P.pre_s = sc; sc += (size_t)P.d.n_pre * kPreScratch;
+        P.m_dx = sc; sc += n + 32; P.m_r = sc; sc += n + 32; P.m_v = sc; sc += n + 32; sc += n + 32;
+        P.m_T = sc;
+    }
+    SolveOut &out = b.out[blockIdx.x];
+    // ---- load user memory ----
+    for (int i = tid; i < P.d.n_frames * 16; i += ST) { const double v = P.states_g[i]; s.us[i] = v; s.xs[i] = v; s.cs[i] = v; }
+    for (int f = tid; f < kMaxActive; f += ST) {
+        const unsigned char fl = f < P.d.n_active ? P.flags_g[f] : 0;
+        s.pose_free[f] = fl & 1; s.motion_free[f] = (fl >> 1) & 1;
+    }
+    __syncthreads();
+    for (int c = tid; c < kNP; c += ST) {
+        const int f = c / 15, k = c % 15;
+        s.col_free[c] = (c < P.NPc) && (k < 6 ? s.pose_free[f] : s.motion_free[f]);
+        s.scale[c] = 1.0; s.D[c] = 1.0; s.y[c] = 0.0;
+    }
+    for (int l = tid; l < P.M; l += ST) { P.inv_x[l] = P.invd_user[l]; P.inv_c[l] = P.invd_user[l]; P.y_l[l] = 0.0; P.sc_l[l] = 1.0; P.D_l[l] = 1.0; }
+    __syncthreads();
+    int nfree = 0;
+    for (int c = 0; c < P.NPc; ++c) nfree += s.col_free[c];
+    nfree += P.M;
+
+    // ---- iteration zero ----
+    double x_cost = evaluate(P, s, s.xs, P.inv_x, rg, true);
+    if (nfree == 0) {
+        if (tid == 0) { out.iterations = 1; out.termination = 6; out.initial_cost = out.final_cost = x_cost; out.cost_trace[0] = x_cost; out.n_successful = out.n_unsuccessful = 0; }
+        return;
+    }
+    double gmax;
+    {
+        double m = 0.0;
+        for (int c = tid; c < P.NPc; c += ST) m = fmax(m, fabs(s.g[c]));
+        for (int l = tid; l < P.M; l += ST) m = fmax(m, fabs(P.g_l[l]));
+        gmax = block_max(m, s);
+    }
+    // Jacobi scaling, computed once: 1 / (1 + ||column||)
+    for (int c = tid; c < P.NPc; c += ST) s.scale[c] = s.col_free[c] ? 1.0 / (1.0 + sqrt(s.H[hidx(c, c)])) : 1.0;
+    for (int l = tid; l < P.M; l += ST) P.sc_l[l] = 1.0 / (1.0 + sqrt(P.h_ll[l]));
+    __syncthreads();
+
+    auto apply_scaling = [&]() {
+        for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) {
+            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while (i * (i + 1) / 2 > e) --i;
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            const int j = e - i * (i + 1) / 2;
+            if (s.col_free[i] && s.col_free[j]) s.H[e] *= s.scale[i] * s.scale[j];
+        }
+        for (int c = tid; c < P.NPc; c += ST) s.g[c] *= s.scale[c];
+        for (int l = tid; l < P.M; l += ST) { const double sl = P.sc_l[l]; P.h_ll[l] *= sl * sl; P.g_l[l] *= sl; }
+        for (int e = tid; e < P.d.n_active * 6 * P.M; e += ST) {
+            const int l = e % P.M, ck = e / P.M;
+            const int f = ck / 6, k = ck % 6;
+            P.W[(size_t)ck * P.M + l] *= P.sc_l[l] * s.scale[15 * f + k];
+        }
+        __syncthreads();
+        for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) P.Hcopy[e] = s.H[e];
+        __syncthreads();
+    };
+    apply_scaling();
+
+    double x_norm = sqrt(ambient_sq(P, s, s.xs, nullptr, P.inv_x, nullptr));
+    double minimum_cost = x_cost;
+    double radius = kInitialRadius, mu = kMinMu, alpha = 0.0, dogleg_step_norm = 0.0;
+    bool reuse = false;
+    // scalars of the current linearisation
+    double gnorm2 = 0.0, uHu = 0.0, gsy = 0.0, D2y2 = 0.0, gn_norm2 = 0.0, grad_dot_gn = 0.0;
+    int iteration = 0, termination = -1, n_succ = 0, n_unsucc = 0, n_invalid = 0, n_rec = 0;
+    bool it_success = true;
+    double it_cost = x_cost;
+    if (tid == 0) { out.initial_cost = x_cost; }
+
+    while (true) {
+        // ---- FinalizeIterationAndCheckIfMinimizerCanContinue ----
+        if (it_success) {
+            n_succ++;
+            if (x_cost < minimum_cost || iteration == 0) {
+                minimum_cost = fmin(minimum_cost, x_cost);
+                // parameters <- x ; StateUpdatingCallback copies them to user memory
+                for (int i = tid; i < P.d.n_active * 16; i += ST) { s.us[i] = s.xs[i]; P.states_g[i] = s.xs[i]; }
+                for (int l = tid; l < P.M; l += ST) P.invd_user[l] = P.inv_x[l];
+                __syncthreads();
+            }
+        } else n_unsucc++;
+        if (tid == 0 && n_rec < kMaxIter) out.cost_trace[n_rec] = it_cost;
+        n_rec++;
+        if (iteration >= P.d.max_iterations) { termination = 0; break; }
+        if (gmax <= kGradTol) { termination = 1; break; }
+        if (radius <= kMinRadius) { termination = 2; break; }
+        iteration++;
+        it_success = false;
+        // ---- DoglegStrategy::ComputeStep ----
+        bool solver_failed = false;
+        if (!reuse) {
+            reuse = true;
+            // diagonal = sqrt(clamp(diag(Js^T Js)))
+            for (int c = tid; c < P.NPc; c += ST)
+                s.D[c] = s.col_free[c] ? sqrt(fmin(fmax(s.H[hidx(c, c)], kMinDiag), kMaxDiag)) : 1.0;
+            for (int l = tid; l < P.M; l += ST) P.D_l[l] = sqrt(fmin(fmax(P.h_ll[l], kMinDiag), kMaxDiag));
+            __syncthreads();
+            // gradient / Cauchy point: ||grad||^2 with grad = gs / D ; uHu = v^T Hs v with v = gs / D^2
+            double a = 0.0, q = 0.0;
+            for (int c = tid; c < P.NPc; c += ST) { const double t = s.g[c] / s.D[c]; a += t * t; s.bred[c] = s.g[c] / (s.D[c] * s.D[c]); }
+            for (int l = tid; l < P.M; l += ST) { const double t = P.g_l[l] / P.D_l[l]; a += t * t; }
+            gnorm2 = block_sum(a, s);
+            for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) {
+                int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                while (i * (i + 1) / 2 > e) --i;
+                while ((i + 1) * (i + 2) / 2 <= e) ++i;
+                const int j = e - i * (i + 1) / 2;
+                if (s.col_free[i] && s.col_free[j]) q += (i == j ? 1.0 : 2.0) * s.bred[i] * s.H[e] * s.bred[j];
+            }
+            for (int l = tid; l < P.M; l += ST) {
+                const double vl = P.g_l[l] / (P.D_l[l] * P.D_l[l]);
+                double wv = 0.0;
+                for (int f = 0; f < P.d.n_active; ++f)
+                    if (s.pose_free[f])
+                        for (int k = 0; k < 6; ++k) wv += P.W[(size_t)(f * 6 + k) * P.M + l] * s.bred[15 * f + k];
+                q += 2.0 * vl * wv + P.h_ll[l] * vl * vl;
+            }
+            uHu = block_sum(q, s);
+            alpha = gnorm2 / uHu;
+            // Gauss-Newton step with the mu loop
+            solver_failed = true;
+            while (mu < kMaxMu) {
+                if (gauss_newton(P, s, mu)) { solver_failed = false; break; }
+                mu *= kMuInc;
+                for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) s.H[e] = P.Hcopy[e];
+                __syncthreads();
+            }
+            if (!solver_failed) {
+                double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+                for (int c = tid; c < P.NPc; c += ST)
+                    if (s.col_free[c]) { t1 += s.g[c] * s.y[c]; t2 += s.D[c] * s.D[c] * s.y[c] * s.y[c]; }
+                for (int l = tid; l < P.M; l += ST) { t1 += P.g_l[l] * P.y_l[l]; t2 += P.D_l[l] * P.D_l[l] * P.y_l[l] * P.y_l[l]; }
+                gsy = block_sum(t1, s);
+                D2y2 = block_sum(t2, s);
+                gn_norm2 = D2y2;               // ||gn||^2 with gn = -D y
+                grad_dot_gn = -gsy;            // grad . gn = sum (gs/D)(-D y)
+                (void)t3;
+            }
+        }
+        double c1 = 0.0, c2 = 0.0, model_cost_change = 0.0;
+        bool step_valid = false;
+        if (!solver_failed) {
+            // ComputeTraditionalDoglegStep
+            const double gnorm = sqrt(gnorm2), gn_norm = sqrt(gn_norm2);
+            if (gn_norm <= radius) { c1 = 0.0; c2 = 1.0; dogleg_step_norm = gn_norm; }
+            else if (gnorm * alpha >= radius) { c1 = radius / gnorm; c2 = 0.0; dogleg_step_norm = radius; }
+            else {
+                const double b_dot_a = -alpha * grad_dot_gn;
+                const double a_sq = (alpha * gnorm) * (alpha * gnorm);
+                const double bma_sq = a_sq - 2.0 * b_dot_a + gn_norm2;
+                const double c = b_dot_a - a_sq;
+                const double d = sqrt(c * c + bma_sq * (radius * radius - a_sq));
+                const double beta = (c <= 0) ? (d - c) / bma_sq : (radius * radius - a_sq) / (d + c);
+                c1 = alpha * (1.0 - beta); c2 = beta;
+                dogleg_step_norm = sqrt(fmax(c1 * c1 * gnorm2 - 2.0 * c1 * c2 * grad_dot_gn + c2 * c2 * gn_norm2, 0.0));
+            }
+            // step = c1 u + c2 w (Jacobi-scaled space), u = -gs/D^2, w = -y, Hs w = -gs + mu D^2 y
+            const double u_g = -gnorm2, w_g = -gsy;
+            const double uHw = gnorm2 - mu * gsy;
+            const double wHw = gsy - mu * D2y2;
+            model_cost_change = -(c1 * u_g + c2 * w_g) - 0.5 * (c1 * c1 * uHu + 2.0 * c1 * c2 * uHw + c2 * c2 * wHw);
+            step_valid = model_cost_change > 0.0;
+        }
+        if (!step_valid) {
+            n_invalid++;
+            if (n_invalid >= kMaxInvalid) { termination = 3; if (tid == 0 && n_rec < kMaxIter) out.cost_trace[n_rec] = it_cost; n_rec++; break; }
+            mu *= kMuInc; reuse = false;
+            // the linearisation is unchanged, but H was consumed by the factorisation
+            for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) s.H[e] = P.Hcopy[e];
+            __syncthreads();
+            continue;
+        }
+        n_invalid = 0;
+        make_candidate(P, s, c1, c2);
+        double cand_cost = evaluate(P, s, s.cs, P.inv_c, rg, false);
+        if (!isfinite(cand_cost)) cand_cost = x_cost;
+        const double step_norm = sqrt(ambient_sq(P, s, s.xs, s.cs, P.inv_x, P.inv_c));
+        if (step_norm <= kParamTol * (x_norm + kParamTol)) { termination = 4; if (tid == 0 && n_rec < kMaxIter) out.cost_trace[n_rec] = it_cost; n_rec++; break; }
+        const double cost_change = x_cost - cand_cost;
+        if (fabs(cost_change) <= kFuncTol * x_cost) { termination = 5; if (tid == 0 && n_rec < kMaxIter) out.cost_trace[n_rec] = it_cost; n_rec++; break; }
+        const double rel = cost_change / model_cost_change;
+        if (rel > kMinRelDecrease) {
+            // HandleSuccessfulStep: user memory still holds the previous iterate here (D10)
+            for (int i = tid; i < P.d.n_frames * 16; i += ST) s.xs[i] = s.cs[i];
+            for (int l = tid; l < P.M; l += ST) P.inv_x[l] = P.inv_c[l];
+            __syncthreads();
+            x_norm = sqrt(ambient_sq(P, s, s.xs, nullptr, P.inv_x, nullptr));
+            x_cost = evaluate(P, s, s.xs, P.inv_x, rg, true);
+            {
+                double m = 0.0;
+                for (int c = tid; c < P.NPc; c += ST) m = fmax(m, fabs(s.g[c]));
+                for (int l = tid; l < P.M; l += ST) m = fmax(m, fabs(P.g_l[l]));
+                gmax = block_max(m, s);
+            }
+            apply_scaling();
+            it_success = true;
+            it_cost = x_cost;
+            if (rel < 0.25) radius *= 0.5;
+            if (rel > 0.75) radius = fmax(radius, 3.0 * dogleg_step_norm);
+            mu = fmax(kMinMu, 2.0 * mu / kMuInc);
+            reuse = false;
+        } else {
+            it_success = false;
+            it_cost = cand_cost;
+            radius *= 0.5;
+            reuse = true;
+        }
+    }
+    if (tid == 0) {
+        out.iterations = n_rec; out.termination = termination; out.n_successful = n_succ; out.n_unsuccessful = n_unsucc;
+        out.final_cost = minimum_cost;
+    }
+}
+
+void solve(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
+    if (n_problems <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        attr_set = true;
+    }
+    solve_kernel<<<n_problems, ST, sizeof(Smem), st>>>(b, rig);
+}
+
+// A0 = S^T S, one CTA per prior
+__global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ S, double *__restrict__ A0, int n, size_t stride) {
+    const double *Sp = S + (size_t)blockIdx.x * stride;
+    double *Ap = A0 + (size_t)blockIdx.x * stride;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e % n;
+        double a = 0.0;
+        for (int r = 0; r < n; ++r) a += Sp[(size_t)r * n + i] * Sp[(size_t)r * n + j];
+        Ap[e] = a;
+    }
+}
+void gram(const double *S, double *A0, int n, int n_priors, size_t stride, cudaStream_t st) {
+    if (n_priors <= 0 || n <= 0) return;
+    gram_kernel<<<n_priors, 256, 0, st>>>(S, A0, n, stride);
+}
+
+}  // namespace xvbe

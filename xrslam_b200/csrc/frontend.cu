@@ -1,0 +1,634 @@
+// Front-end kernels for sm_100a.  See frontend.cuh.  Compiled with -fmad=false: the float
+// arithmetic of CLAHE interpolation, Harris and LK mirrors OpenCV's scalar code, which is not
+// FMA-contracted in its SSE3 baseline build.
+#include "frontend.cuh"
+#include <cfloat>
+#include <cmath>
+
+namespace xvfe {
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) {
+        if (p < 0) p = -p;
+        else p = 2 * len - 2 - p;
+    }
+    return p;
+}
+__device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }   // round half to even
+__device__ __forceinline__ uint8_t sat_u8(int v) { return (uint8_t)min(max(v, 0), 255); }
+
+// ------------------------------------------------------------------------------------------------
+// K1 CLAHE.  OpenCV clahe.cpp: per-tile histogram -> clip -> redistribute -> cdf LUT; then bilinear
+// blend of the four neighbouring tile LUTs (float).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ lut,
+                                                         int w, int h, int tw, int th, int tiles_x, int clip,
+                                                         float lut_scale) {
+    __shared__ int hist[256];
+    __shared__ int wsum[8];
+    __shared__ int scan_base[8];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x, img = blockIdx.y;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const uint8_t *I = src + (size_t)img * w * h;
+    hist[tid] = 0;
+    __syncthreads();
+    const int npx = tw * th;
+    const int x0 = tx * tw, y0 = ty * th;
+    for (int i = tid; i < npx; i += 256) {
+        int ly = i / tw, lx = i - ly * tw;
+        int x = x0 + lx, y = y0 + ly;
+        if (x >= w) x = reflect101(x, w);   // copyMakeBorder(..., BORDER_REFLECT_101) on right/bottom
+        if (y >= h) y = reflect101(y, h);
+        atomicAdd(&hist[I[(size_t)y * w + x]], 1);
+    }
+    __syncthreads();
+    int v = hist[tid];
+    int excess = 0;
+    if (clip > 0 && v > clip) { excess = v - clip; v = clip; }
+    // block sum of excess
+    int s = excess;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) wsum[tid >> 5] = s;
+    __syncthreads();
+    int clipped = 0;
+    for (int k = 0; k < 8; ++k) clipped += wsum[k];
+    if (clip > 0) {
+        int batch = clipped / 256;
+        int residual = clipped - batch * 256;
+        v += batch;
+        if (residual != 0) {
+            int step = max(256 / residual, 1);
+            if (tid % step == 0 && tid / step < residual) v++;
+        }
+    }
+    // inclusive scan over 256 bins
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((tid & 31) >= o) inc += t;
+    }
+    __syncthreads();
+    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int k = 0; k < 8; ++k) { scan_base[k] = acc; acc += wsum[k]; }
+    }
+    __syncthreads();
+    int sum = inc + scan_base[tid >> 5];
+    float f = (float)sum * lut_scale;
+    lut[((size_t)img * gridDim.x + tile) * 256 + tid] = sat_u8(cv_round(f));
+}
+
+__global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                           const uint8_t *__restrict__ lut, int w, int h, int tiles_x,
+                                                           int tiles_y, float inv_tw, float inv_th) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int img = blockIdx.z;
+    if (x >= w) return;
+    const uint8_t *L = lut + (size_t)img * tiles_x * tiles_y * 256;
+    float txf = (float)x * inv_tw - 0.5f;
+    int tx1 = (int)floorf(txf);
+    int tx2 = tx1 + 1;
+    float xa = txf - (float)tx1, xa1 = 1.0f - xa;
+    tx1 = max(tx1, 0); tx2 = min(tx2, tiles_x - 1);
+    float tyf = (float)y * inv_th - 0.5f;
+    int ty1 = (int)floorf(tyf);
+    int ty2 = ty1 + 1;
+    float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
+    ty1 = max(ty1, 0); ty2 = min(ty2, tiles_y - 1);
+    size_t p = (size_t)img * w * h + (size_t)y * w + x;
+    int v = src[p];
+    const uint8_t *P1 = L + (size_t)ty1 * tiles_x * 256;
+    const uint8_t *P2 = L + (size_t)ty2 * tiles_x * 256;
+    float l11 = (float)P1[tx1 * 256 + v], l12 = (float)P1[tx2 * 256 + v];
+    float l21 = (float)P2[tx1 * 256 + v], l22 = (float)P2[tx2 * 256 + v];
+    float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
+    dst[p] = sat_u8(cv_round(res));
+}
+
+void clahe(const uint8_t *src, uint8_t *dst, uint8_t *lut, int n, int w, int h, double clip_limit, int tiles_x,
+           int tiles_y, cudaStream_t st) {
+    int wext = (w % tiles_x == 0) ? w : w + (tiles_x - w % tiles_x);
+    int hext = (h % tiles_y == 0) ? h : h + (tiles_y - h % tiles_y);
+    if (w % tiles_x != 0 || h % tiles_y != 0) { wext = w + (tiles_x - w % tiles_x); hext = h + (tiles_y - h % tiles_y); }
+    int tw = wext / tiles_x, th = hext / tiles_y;
+    int area = tw * th;
+    float lut_scale = 255.0f / (float)area;
+    int clip = 0;
+    if (clip_limit > 0.0) { clip = (int)(clip_limit * area / 256); clip = clip > 1 ? clip : 1; }
+    clahe_lut_kernel<<<dim3(tiles_x * tiles_y, n), 256, 0, st>>>(src, lut, w, h, tw, th, tiles_x, clip, lut_scale);
+    float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+    clahe_apply_kernel<<<dim3((w + 255) / 256, h, n), 256, 0, st>>>(src, dst, lut, w, h, tiles_x, tiles_y, inv_tw, inv_th);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 pyrDown (5x5 Gaussian [1 4 6 4 1]^2 / 256, BORDER_REFLECT_101, rounding (s + 128) >> 8)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pyrdown_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                       int sw, int sh, int dw, int dh, size_t img_stride) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    const uint8_t *S = src + (size_t)blockIdx.z * img_stride;
+    uint8_t *D = dst + (size_t)blockIdx.z * img_stride;
+    const int wts[5] = {1, 4, 6, 4, 1};
+    int acc = 0;
+#pragma unroll
+    for (int j = -2; j <= 2; ++j) {
+        int yy = reflect101(2 * y + j, sh);
+        const uint8_t *row = S + (size_t)yy * sw;
+        int r = 0;
+#pragma unroll
+        for (int i = -2; i <= 2; ++i) {
+            int xx = reflect101(2 * x + i, sw);
+            r += wts[i + 2] * row[xx];
+        }
+        acc += wts[j + 2] * r;
+    }
+    D[(size_t)y * dw + x] = (uint8_t)((acc + 128) >> 8);
+}
+
+void pyramid(uint8_t *pyr, int n, const PyrLayout &L, cudaStream_t st) {
+    for (int l = 1; l < kPyrLevels; ++l) {
+        dim3 grid((L.w[l] + 31) / 32, (L.h[l] + 7) / 8, n);
+        pyrdown_kernel<<<grid, 256, 0, st>>>(pyr + L.off[l - 1], pyr + L.off[l], L.w[l - 1], L.h[l - 1], L.w[l], L.h[l], L.total);
+    }
+}
+
+// Scharr derivatives as calcSharrDeriv (lkpyramid.cpp): interleaved (dx, dy) int16.
+__global__ void scharr_kernel(const uint8_t *__restrict__ img, int16_t *__restrict__ deriv, int w, int h) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t *I = img + (size_t)blockIdx.z * w * h;
+    int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+    int ym = reflect101(y - 1, h), yp = reflect101(y + 1, h);
+    auto P = [&](int xx, int yy) { return (int)I[(size_t)yy * w + xx]; };
+    int t0m = (P(xm, ym) + P(xm, yp)) * 3 + P(xm, y) * 10;
+    int t0p = (P(xp, ym) + P(xp, yp)) * 3 + P(xp, y) * 10;
+    int t1m = P(xm, yp) - P(xm, ym);
+    int t1c = P(x, yp) - P(x, ym);
+    int t1p = P(xp, yp) - P(xp, ym);
+    size_t o = ((size_t)blockIdx.z * w * h + (size_t)y * w + x) * 2;
+    deriv[o] = (int16_t)(t0p - t0m);
+    deriv[o + 1] = (int16_t)((t1p + t1m) * 3 + t1c * 10);
+}
+void scharr(const uint8_t *img, int16_t *deriv, int n, int w, int h, cudaStream_t st) {
+    scharr_kernel<<<dim3((w + 127) / 128, h, n), 128, 0, st>>>(img, deriv, w, h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 GFTT with Harris response (goodFeaturesToTrack(useHarris) = cornerHarris(block 3, Sobel 3,
+// k 0.04) -> threshold q*max -> 3x3 NMS -> sort -> min-distance grid -> first max_corners).
+// ------------------------------------------------------------------------------------------------
+constexpr int HT_W = 32, HT_H = 16;       // response tile
+template <int HALO>                        // HALO = 0: max pass, 1: NMS pass
+__device__ __forceinline__ void harris_tile(const uint8_t *__restrict__ I, int w, int h, int bx, int by,
+                                            float (*resp)[HT_W + 2 * HALO]) {
+    // image tile with halo HALO + 2, derivative tiles with halo HALO + 1
+    constexpr int IW = HT_W + 2 * (HALO + 2), IH = HT_H + 2 * (HALO + 2);
+    constexpr int DW = HT_W + 2 * (HALO + 1), DH = HT_H + 2 * (HALO + 1);
+    constexpr int RW = HT_W + 2 * HALO, RH = HT_H + 2 * HALO;
+    __shared__ uint8_t simg[IH][IW];
+    __shared__ float sdx[DH][DW], sdy[DH][DW];
+    const int tid = threadIdx.x;
+    const int ix0 = bx - (HALO + 2), iy0 = by - (HALO + 2);
+    for (int i = tid; i < IW * IH; i += blockDim.x) {
+        int ly = i / IW, lx = i - ly * IW;
+        simg[ly][lx] = I[(size_t)reflect101(iy0 + ly, h) * w + reflect101(ix0 + lx, w)];
+    }
+    __syncthreads();
+    const float s1 = (float)(1.0 / 3060.0), s2 = (float)(2.0 / 3060.0);   // scale = 1/(4*3*255)
+    const int dx0 = bx - (HALO + 1), dy0 = by - (HALO + 1);
+    for (int i = tid; i < DW * DH; i += blockDim.x) {
+        int ly = i / DW, lx = i - ly * DW;
+        int gx = dx0 + lx, gy = dy0 + ly;
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+            int cx = lx + 1, cy = ly + 1;   // position in simg
+            // Dx: row filter [-1 0 1] (exact), column filter [s 2s s]
+            float rm = (float)((int)simg[cy - 1][cx + 1] - (int)simg[cy - 1][cx - 1]);
+            float r0 = (float)((int)simg[cy][cx + 1] - (int)simg[cy][cx - 1]);
+            float rp = (float)((int)simg[cy + 1][cx + 1] - (int)simg[cy + 1][cx - 1]);
+            sdx[ly][lx] = s2 * r0 + s1 * (rm + rp);
+            // Dy: row filter [s 2s s], column filter [-1 0 1]
+            float um = s2 * (float)simg[cy - 1][cx] + s1 * (float)((int)simg[cy - 1][cx - 1] + (int)simg[cy - 1][cx + 1]);
+            float up = s2 * (float)simg[cy + 1][cx] + s1 * (float)((int)simg[cy + 1][cx - 1] + (int)simg[cy + 1][cx + 1]);
+            sdy[ly][lx] = up - um;
+        }
+    }
+    __syncthreads();
+    // out-of-image derivative positions take the value at the reflected position (BORDER_REFLECT_101 of boxFilter)
+    for (int i = tid; i < DW * DH; i += blockDim.x) {
+        int ly = i / DW, lx = i - ly * DW;
+        int gx = dx0 + lx, gy = dy0 + ly;
+        if (!(gx >= 0 && gx < w && gy >= 0 && gy < h)) {
+            int rx = reflect101(gx, w) - dx0, ry = reflect101(gy, h) - dy0;
+            if (rx >= 0 && rx < DW && ry >= 0 && ry < DH) { sdx[ly][lx] = sdx[ry][rx]; sdy[ly][lx] = sdy[ry][rx]; }
+            else { sdx[ly][lx] = 0.f; sdy[ly][lx] = 0.f; }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < RW * RH; i += blockDim.x) {
+        int ly = i / RW, lx = i - ly * RW;
+        int gx = bx - HALO + lx, gy = by - HALO + ly;
+        float val = -FLT_MAX;
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+            float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float ra = 0.f, rb = 0.f, rc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float dx = sdx[ly + j][lx + k], dy = sdy[ly + j][lx + k];
+                    ra += dx * dx; rb += dx * dy; rc += dy * dy;
+                }
+                a += ra; b += rb; c += rc;
+            }
+            double da = a, db = b, dc = c;
+            val = (float)(da * dc - db * db - 0.04 * (da + dc) * (da + dc));
+        }
+        resp[ly][lx] = val;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) harris_max_kernel(const uint8_t *__restrict__ img, size_t img_stride, int w, int h,
+                                                          unsigned int *__restrict__ maxval) {
+    __shared__ float resp[HT_H][HT_W];
+    __shared__ float wmax[8];
+    const uint8_t *I = img + (size_t)blockIdx.z * img_stride;
+    harris_tile<0>(I, w, h, blockIdx.x * HT_W, blockIdx.y * HT_H, resp);
+    float m = 0.f;
+    for (int i = threadIdx.x; i < HT_W * HT_H; i += blockDim.x) m = fmaxf(m, resp[i / HT_W][i % HT_W]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) m = fmaxf(m, wmax[k]);
+        if (m > 0.f) atomicMax(&maxval[blockIdx.z], __float_as_uint(m));   // positive floats order as uints
+    }
+}
+
+__global__ void __launch_bounds__(256) harris_nms_kernel(const uint8_t *__restrict__ img, size_t img_stride, int w, int h,
+                                                          const unsigned int *__restrict__ maxval, float quality,
+                                                          unsigned long long *__restrict__ cand,
+                                                          int *__restrict__ cand_count) {
+    __shared__ float resp[HT_H + 2][HT_W + 2];
+    const uint8_t *I = img + (size_t)blockIdx.z * img_stride;
+    const int bx = blockIdx.x * HT_W, by = blockIdx.y * HT_H;
+    harris_tile<1>(I, w, h, bx, by, resp);
+    const float thr = (float)((double)__uint_as_float(maxval[blockIdx.z]) * (double)quality);
+    for (int i = threadIdx.x; i < HT_W * HT_H; i += blockDim.x) {
+        int ly = i / HT_W, lx = i - ly * HT_W;
+        int gx = bx + lx, gy = by + ly;
+        if (gx < 1 || gx >= w - 1 || gy < 1 || gy >= h - 1) continue;
+        float v = resp[ly + 1][lx + 1];
+        if (!(v > thr) || v == 0.f) continue;      // THRESH_TOZERO, then `val != 0`
+        bool is_max = true;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) is_max = is_max && (resp[ly + j][lx + k] <= v);
+        if (is_max) {
+            int slot = atomicAdd(&cand_count[blockIdx.z], 1);
+            if (slot < kMaxCand)
+                cand[(size_t)blockIdx.z * kMaxCand + slot] =
+                    ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(gy * w + gx);
+        }
+    }
+}
+
+// sort candidates (descending by response, then by descending address == descending y*w+x), greedy
+// min-distance selection on a cell grid (goodFeaturesToTrack), one block per image.
+__global__ void __launch_bounds__(1024) corner_select_kernel(unsigned long long *__restrict__ cand,
+                                                              const int *__restrict__ cand_count, int w, int h,
+                                                              int max_corners, float min_distance,
+                                                              float *__restrict__ corners, int *__restrict__ count) {
+    const int img = blockIdx.x;
+    unsigned long long *C = cand + (size_t)img * kMaxCand;
+    const int n = min(cand_count[img], kMaxCand);
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = n + threadIdx.x; i < np2; i += blockDim.x) C[i] = 0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                int l = i ^ j;
+                if (l > i) {
+                    unsigned long long a = C[i], b = C[l];
+                    bool desc = ((i & k) == 0);
+                    if (desc ? (a < b) : (a > b)) { C[i] = b; C[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // greedy selection by warp 0
+    constexpr int CELL_CAP = 8;
+    const int cell = __float2int_rn(min_distance);
+    const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+    extern __shared__ unsigned char smem_raw[];
+    short *cell_cnt = reinterpret_cast<short *>(smem_raw);                 // gw*gh
+    short2 *cell_pts = reinterpret_cast<short2 *>(cell_cnt + ((gw * gh + 1) & ~1));   // gw*gh*CELL_CAP
+    for (int i = threadIdx.x; i < gw * gh; i += blockDim.x) cell_cnt[i] = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const float md2 = min_distance * min_distance;
+        int ncorners = 0;
+        for (int i = 0; i < n && ncorners < max_corners; ++i) {
+            unsigned long long key = C[i];
+            int idx = (int)(key & 0xffffffffu);
+            int y = idx / w, x = idx - y * w;
+            int xc = x / cell, yc = y / cell;
+            bool bad = false;
+            if (lane < 9) {
+                int xx = xc - 1 + lane % 3, yy = yc - 1 + lane / 3;
+                if (xx >= 0 && xx < gw && yy >= 0 && yy < gh) {
+                    int c = yy * gw + xx;
+                    int m = cell_cnt[c];
+                    for (int q = 0; q < m; ++q) {
+                        short2 p = cell_pts[c * CELL_CAP + q];
+                        float dx = (float)(x - p.x), dy = (float)(y - p.y);
+                        if (dx * dx + dy * dy < md2) bad = true;
+                    }
+                }
+            }
+            bad = __any_sync(0xffffffffu, bad);
+            if (!bad) {
+                if (lane == 0) {
+                    int c = yc * gw + xc;
+                    int m = cell_cnt[c];
+                    if (m < CELL_CAP) { cell_pts[c * CELL_CAP + m] = make_short2((short)x, (short)y); cell_cnt[c] = m + 1; }
+                    float *o = corners + ((size_t)img * kMaxCorners + ncorners) * 3;
+                    o[0] = (float)x; o[1] = (float)y; o[2] = __uint_as_float((unsigned int)(key >> 32));
+                }
+                ncorners++;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) count[img] = ncorners;
+    }
+}
+
+void gftt_harris(const uint8_t *img, size_t img_stride, int n, int w, int h, int max_corners, float quality,
+                 float min_distance, float *corners, int *count, unsigned long long *cand, int *cand_count,
+                 unsigned int *maxval, cudaStream_t st) {
+    cudaMemsetAsync(maxval, 0, sizeof(unsigned int) * n, st);
+    cudaMemsetAsync(cand_count, 0, sizeof(int) * n, st);
+    dim3 grid((w + HT_W - 1) / HT_W, (h + HT_H - 1) / HT_H, n);
+    harris_max_kernel<<<grid, 256, 0, st>>>(img, img_stride, w, h, maxval);
+    harris_nms_kernel<<<grid, 256, 0, st>>>(img, img_stride, w, h, maxval, quality, cand, cand_count);
+    int cell = (int)lrintf(min_distance);
+    int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+    size_t smem = (size_t)((gw * gh + 1) & ~1) * sizeof(short) + (size_t)gw * gh * 8 * sizeof(short2);
+    if (max_corners > kMaxCorners) max_corners = kMaxCorners;
+    corner_select_kernel<<<n, 1024, smem, st>>>(cand, cand_count, w, h, max_corners, min_distance, corners, count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 pyramidal Lucas-Kanade (calcOpticalFlowPyrLK, winSize 21x21, maxLevel 3, 30 iterations, eps
+// 0.01, OPTFLOW_USE_INITIAL_FLOW, minEigThreshold 1e-4) -- one warp per keypoint, forward pass,
+// the reference's gates, backward pass and the 0.5 px round-trip check fused.
+// ------------------------------------------------------------------------------------------------
+constexpr int WIN = 21;
+constexpr int WINP = WIN + 1;     // 22: window + 1 for bilinear taps
+constexpr int RAWP = WIN + 3;     // 24: + 1 px ring for the Scharr stencil
+constexpr int KLT_WARPS = 4;
+
+struct KltSmem {
+    uint8_t raw[RAWP][RAWP + 4];      // level image around the template window (reflect-101 border)
+    short dx[WINP][WINP];             // Scharr derivatives at the 22x22 positions (0 outside the image)
+    short dy[WINP][WINP];
+    short I[WIN * WIN];               // template patch  (<< 5)
+    short Ix[WIN * WIN], Iy[WIN * WIN];
+    uint8_t J[WINP][WINP + 2];        // search window in the other image
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One LK run for one point through all levels.  Returns status; out = tracked point (level 0).
+__device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *__restrict__ pyrJ, const PyrLayout &L,
+                               float px, float py, float gx, float gy, float &ox, float &oy, KltSmem &sm) {
+    const int lane = threadIdx.x & 31;
+    bool status = true;
+    float outx = 0.f, outy = 0.f;
+    for (int level = kPyrLevels - 1; level >= 0; --level) {
+        const int cols = L.w[level], rows = L.h[level];
+        const uint8_t *I = pyrI + L.off[level];
+        const uint8_t *J = pyrJ + L.off[level];
+        const float sc = 1.f / (float)(1 << level);
+        float ppx = px * sc, ppy = py * sc;
+        float nx, ny;
+        if (level == kPyrLevels - 1) { nx = gx * sc; ny = gy * sc; }
+        else { nx = outx * 2.f; ny = outy * 2.f; }
+        outx = nx; outy = ny;
+        ppx -= 10.f; ppy -= 10.f;
+        const int ipx = (int)floorf(ppx), ipy = (int)floorf(ppy);
+        if (ipx < -WIN || ipx >= cols || ipy < -WIN || ipy >= rows) {
+            if (level == 0) status = false;
+            continue;
+        }
+        float a = ppx - (float)ipx, b = ppy - (float)ipy;
+        int iw00 = cv_round((1.f - a) * (1.f - b) * 16384.f);
+        int iw01 = cv_round(a * (1.f - b) * 16384.f);
+        int iw10 = cv_round((1.f - a) * b * 16384.f);
+        int iw11 = 16384 - iw00 - iw01 - iw10;
+        // stage the raw template neighbourhood
+        __syncwarp();
+        for (int i = lane; i < RAWP * RAWP; i += 32) {
+            int ly = i / RAWP, lx = i - ly * RAWP;
+            sm.raw[ly][lx] = I[(size_t)reflect101(ipy - 1 + ly, rows) * cols + reflect101(ipx - 1 + lx, cols)];
+        }
+        __syncwarp();
+        for (int i = lane; i < WINP * WINP; i += 32) {
+            int ly = i / WINP, lx = i - ly * WINP;
+            int X = ipx + lx, Y = ipy + ly;
+            short ddx = 0, ddy = 0;
+            if (X >= 0 && X < cols && Y >= 0 && Y < rows) {
+                int cx = lx + 1, cy = ly + 1;
+                int t0m = ((int)sm.raw[cy - 1][cx - 1] + (int)sm.raw[cy + 1][cx - 1]) * 3 + (int)sm.raw[cy][cx - 1] * 10;
+                int t0p = ((int)sm.raw[cy - 1][cx + 1] + (int)sm.raw[cy + 1][cx + 1]) * 3 + (int)sm.raw[cy][cx + 1] * 10;
+                int t1m = (int)sm.raw[cy + 1][cx - 1] - (int)sm.raw[cy - 1][cx - 1];
+                int t1c = (int)sm.raw[cy + 1][cx] - (int)sm.raw[cy - 1][cx];
+                int t1p = (int)sm.raw[cy + 1][cx + 1] - (int)sm.raw[cy - 1][cx + 1];
+                ddx = (short)(t0p - t0m);
+                ddy = (short)((t1p + t1m) * 3 + t1c * 10);
+            }
+            sm.dx[ly][lx] = ddx; sm.dy[ly][lx] = ddy;
+        }
+        __syncwarp();
+        float A11 = 0.f, A12 = 0.f, A22 = 0.f;
+        for (int i = lane; i < WIN * WIN; i += 32) {
+            int y = i / WIN, x = i - y * WIN;
+            int cy = y + 1, cx = x + 1;
+            int ival = ((int)sm.raw[cy][cx] * iw00 + (int)sm.raw[cy][cx + 1] * iw01 + (int)sm.raw[cy + 1][cx] * iw10 +
+                        (int)sm.raw[cy + 1][cx + 1] * iw11 + (1 << 8)) >> 9;
+            int ixval = ((int)sm.dx[y][x] * iw00 + (int)sm.dx[y][x + 1] * iw01 + (int)sm.dx[y + 1][x] * iw10 +
+                         (int)sm.dx[y + 1][x + 1] * iw11 + (1 << 13)) >> 14;
+            int iyval = ((int)sm.dy[y][x] * iw00 + (int)sm.dy[y][x + 1] * iw01 + (int)sm.dy[y + 1][x] * iw10 +
+                         (int)sm.dy[y + 1][x + 1] * iw11 + (1 << 13)) >> 14;
+            sm.I[i] = (short)ival; sm.Ix[i] = (short)ixval; sm.Iy[i] = (short)iyval;
+            A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
+        }
+        const float FLT_SCALE = 1.f / (float)(1 << 20);
+        A11 = warp_sum(A11) * FLT_SCALE; A12 = warp_sum(A12) * FLT_SCALE; A22 = warp_sum(A22) * FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
+        if ((double)minEig < 1e-4 || D < FLT_EPSILON) {
+            if (level == 0) status = false;
+            continue;
+        }
+        D = 1.f / D;
+        nx -= 10.f; ny -= 10.f;
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < 30; ++j) {
+            const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+            if (inx < -WIN || inx >= cols || iny < -WIN || iny >= rows) {
+                if (level == 0) status = false;
+                break;
+            }
+            a = nx - (float)inx; b = ny - (float)iny;
+            iw00 = cv_round((1.f - a) * (1.f - b) * 16384.f);
+            iw01 = cv_round(a * (1.f - b) * 16384.f);
+            iw10 = cv_round((1.f - a) * b * 16384.f);
+            iw11 = 16384 - iw00 - iw01 - iw10;
+            __syncwarp();
+            for (int i = lane; i < WINP * WINP; i += 32) {
+                int ly = i / WINP, lx = i - ly * WINP;
+                sm.J[ly][lx] = J[(size_t)reflect101(iny + ly, rows) * cols + reflect101(inx + lx, cols)];
+            }
+            __syncwarp();
+            float b1 = 0.f, b2 = 0.f;
+            for (int i = lane; i < WIN * WIN; i += 32) {
+                int y = i / WIN, x = i - y * WIN;
+                int diff = (((int)sm.J[y][x] * iw00 + (int)sm.J[y][x + 1] * iw01 + (int)sm.J[y + 1][x] * iw10 +
+                             (int)sm.J[y + 1][x + 1] * iw11 + (1 << 8)) >> 9) - (int)sm.I[i];
+                b1 += (float)(diff * (int)sm.Ix[i]);
+                b2 += (float)(diff * (int)sm.Iy[i]);
+            }
+            b1 = warp_sum(b1) * FLT_SCALE; b2 = warp_sum(b2) * FLT_SCALE;
+            float dxv = (A12 * b2 - A22 * b1) * D;
+            float dyv = (A12 * b1 - A11 * b2) * D;
+            nx += dxv; ny += dyv;
+            outx = nx + 10.f; outy = ny + 10.f;
+            if ((double)dxv * (double)dxv + (double)dyv * (double)dyv <= 0.01 * 0.01) break;
+            if (j > 0 && fabsf(dxv + pdx) < 0.01f && fabsf(dyv + pdy) < 0.01f) {
+                outx -= dxv * 0.5f; outy -= dyv * 0.5f;
+                break;
+            }
+            pdx = dxv; pdy = dyv;
+        }
+    }
+    ox = outx; oy = outy;
+    return status;
+}
+
+__global__ void __launch_bounds__(32 * KLT_WARPS) klt_kernel(const uint8_t *__restrict__ prev_pyr,
+                                                              const uint8_t *__restrict__ next_pyr, PyrLayout L,
+                                                              const float *__restrict__ prev_pts,
+                                                              float *__restrict__ next_pts,
+                                                              const int *__restrict__ npts,
+                                                              uint8_t *__restrict__ status) {
+    __shared__ KltSmem sm[KLT_WARPS];
+    const int img = blockIdx.y;
+    const int warp = threadIdx.x >> 5;
+    const int pt = blockIdx.x * KLT_WARPS + warp;
+    if (pt >= npts[img]) return;
+    const uint8_t *P = prev_pyr + (size_t)img * L.total;
+    const uint8_t *N = next_pyr + (size_t)img * L.total;
+    const size_t o = ((size_t)img * kMaxPts + pt) * 2;
+    const float px = prev_pts[o], py = prev_pts[o + 1];
+    const float gx = next_pts[o], gy = next_pts[o + 1];
+    float qx, qy;
+    bool st = lk_track_point(P, N, L, px, py, gx, gy, qx, qy, sm[warp]);
+    const int cols = L.w[0], rows = L.h[0];
+    // reference gates, opencv_image.cpp:99-113
+    if (qx < 20.f || qx >= (float)(cols - 20) || qy < 20.f || qy >= (float)(rows - 20)) st = false;
+    if (st) {
+        double fx = (double)(qx - px), fy = (double)(qy - py);
+        if (sqrt(fx * fx + fy * fy) > (double)(rows / 4)) st = false;
+    }
+    if (st) {
+        float bx, by;
+        bool stb = lk_track_point(N, P, L, qx, qy, px, py, bx, by, sm[warp]);
+        double ex = (double)(px - bx), ey = (double)(py - by);
+        if (!stb || sqrt(ex * ex + ey * ey) > 0.5) st = false;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        next_pts[o] = qx; next_pts[o + 1] = qy;
+        status[(size_t)img * kMaxPts + pt] = st ? 1 : 0;
+    }
+}
+
+void klt_track(const uint8_t *prev_pyr, const uint8_t *next_pyr, int n, const PyrLayout &L, const float *prev_pts,
+               float *next_pts, const int *npts, uint8_t *status, cudaStream_t st) {
+    dim3 grid(kMaxPts / KLT_WARPS, n);
+    klt_kernel<<<grid, 32 * KLT_WARPS, 0, st>>>(prev_pyr, next_pyr, L, prev_pts, next_pts, npts, status);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 Poisson-disk filter (poisson_disk_filter.h): one warp per list; the 25-cell neighbourhood scan
+// (first cell skipped, one extra cell visited) is spread over the lanes.
+// ------------------------------------------------------------------------------------------------
+constexpr int PG_W = 192, PG_H = 128;    // grid cells available (cell = radius / sqrt 2)
+__global__ void __launch_bounds__(32) poisson_kernel(const double *__restrict__ pts, const int *__restrict__ n_preset,
+                                                      const int *__restrict__ n_total,
+                                                      const uint8_t *__restrict__ veto, uint8_t *__restrict__ keep,
+                                                      double radius) {
+    extern __shared__ short grid[];      // PG_W * PG_H, -1 = empty
+    const int list = blockIdx.x, lane = threadIdx.x;
+    for (int i = lane; i < PG_W * PG_H; i += 32) grid[i] = -1;
+    __syncwarp();
+    const double *P = pts + (size_t)list * kMaxPts * 2;
+    const double r2 = radius * radius;
+    const double gs = radius / sqrt(2.0);
+    const int npre = n_preset[list], ntot = n_total[list];
+    for (int i = 0; i < ntot; ++i) {
+        const double x = P[2 * i], y = P[2 * i + 1];
+        const int ix = (int)floor(x / gs), iy = (int)floor(y / gs);
+        bool ok = true;
+        if (i >= npre) {
+            bool hit = false;
+            if (lane < 25) {
+                // visit order of test_point: all cells of the 5x5 block except (bx,by), plus (bx, ey + 1)
+                int cx, cy;
+                if (lane == 0) { cx = ix - 2; cy = iy + 3; }
+                else { cx = ix - 2 + lane % 5; cy = iy - 2 + lane / 5; }
+                if (cx >= 0 && cx < PG_W && cy >= 0 && cy < PG_H) {
+                    int k = grid[cy * PG_W + cx];
+                    if (k >= 0) {
+                        double dx = x - P[2 * k], dy = y - P[2 * k + 1];
+                        if (dx * dx + dy * dy < r2) hit = true;
+                    }
+                }
+            }
+            ok = !__any_sync(0xffffffffu, hit);
+            if (veto != nullptr && veto[(size_t)list * kMaxPts + i]) ok = false;
+            if (lane == 0) keep[(size_t)list * kMaxPts + i] = ok ? 1 : 0;
+        } else if (lane == 0) keep[(size_t)list * kMaxPts + i] = 1;
+        if (ok && lane == 0 && ix >= 0 && ix < PG_W && iy >= 0 && iy < PG_H) grid[iy * PG_W + ix] = (short)i;
+        __syncwarp();
+    }
+}
+
+void poisson_filter(const double *pts, const int *n_preset, const int *n_total, const uint8_t *veto, uint8_t *keep,
+                    int n, double radius, cudaStream_t st) {
+    static bool attr_set = false;
+    size_t smem = (size_t)PG_W * PG_H * sizeof(short);
+    if (!attr_set) {
+        cudaFuncSetAttribute(poisson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    poisson_kernel<<<n, 32, smem, st>>>(pts, n_preset, n_total, veto, keep, radius);
+}
+
+}  // namespace xvfe

@@ -1,0 +1,419 @@
+// Shared device code of the solve (K7-K11) and marginalisation (K12) kernels.
+// K7-K11: one CTA per sliding-window problem runs the whole trust-region solve on chip:
+// residual / Jacobian evaluation, robust corrector, block-sparse J^T J with warp-shuffle segmented
+// reductions, scalar-landmark Schur complement, in-shared-memory Cholesky of the reduced system,
+// traditional dogleg step, Ceres-1.14 accept / reject / radius logic, candidate evaluation.
+// The problem wiring follows xrslam/src/xrslam/estimation/solver.cpp:84-190; the loop restates the
+// published Ceres 1.14 trust-region minimiser (not under /root/reference).
+#pragma once
+#include "backend.cuh"
+#include "factors.cuh"
+#include <cfloat>
+
+namespace xvbe {
+using namespace xv;
+
+constexpr int ST = 256;                    // threads per CTA
+constexpr int NW = ST / 32;
+constexpr int HPACK = kNP * (kNP + 1) / 2;
+constexpr int kPreScratch = 1024;          // doubles of scratch per preintegration factor
+
+// Ceres 1.14 Solver::Options defaults (Appendix C of SURVEY.md)
+constexpr double kInitialRadius = 1e4, kMinRadius = 1e-32, kMinRelDecrease = 1e-3;
+constexpr double kFuncTol = 1e-6, kGradTol = 1e-10, kParamTol = 1e-8;
+constexpr double kMinDiag = 1e-6, kMaxDiag = 1e32, kMinMu = 1e-8, kMaxMu = 1.0, kMuInc = 10.0;
+constexpr int kMaxInvalid = 5;
+
+struct Smem {
+    double H[HPACK];                       // packed lower-triangular, row i at i(i+1)/2
+    double xs[kMaxFrames * 16];            // current iterate
+    double cs[kMaxFrames * 16];            // candidate
+    double us[kMaxFrames * 16];            // user memory (last state written back)
+    double g[kNP], scale[kNP], D[kNP], y[kNP], bred[kNP];
+    double red[NW];
+    double jrinv[kMaxActive * 9];
+    unsigned char col_free[kNP];
+    unsigned char pose_free[kMaxActive], motion_free[kMaxActive];
+    double sc[16];                         // broadcast scalars
+    int flag;
+};
+
+__device__ __forceinline__ int hidx(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
+
+__device__ __forceinline__ double block_sum(double v, Smem &s) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < NW; ++k) t += s.red[k];
+    return t;
+}
+__device__ __forceinline__ double block_max(double v, Smem &s) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < NW; ++k) t = fmax(t, s.red[k]);
+    return t;
+}
+
+// segmented suffix sum over lanes with sorted (contiguous) keys; segment heads end up with the sum
+__device__ __forceinline__ double seg_sum(double v, int key, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_down_sync(0xffffffffu, v, o);
+        int k = __shfl_down_sync(0xffffffffu, key, o);
+        if (lane + o < 32 && k == key) v += t;
+    }
+    return v;
+}
+
+struct Prob {
+    SolveDesc d;
+    double *states_g;              // user memory in global
+    const unsigned char *flags_g;
+    double *invd_user;             // user memory (global)
+    const RpeObs *rpe;
+    const RotObs *rot;
+    const PreRef *pre;
+    const double *pre_blocks;
+    const int *marg_frames;
+    const double *marg_lin, *marg_S, *marg_info, *marg_A0;
+    int marg_n;
+    // scratch (global)
+    double *inv_x, *inv_c, *h_ll, *g_l, *sc_l, *D_l, *y_l, *ht_l, *W, *Hcopy, *pre_s, *m_dx, *m_r, *m_v, *m_T;
+    int M, NPc;                    // free landmarks, pose/motion columns = 15 * n_active
+};
+
+// ------------------------------------------------------------------------------------------------
+// Residual (+ Jacobian) evaluation at S (= xs or cs) / inv (= inv_x or inv_c).  Returns the cost.
+// With want_jac the unscaled H (pose/motion block, packed in shared memory), g, W, h_ll, g_l are
+// rebuilt.  Constant blocks and "user memory" reads come from us / invd_user.
+// ------------------------------------------------------------------------------------------------
+static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const double *inv, const RigParams &rg,
+                           bool want_jac, bool robust = true) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = P.M;
+    if (want_jac) {
+        for (int i = tid; i < HPACK; i += ST) s.H[i] = 0.0;
+        for (int i = tid; i < kNP; i += ST) s.g[i] = 0.0;
+        for (int i = tid; i < M; i += ST) { P.h_ll[i] = 0.0; P.g_l[i] = 0.0; }
+        const int nw = P.d.n_active * 6 * M;
+        for (int i = tid; i < nw; i += ST) P.W[i] = 0.0;
+    }
+    __syncthreads();
+    double cost = 0.0;
+    // ---------------- reprojection residuals (Cauchy loss) ----------------
+    for (int base = warp * 32; base < P.d.n_rpe; base += NW * 32) {
+        const int o = base + lane;
+        const bool valid = o < P.d.n_rpe;
+        RpeEval e;
+        int ts = 0, rs = 0, lm = 0;
+        bool prior = true, tf = false, rf = false, lf = false;
+        double w = 0.0;
+        if (valid) {
+            const RpeObs ob = P.rpe[P.d.rpe_off + o];
+            ts = ob.tgt; rs = ob.ref; lm = ob.lm; prior = ob.prior != 0;
+            const double *st = S + ts * 16;
+            const double *sr = prior ? (s.us + rs * 16) : (S + rs * 16);
+            const double idp = prior ? P.invd_user[lm] : inv[lm];
+            tf = ts < P.d.n_active && s.pose_free[ts];
+            rf = !prior && rs < P.d.n_active && s.pose_free[rs];
+            lf = !prior && lm < M;
+            rpe_eval(ld4(st), ld3(st + 4), ld4(sr), ld3(sr + 4), idp, ld3(ob.zt), ld3(ob.zr), rg, want_jac,
+                     want_jac && !prior, e);
+            const double sq = e.r[0] * e.r[0] + e.r[1] * e.r[1];
+            if (robust) {
+                cost += 0.5 * log(1.0 + sq);                // CauchyLoss(1): rho(s) = log(1 + s)
+                w = sqrt(1.0 / (1.0 + sq));                 // corrector: rho'' < 0 -> scale by sqrt(rho')
+            } else { cost += 0.5 * sq; w = 1.0; }
+        }
+        if (!want_jac) continue;                            // warp-uniform
+        if (valid) {
+            e.r[0] *= w; e.r[1] *= w;
+            for (int k = 0; k < 12; ++k) e.Jt[k] *= w;
+            if (!prior) { for (int k = 0; k < 12; ++k) e.Jr[k] *= w; e.Jl[0] *= w; e.Jl[1] *= w; }
+        }
+        // --- (tgt,tgt) block + g_tgt : segments keyed by tgt ---
+        {
+            const int key = (valid && tf) ? ts : -1 - lane;
+            const bool head = (lane == 0) || (__shfl_up_sync(0xffffffffu, key, 1) != key);
+            const bool act = valid && tf;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    double v = act ? (e.Jt[i] * e.Jt[j] + e.Jt[6 + i] * e.Jt[6 + j]) : 0.0;
+                    v = seg_sum(v, key, lane);
+                    if (act && head) atomicAdd(&s.H[hidx(15 * ts + i, 15 * ts + j)], v);
+                }
+                double gv = act ? (e.Jt[i] * e.r[0] + e.Jt[6 + i] * e.r[1]) : 0.0;
+                gv = seg_sum(gv, key, lane);
+                if (act && head) atomicAdd(&s.g[15 * ts + i], gv);
+            }
+        }
+        // --- (tgt,ref), (ref,ref) blocks + g_ref : segments keyed by (tgt, ref) ---
+        const unsigned any_full = __ballot_sync(0xffffffffu, valid && !prior);
+        if (any_full) {
+            const int key = (valid && !prior) ? ((ts << 8) | rs) : -1 - lane;
+            const bool head = (lane == 0) || (__shfl_up_sync(0xffffffffu, key, 1) != key);
+            const bool act_tr = valid && tf && rf, act_rr = valid && rf;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    double v = act_tr ? (e.Jt[i] * e.Jr[j] + e.Jt[6 + i] * e.Jr[6 + j]) : 0.0;
+                    v = seg_sum(v, key, lane);
+                    if (act_tr && head) {
+                        const int a = 15 * ts + i, b = 15 * rs + j;
+                        atomicAdd(&s.H[a > b ? hidx(a, b) : hidx(b, a)], v);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    double v = act_rr ? (e.Jr[i] * e.Jr[j] + e.Jr[6 + i] * e.Jr[6 + j]) : 0.0;
+                    v = seg_sum(v, key, lane);
+                    if (act_rr && head) atomicAdd(&s.H[hidx(15 * rs + i, 15 * rs + j)], v);
+                }
+                double gv = act_rr ? (e.Jr[i] * e.r[0] + e.Jr[6 + i] * e.r[1]) : 0.0;
+                gv = seg_sum(gv, key, lane);
+                if (act_rr && head) atomicAdd(&s.g[15 * rs + i], gv);
+            }
+            // landmark column: h_ll, g_l, W (W[slot][k][l], l fastest)
+            if (valid && lf) {
+                atomicAdd(&P.h_ll[lm], e.Jl[0] * e.Jl[0] + e.Jl[1] * e.Jl[1]);
+                atomicAdd(&P.g_l[lm], e.Jl[0] * e.r[0] + e.Jl[1] * e.r[1]);
+                if (tf)
+                    for (int k = 0; k < 6; ++k) P.W[(size_t)(ts * 6 + k) * M + lm] = e.Jl[0] * e.Jt[k] + e.Jl[1] * e.Jt[6 + k];
+                if (rf)
+                    for (int k = 0; k < 6; ++k) atomicAdd(&P.W[(size_t)(rs * 6 + k) * M + lm], e.Jl[0] * e.Jr[k] + e.Jl[1] * e.Jr[6 + k]);
+            }
+        }
+    }
+    // ---------------- rotation priors (Cauchy loss), rare ----------------
+    for (int o = tid; o < P.d.n_rot; o += ST) {
+        const RotObs ob = P.rot[P.d.rot_off + o];
+        const int ts = ob.tgt;
+        double r[2], Jq[6];
+        rot_eval(ld4(S + ts * 16), ld4(s.us + ob.ref * 16), ld3(ob.zt), ld3(ob.zr), rg, want_jac, r, Jq);
+        const double sq = r[0] * r[0] + r[1] * r[1];
+        cost += 0.5 * log(1.0 + sq);
+        if (want_jac && ts < P.d.n_active && s.pose_free[ts]) {
+            const double w = sqrt(1.0 / (1.0 + sq));
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j <= i; ++j)
+                    atomicAdd(&s.H[hidx(15 * ts + i, 15 * ts + j)], w * w * (Jq[i] * Jq[j] + Jq[3 + i] * Jq[3 + j]));
+                atomicAdd(&s.g[15 * ts + i], w * w * (Jq[i] * r[0] + Jq[3 + i] * r[1]));
+            }
+        }
+    }
+    // ---------------- preintegration factors (no loss), one warp per factor ----------------
+    for (int f = warp; f < P.d.n_pre; f += NW) {
+        const PreRef pf = P.pre[P.d.pre_off + f];
+        const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
+        double *sc = P.pre_s + (size_t)f * kPreScratch;     // [0,15) r  [16,241) Ji  [241,466) Jj  [466,691) Jwi [691,916) Jwj [916,931) rw
+        const double *si = pf.prior ? (s.us + pf.i * 16) : (S + pf.i * 16);
+        const double *sj = S + pf.j * 16;
+        if (lane == 0) pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, want_jac, sc, sc + 16, sc + 241);
+        __syncwarp();
+        const double *Sic = pb + PB_SIC;
+        if (lane < 15) {
+            double a = 0.0;
+            for (int k = 0; k < 15; ++k) a += Sic[lane * 15 + k] * sc[k];
+            sc[916 + lane] = a;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double a = 0.0;
+            for (int k = 0; k < 15; ++k) a += sc[916 + k] * sc[916 + k];
+            cost += 0.5 * a;
+        }
+        if (!want_jac) continue;
+        for (int e = lane; e < 450; e += 32) {              // whiten: Jw = sqrt_inv_cov * J
+            const int which = e / 225, idx = e % 225, r = idx / 15, c = idx % 15;
+            const double *J = sc + (which ? 241 : 16);
+            double a = 0.0;
+            for (int k = 0; k < 15; ++k) a += Sic[r * 15 + k] * J[k * 15 + c];
+            sc[(which ? 691 : 466) + idx] = a;
+        }
+        __syncwarp();
+        const double *Jwi = sc + 466, *Jwj = sc + 691, *rw = sc + 916;
+        const bool has_i = !pf.prior && pf.i < P.d.n_active;
+        const bool has_j = pf.j < P.d.n_active;
+        const int ci = 15 * pf.i, cj = 15 * pf.j;
+        // (i,i) and (j,j) lower triangles, cross block, gradients
+        for (int e = lane; e < 120 + 120 + 225 + 30; e += 32) {
+            if (e < 240) {
+                const bool isj = e >= 120;
+                if (isj ? !has_j : !has_i) continue;
+                int t = isj ? e - 120 : e;
+                int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while (r * (r + 1) / 2 > t) --r;
+                while ((r + 1) * (r + 2) / 2 <= t) ++r;
+                int c = t - r * (r + 1) / 2;
+                const double *J = isj ? Jwj : Jwi;
+                const int c0 = isj ? cj : ci;
+                if (!s.col_free[c0 + r] || !s.col_free[c0 + c]) continue;
+                double a = 0.0;
+                for (int k = 0; k < 15; ++k) a += J[k * 15 + r] * J[k * 15 + c];
+                atomicAdd(&s.H[hidx(c0 + r, c0 + c)], a);
+            } else if (e < 465) {
+                if (!has_i || !has_j) continue;
+                int t = e - 240, r = t / 15, c = t % 15;     // r: column of Jwi, c: column of Jwj
+                if (!s.col_free[ci + r] || !s.col_free[cj + c]) continue;
+                double a = 0.0;
+                for (int k = 0; k < 15; ++k) a += Jwi[k * 15 + r] * Jwj[k * 15 + c];
+                const int A = ci + r, B = cj + c;
+                atomicAdd(&s.H[A > B ? hidx(A, B) : hidx(B, A)], a);
+            } else {
+                int t = e - 465;
+                const bool isj = t >= 15;
+                if (isj ? !has_j : !has_i) continue;
+                int c = isj ? t - 15 : t;
+                const double *J = isj ? Jwj : Jwi;
+                const int c0 = isj ? cj : ci;
+                if (!s.col_free[c0 + c]) continue;
+                double a = 0.0;
+                for (int k = 0; k < 15; ++k) a += J[k * 15 + c] * rw[k];
+                atomicAdd(&s.g[c0 + c], a);
+            }
+        }
+    }
+    __syncthreads();
+    // ---------------- marginalisation prior (no loss) ----------------
+    if (P.d.marg_k > 0) {
+        const int K = P.d.marg_k, n = P.marg_n;
+        if (tid < K) {
+            const int f = P.marg_frames[P.d.marg_frames_off + tid];
+            M3 Jri;
+            marg_dx(S + f * 16, P.marg_lin + tid * 16, P.m_dx + 15 * tid, want_jac ? &Jri : nullptr);
+            if (want_jac)
+                for (int k = 0; k < 9; ++k) s.jrinv[tid * 9 + k] = Jri.m[k];
+        }
+        __syncthreads();
+        for (int r = warp; r < n; r += NW) {               // r = S dx + infovec, one warp per row
+            double a = 0.0;
+            for (int c = lane; c < n; c += 32) a += P.marg_S[(size_t)r * n + c] * P.m_dx[c];
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) { a += P.marg_info[r]; P.m_r[r] = a; cost += 0.5 * a * a; }
+        }
+        if (want_jac) {
+            __syncthreads();
+            for (int c = tid; c < n; c += ST) {            // v = S^T r
+                double a = 0.0;
+                for (int r = 0; r < n; ++r) a += P.marg_S[(size_t)r * n + c] * P.m_r[r];
+                P.m_v[c] = a;
+            }
+            // T = A0 * B  (B = blockdiag(Jr^-1 on q blocks, I))
+            for (int e = tid; e < n * K * 5; e += ST) {
+                const int r = e / (K * 5), cb = e % (K * 5);       // 3-column block cb
+                const int k = cb / 5, sub = cb % 5;
+                const double *a0 = P.marg_A0 + (size_t)r * n + 15 * k + 3 * sub;
+                double *t = P.m_T + (size_t)r * n + 15 * k + 3 * sub;
+                if (sub == 0) {
+                    const double *Jr = s.jrinv + 9 * k;
+                    for (int c = 0; c < 3; ++c) t[c] = a0[0] * Jr[0 * 3 + c] + a0[1] * Jr[1 * 3 + c] + a0[2] * Jr[2 * 3 + c];
+                } else { t[0] = a0[0]; t[1] = a0[1]; t[2] = a0[2]; }
+            }
+            __syncthreads();
+            // H += B^T T (lower triangle), g += B^T v ; one thread per entry, no atomics needed now
+            for (int e = tid; e < n * (n + 1) / 2; e += ST) {
+                int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                while (i * (i + 1) / 2 > e) --i;
+                while ((i + 1) * (i + 2) / 2 <= e) ++i;
+                const int j = e - i * (i + 1) / 2;
+                const int ki = i / 15, oi = i % 15;
+                double a;
+                if (oi < 3) {
+                    const double *Jr = s.jrinv + 9 * ki;
+                    a = Jr[0 * 3 + oi] * P.m_T[(size_t)(15 * ki + 0) * n + j] + Jr[1 * 3 + oi] * P.m_T[(size_t)(15 * ki + 1) * n + j] +
+                        Jr[2 * 3 + oi] * P.m_T[(size_t)(15 * ki + 2) * n + j];
+                } else a = P.m_T[(size_t)i * n + j];
+                const int fi = P.marg_frames[P.d.marg_frames_off + ki], fj = P.marg_frames[P.d.marg_frames_off + j / 15];
+                if (fi >= P.d.n_active || fj >= P.d.n_active) continue;
+                const int A = 15 * fi + oi, B = 15 * fj + j % 15;
+                if (!s.col_free[A] || !s.col_free[B]) continue;
+                s.H[A >= B ? hidx(A, B) : hidx(B, A)] += a;     // distinct (i,j) map to distinct (A,B)
+            }
+            for (int c = tid; c < n; c += ST) {
+                const int k = c / 15, oc = c % 15;
+                double a;
+                if (oc < 3) {
+                    const double *Jr = s.jrinv + 9 * k;
+                    a = Jr[0 * 3 + oc] * P.m_v[15 * k] + Jr[1 * 3 + oc] * P.m_v[15 * k + 1] + Jr[2 * 3 + oc] * P.m_v[15 * k + 2];
+                } else a = P.m_v[c];
+                const int f = P.marg_frames[P.d.marg_frames_off + k];
+                if (f < P.d.n_active && s.col_free[15 * f + oc]) s.g[15 * f + oc] += a;
+            }
+        }
+    }
+    cost = block_sum(cost, s);
+    if (want_jac) {
+        // constant columns: unit diagonal, zero gradient (their off-diagonals were never accumulated)
+        for (int c = tid; c < P.NPc; c += ST)
+            if (!s.col_free[c]) { s.H[hidx(c, c)] = 1.0; s.g[c] = 0.0; }
+        __syncthreads();
+    }
+    return cost;
+}
+
+
+// Eliminate the (scalar) inverse-depth blocks: H_pp -= sum_l w_l w_l^T / ht_l and
+// rhs_p -= sum_l w_l g_l / ht_l, with ht_l = P.ht_l (landmarks with a non-finite 1/ht_l are skipped,
+// marginalization_factor.h:384-386).  One warp per pair of frame slots, lanes over landmarks.
+static __device__ void schur_landmarks(const Prob &P, Smem &s, double *rhs) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = P.M, na = P.d.n_active;
+    (void)tid;
+    if (M > 0) {
+        // S -= sum_l w_l w_l^T / ht_l ; one warp per pair of frame slots, lanes over landmarks
+        const int npairs = na * (na + 1) / 2;
+        for (int pr = warp; pr < npairs; pr += NW) {
+            int a = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+            while (a * (a + 1) / 2 > pr) --a;
+            while ((a + 1) * (a + 2) / 2 <= pr) ++a;
+            const int b = pr - a * (a + 1) / 2;        // a >= b
+            if (!s.pose_free[a] || !s.pose_free[b]) continue;
+            double acc[36];
+#pragma unroll
+            for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+            for (int l = lane; l < M; l += 32) {
+                double ih = 1.0 / P.ht_l[l];
+                if (!isfinite(ih)) ih = 0.0;
+                double wa[6], wb[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { wa[k] = P.W[(size_t)(a * 6 + k) * M + l]; wb[k] = P.W[(size_t)(b * 6 + k) * M + l] * ih; }
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) acc[i * 6 + j] += wa[i] * wb[j];
+            }
+#pragma unroll
+            for (int k = 0; k < 36; ++k) {
+                double v = acc[k];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                acc[k] = v;
+            }
+            if (lane == 0) {
+                for (int i = 0; i < 6; ++i)
+                    for (int j = 0; j < 6; ++j) {
+                        if (a == b && j > i) continue;
+                        s.H[hidx(15 * a + i, 15 * b + j)] -= acc[i * 6 + j];
+                    }
+            }
+        }
+        // b_red = gs_p - sum_l w_l gs_l / ht_l
+        for (int c = warp; c < na * 6; c += NW) {
+            const int a = c / 6, k = c % 6;
+            if (!s.pose_free[a]) continue;
+            double v = 0.0;
+            for (int l = lane; l < M; l += 32) { double ih = 1.0 / P.ht_l[l]; if (!isfinite(ih)) ih = 0.0; v += P.W[(size_t)c * M + l] * P.g_l[l] * ih; }
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) rhs[15 * a + k] -= v;
+        }
+    }
+}
+
+}  // namespace xvbe
