@@ -139,7 +139,8 @@ static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const
         // --- (tgt,tgt) block + g_tgt : segments keyed by tgt ---
         {
             const int key = (valid && tf) ? ts : -1 - lane;
-            const bool head = (lane == 0) || (__shfl_up_sync(0xffffffffu, key, 1) != key);
+            const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);   // unconditional: every lane must take part
+            const bool head = (lane == 0) || (key_prev != key);
             const bool act = valid && tf;
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
@@ -158,7 +159,8 @@ static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const
         const unsigned any_full = __ballot_sync(0xffffffffu, valid && !prior);
         if (any_full) {
             const int key = (valid && !prior) ? ((ts << 8) | rs) : -1 - lane;
-            const bool head = (lane == 0) || (__shfl_up_sync(0xffffffffu, key, 1) != key);
+            const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);   // unconditional: every lane must take part
+            const bool head = (lane == 0) || (key_prev != key);
             const bool act_tr = valid && tf && rf, act_rr = valid && rf;
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
