@@ -43,7 +43,7 @@ extern "C" {
 #define XRVIO_MAX_CORNERS 256     /* slots per image in xrvio_op_gftt output   */
 #define XRVIO_MAX_PTS 512         /* keypoint slots per image (klt / poisson)  */
 #define XRVIO_PRE_BLOCK 512       /* doubles per preintegration result         */
-#define XRVIO_MAX_ACTIVE 11       /* free frames per solve                     */
+#define XRVIO_MAX_ACTIVE 12       /* free frames per solve                     */
 #define XRVIO_MAX_FRAMES 96       /* frames referenced by one solve            */
 #define XRVIO_MAX_ITER 64
 
@@ -147,6 +147,66 @@ int xrvio_op_marginalize(const xrvio_rig *rig, xrvio_marg_desc *desc, int n_prob
                          const int *marg_frames, int n_marg_frames, const double *marg, long long n_marg_doubles,
                          double *out, long long n_out_doubles, int *rank_out);
 int xrvio_op_triangulate(const xrvio_tri_job *jobs, int n_jobs, const double *views, int n_views, double *out_xyz_valid);
+
+/* ------------------------------------------------------------------------------------------------
+ * Session level: n_sessions independent VIO sessions advanced together on one GPU.
+ * Mirrors, per session, XRSLAM::Detail (xrslam/src/xrslam/core/detail.h:33-45):
+ *   xrvio_push_imu     <-> track_imu after gyro/accelerometer interpolation (detail.cpp:130-142)
+ *   xrvio_push_images  <-> track_camera (detail.cpp:103-128): queues the frame, returns nothing; the
+ *                          IMU-propagated output pose for that image is read with xrvio_get_pose
+ *   xrvio_step         <-> the Worker loops FeatureTracker::work + FrontendWorker::work for every frame
+ *                          released by a later IMU sample (feature_tracker.cpp:24-153,
+ *                          frontend_worker.cpp:28-86), batched over sessions
+ *   xrvio_get_state    <-> get_system_state (frontend_worker.cpp:120-127)
+ * The reference's Initializer (SfM + IMU alignment) is not part of this hot path:
+ * a session leaves INITIALIZING through xrvio_push_bootstrap_state (poses/velocities of the frames,
+ * e.g. ground truth) followed by the reference's own mirror_keyframe_map + final visual-inertial BA.
+ */
+typedef struct xrvio_ctx xrvio_ctx;
+
+typedef struct xrvio_params {
+    int width, height;
+    double fx, fy, cx, cy;
+    double q_bc[4], p_bc[3], q_bi[4], p_bi[3], q_bo[4], p_bo[3];
+    double cov_g[9], cov_a[9], cov_bg[9], cov_ba[9];
+    double keypoint_cov[2];
+    int sliding_window_size, subframe_size, force_keyframe_landmarks;
+    double min_keypoint_distance;
+    int max_keypoint_detection, max_init_frames, max_frames, predict_keypoints;
+    double clahe_clip_limit;
+    int clahe_width, clahe_height;
+    int init_keyframe_num, init_keyframe_gap;
+    int solver_iteration_limit;
+    double rotation_misalignment_threshold, rotation_ransac_threshold;
+} xrvio_params;
+
+typedef struct xrvio_imu { double t, w[3], a[3]; } xrvio_imu;
+typedef struct xrvio_pose { double q[4], p[3], t; int valid; int pad; } xrvio_pose;   /* q xyzw, like XRSLAMPose */
+typedef struct xrvio_stats {
+    long long frames_processed;         /* frames through the front end over all sessions */
+    long long kernels_launched;         /* CUDA kernel launches issued by the library */
+    long long h2d_bytes, d2h_bytes;
+    long long window_solves, localize_solves, subwindow_solves, marginalizations;
+    double last_window_cost_initial, last_window_cost_final;
+} xrvio_stats;
+
+#define XRVIO_STATE_INITIALIZING 0   /* SysState::SYS_INITIALIZING */
+#define XRVIO_STATE_TRACKING 1       /* SysState::SYS_TRACKING */
+
+int xrvio_default_params(xrvio_params *p, int width, int height);   /* configs/euroc_slam.yaml + euroc_sensor.yaml */
+int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **ctx);
+int xrvio_destroy(xrvio_ctx *ctx);
+int xrvio_push_imu(xrvio_ctx *ctx, const int *session, const xrvio_imu *samples, int n);
+int xrvio_push_bootstrap_state(xrvio_ctx *ctx, int session, double t, const double q[4], const double p[3], const double v[3]);
+/* data[i]: pointer to a height*stride[i] 8-bit image; on_device != 0: device pointers */
+int xrvio_push_images(xrvio_ctx *ctx, const int *session, const uint8_t *const *data, const int *stride, const double *t,
+                      int n, int on_device);
+int xrvio_step(xrvio_ctx *ctx);
+int xrvio_get_pose(xrvio_ctx *ctx, int session, xrvio_pose *pose);          /* output pose of the latest pushed image */
+int xrvio_get_latest_state(xrvio_ctx *ctx, int session, double *t, double state16[16]);   /* last optimised frame */
+int xrvio_get_state(xrvio_ctx *ctx, int session);                           /* XRVIO_STATE_* or < 0 */
+int xrvio_get_landmarks(xrvio_ctx *ctx, int session, double *xyz, int capacity);   /* returns count */
+int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *stats);
 
 #ifdef __cplusplus
 }

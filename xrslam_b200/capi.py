@@ -6,7 +6,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libxrvio.so")
 
-MAX_CORNERS, MAX_PTS, PRE_BLOCK, MAX_ACTIVE, MAX_FRAMES, MAX_ITER = 256, 512, 512, 11, 96, 64
+MAX_CORNERS, MAX_PTS, PRE_BLOCK, MAX_ACTIVE, MAX_FRAMES, MAX_ITER = 256, 512, 512, 12, 96, 64
 
 
 class XrvioError(RuntimeError):
@@ -179,3 +179,95 @@ def op_triangulate(jobs, views):
     out = np.zeros((len(jobs), 4), np.float64)
     lib.check(lib.xrvio_op_triangulate(_p(jobs), len(jobs), _p(views), len(views), _p(out)))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# session level
+# ------------------------------------------------------------------------------------------------
+params_dtype = np.dtype([("width", "i4"), ("height", "i4"), ("fx", "f8"), ("fy", "f8"), ("cx", "f8"), ("cy", "f8"),
+                         ("q_bc", "f8", 4), ("p_bc", "f8", 3), ("q_bi", "f8", 4), ("p_bi", "f8", 3), ("q_bo", "f8", 4), ("p_bo", "f8", 3),
+                         ("cov_g", "f8", 9), ("cov_a", "f8", 9), ("cov_bg", "f8", 9), ("cov_ba", "f8", 9), ("keypoint_cov", "f8", 2),
+                         ("sliding_window_size", "i4"), ("subframe_size", "i4"), ("force_keyframe_landmarks", "i4"),
+                         ("min_keypoint_distance", "f8"), ("max_keypoint_detection", "i4"), ("max_init_frames", "i4"),
+                         ("max_frames", "i4"), ("predict_keypoints", "i4"), ("clahe_clip_limit", "f8"), ("clahe_width", "i4"),
+                         ("clahe_height", "i4"), ("init_keyframe_num", "i4"), ("init_keyframe_gap", "i4"),
+                         ("solver_iteration_limit", "i4"), ("rotation_misalignment_threshold", "f8"),
+                         ("rotation_ransac_threshold", "f8")], align=True)
+imu_dtype = np.dtype([("t", "f8"), ("w", "f8", 3), ("a", "f8", 3)], align=True)
+pose_dtype = np.dtype([("q", "f8", 4), ("p", "f8", 3), ("t", "f8"), ("valid", "i4"), ("pad", "i4")], align=True)
+stats_dtype = np.dtype([("frames_processed", "i8"), ("kernels_launched", "i8"), ("h2d_bytes", "i8"), ("d2h_bytes", "i8"),
+                        ("window_solves", "i8"), ("localize_solves", "i8"), ("subwindow_solves", "i8"), ("marginalizations", "i8"),
+                        ("last_window_cost_initial", "f8"), ("last_window_cost_final", "f8")], align=True)
+
+
+def default_params(width=640, height=480):
+    p = np.zeros(1, params_dtype)
+    lib.check(lib.xrvio_default_params(_p(p), width, height))
+    return p
+
+
+class Context:
+    """n_sessions VIO sessions on one GPU (xrvio_create ... xrvio_destroy)."""
+
+    def __init__(self, params, n_sessions, device=0):
+        self.params = params
+        self.n = n_sessions
+        self._h = C.c_void_p()
+        lib.check(lib.xrvio_create(_p(params), n_sessions, device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.xrvio_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push_imu(self, sessions, samples):
+        sessions = np.ascontiguousarray(sessions, np.int32)
+        samples = np.ascontiguousarray(samples)
+        assert samples.dtype == imu_dtype and len(samples) == len(sessions)
+        lib.check(lib.xrvio_push_imu(self._h, _p(sessions), _p(samples), len(sessions)))
+
+    def push_bootstrap_state(self, session, t, q, p, v):
+        q, p, v = (np.ascontiguousarray(x, np.float64) for x in (q, p, v))
+        lib.check(lib.xrvio_push_bootstrap_state(self._h, int(session), C.c_double(t), _p(q), _p(p), _p(v)))
+
+    def push_images(self, sessions, pointers, times, stride=None, on_device=False):
+        """pointers: integer addresses (host numpy .ctypes.data or device data_ptr) of 8-bit images."""
+        n = len(sessions)
+        sessions = np.ascontiguousarray(sessions, np.int32)
+        ptrs = (C.c_void_p * n)(*[int(x) for x in pointers])
+        times = np.ascontiguousarray(times, np.float64)
+        st = None if stride is None else np.ascontiguousarray(stride, np.int32)
+        lib.check(lib.xrvio_push_images(self._h, _p(sessions), ptrs, _p(st), _p(times), n, 1 if on_device else 0))
+
+    def step(self):
+        lib.check(lib.xrvio_step(self._h))
+
+    def get_pose(self, session):
+        p = np.zeros(1, pose_dtype)
+        lib.check(lib.xrvio_get_pose(self._h, int(session), _p(p)))
+        return p[0]
+
+    def get_latest_state(self, session):
+        t = C.c_double()
+        s = np.zeros(16)
+        rc = lib.xrvio_get_latest_state(self._h, int(session), C.byref(t), _p(s))
+        return (t.value, s) if rc == 0 else None
+
+    def get_state(self, session):
+        return lib.xrvio_get_state(self._h, int(session))
+
+    def get_landmarks(self, session, capacity=4096):
+        xyz = np.zeros((capacity, 3))
+        n = lib.xrvio_get_landmarks(self._h, int(session), _p(xyz), capacity)
+        return xyz[:min(n, capacity)]
+
+    def stats(self):
+        s = np.zeros(1, stats_dtype)
+        lib.check(lib.xrvio_get_stats(self._h, _p(s)))
+        return s[0]

@@ -9,8 +9,8 @@
 
 namespace xvbe {
 
-constexpr int kMaxActive = 11;              // free frames per solve (window 10 + the new keyframe)
-constexpr int kNP = 15 * kMaxActive;        // 165 pose/motion columns
+constexpr int kMaxActive = 12;              // free frames per solve (window 10 + the new keyframe)
+constexpr int kNP = 15 * kMaxActive;        // 180 pose/motion columns
 constexpr int kMaxFrames = 96;              // frames referenced by one problem (active + constant refs)
 constexpr int kMaxIter = 64;
 

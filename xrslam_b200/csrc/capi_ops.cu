@@ -61,7 +61,7 @@ int xrvio_op_clahe(const uint8_t *src, uint8_t *dst, int n, int w, int h, double
     DevBuf d_src, d_dst, d_lut;
     CK(d_src.alloc(bytes)); CK(d_dst.alloc(bytes)); CK(d_lut.alloc((size_t)n * tiles_x * tiles_y * 256));
     CK(cudaMemcpy(d_src.p, src, bytes, cudaMemcpyHostToDevice));
-    xvfe::clahe(d_src.as<uint8_t>(), d_dst.as<uint8_t>(), d_lut.as<uint8_t>(), n, w, h, clip_limit, tiles_x, tiles_y, 0);
+    xvfe::clahe(d_src.as<uint8_t>(), nullptr, (size_t)w * h, d_dst.as<uint8_t>(), nullptr, (size_t)w * h, d_lut.as<uint8_t>(), n, w, h, clip_limit, tiles_x, tiles_y, 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(dst, d_dst.p, bytes, cudaMemcpyDeviceToHost));
     return XRVIO_OK;
@@ -74,7 +74,7 @@ int xrvio_op_pyramid(const uint8_t *level0, int n, int w, int h, uint8_t *pyr, i
     CK(d_pyr.alloc((size_t)n * L.total));
     for (int i = 0; i < n; ++i)
         CK(cudaMemcpy(d_pyr.as<uint8_t>() + (size_t)i * L.total, level0 + (size_t)i * w * h, (size_t)w * h, cudaMemcpyHostToDevice));
-    xvfe::pyramid(d_pyr.as<uint8_t>(), n, L, 0);
+    xvfe::pyramid(d_pyr.as<uint8_t>(), nullptr, n, L, 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(pyr, d_pyr.p, (size_t)n * L.total, cudaMemcpyDeviceToHost));
     if (deriv) {
@@ -99,7 +99,7 @@ int xrvio_op_gftt(const uint8_t *img, int n, int w, int h, int max_corners, doub
     CK(d_cand.alloc((size_t)n * xvfe::kMaxCand * 8)); CK(d_cc.alloc(n * sizeof(int))); CK(d_max.alloc(n * sizeof(unsigned)));
     CK(cudaMemcpy(d_img.p, img, bytes, cudaMemcpyHostToDevice));
     CK(cudaMemset(d_cor.p, 0, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float)));
-    xvfe::gftt_harris(d_img.as<uint8_t>(), (size_t)w * h, n, w, h, max_corners, (float)quality, (float)min_distance,
+    xvfe::gftt_harris(d_img.as<uint8_t>(), nullptr, (size_t)w * h, n, w, h, max_corners, (float)quality, (float)min_distance,
                       d_cor.as<float>(), d_cnt.as<int>(), d_cand.as<unsigned long long>(), d_cc.as<int>(), d_max.as<unsigned>(), 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(corners, d_cor.p, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost));
@@ -121,13 +121,13 @@ int xrvio_op_klt(const uint8_t *prev_img, const uint8_t *next_img, int n, int w,
         CK(cudaMemcpy(d_p.as<uint8_t>() + (size_t)i * L.total, prev_img + (size_t)i * w * h, (size_t)w * h, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_n.as<uint8_t>() + (size_t)i * L.total, next_img + (size_t)i * w * h, (size_t)w * h, cudaMemcpyHostToDevice));
     }
-    xvfe::pyramid(d_p.as<uint8_t>(), n, L, 0);
-    xvfe::pyramid(d_n.as<uint8_t>(), n, L, 0);
+    xvfe::pyramid(d_p.as<uint8_t>(), nullptr, n, L, 0);
+    xvfe::pyramid(d_n.as<uint8_t>(), nullptr, n, L, 0);
     CK(cudaMemcpy(d_pp.p, prev_pts, pb, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_np.p, next_pts, pb, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_cnt.p, npts, n * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemset(d_st.p, 0, (size_t)n * xvfe::kMaxPts));
-    xvfe::klt_track(d_p.as<uint8_t>(), d_n.as<uint8_t>(), n, L, d_pp.as<float>(), d_np.as<float>(), d_cnt.as<int>(), d_st.as<uint8_t>(), 0);
+    xvfe::klt_track(d_p.as<uint8_t>(), d_n.as<uint8_t>(), nullptr, nullptr, n, L, d_pp.as<float>(), d_np.as<float>(), d_cnt.as<int>(), d_st.as<uint8_t>(), 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(next_pts, d_np.p, pb, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(status, d_st.p, (size_t)n * xvfe::kMaxPts, cudaMemcpyDeviceToHost));

@@ -1,0 +1,536 @@
+// Session layer of the C ABI (include/xrvio.h, layer 2): n_sessions independent VIO sessions are
+// advanced together.  The per-session control flow restates, in batched phases,
+//   XRSLAM::Detail::track_imu / track_camera / predict_pose        core/detail.cpp:15-28,103-177
+//   FeatureTracker::work                                            core/feature_tracker.cpp:24-153
+//   Frame::track_keypoints / detect_keypoints                       map/frame.cpp:55-174
+//   FrontendWorker::work                                            core/frontend_worker.cpp:28-86
+//   SlidingWindowTracker::{mirror_frame,track,localize_newframe,manage_keyframe,track_landmark,
+//                          refine_window,slide_window,refine_subwindow}   core/sliding_window_tracker.cpp:31-465
+//   Initializer::mirror_keyframe_map + final BA                    core/initializer.cpp:22-76,88-155
+// Every numeric operator is a CUDA kernel launch on the context's stream (frontend.cuh,
+// backend.cuh); the host only does bookkeeping between launches.  No CPU fallback exists.
+#include "../../include/xrvio.h"
+#include "backend.cuh"
+#include "frontend.cuh"
+#include "session_host.hpp"
+#include <map>
+#include <string>
+#include <unordered_set>
+
+void xrvio_set_error(const std::string &e);
+
+using namespace xvs;
+
+#define CKC(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            xrvio_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+            return XRVIO_ERR_CUDA;                                                                    \
+        }                                                                                             \
+    } while (0)
+
+namespace {
+
+// pinned host + device pair that grows on demand
+template <class T> struct Arena {
+    T *h = nullptr, *d = nullptr;
+    size_t cap = 0, n = 0;
+    ~Arena() { if (h) cudaFreeHost(h); if (d) cudaFree(d); }
+    cudaError_t reserve(size_t want) {
+        if (want <= cap) return cudaSuccess;
+        size_t nc = std::max(want, cap * 2 + 64);
+        T *nh = nullptr, *nd = nullptr;
+        cudaError_t e = cudaHostAlloc((void **)&nh, nc * sizeof(T), cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc((void **)&nd, nc * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (h) { std::memcpy(nh, h, n * sizeof(T)); cudaFreeHost(h); }
+        if (d) cudaFree(d);           // device contents are transient per phase
+        h = nh; d = nd; cap = nc;
+        return cudaSuccess;
+    }
+    void clear() { n = 0; }
+    size_t push(const T &v) { h[n] = v; return n++; }
+};
+
+struct DevOnly {
+    void *p = nullptr; size_t bytes = 0;
+    ~DevOnly() { if (p) cudaFree(p); }
+    cudaError_t reserve(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        bytes = want + want / 4 + 4096;
+        return cudaMalloc(&p, bytes);
+    }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+constexpr int kImgQueue = 4;       // frames per session that may wait on the device between steps
+constexpr int kPyrSlots = 3;       // pyramid buffers per session (previous, next, spare)
+
+struct Session {
+    int idx = 0;
+    Map ft_map;                                   // FeatureTracker::map
+    std::unique_ptr<Map> sw_map;                  // SlidingWindowTracker::map (null while INITIALIZING)
+    std::deque<std::unique_ptr<Frame>> queued;    // Detail::frames (waiting for IMU)
+    std::deque<std::unique_ptr<Frame>> released;  // handed to FeatureTracker::track_frame
+    std::deque<Imu> imus, frontal_imus;
+    long long frame_id_counter = 0, track_id_counter = 0;
+    // FeatureTracker::latest_state / FrontendWorker::latest_state
+    bool has_latest = false; double latest_t = 0; State16 latest;
+    bool has_swt_latest = false; double swt_t = 0; long long swt_frame_id = -1; State16 swt_state;
+    xrvio_pose out_pose{};
+    double out_t = 0;
+    std::map<long long, State16> bootstrap;       // keyed by round(t * 1e6)
+    int img_slot_next = 0;
+    int pyr_next = 0;
+    // per-round scratch
+    std::unique_ptr<Frame> cur;                   // frame being processed by the front end
+    Frame *last = nullptr;
+    bool fe_has_last = false;
+    int pre_job = -1;
+    std::vector<double> klt_next;                 // px of tracked points (f64), status
+    std::vector<unsigned char> klt_status;
+    std::vector<std::pair<int, int>> order;       // (keypoint index, track length) sorted
+    std::vector<V3> next_bearings;
+    int n_corners = 0;
+    // back end round
+    int be_mode = 0;                              // 0 none, 1 bootstrap, 2 track
+    bool is_keyframe = false;
+    Frame *new_i = nullptr, *new_j = nullptr;
+    int prob1 = -1, prob2 = -1, marg_job = -1;
+    std::vector<Frame *> prob_frames;             // frame order of the last built problem
+    std::vector<Track *> prob_tracks;
+    std::vector<Track *> tri_tracks; int tri_off = 0;
+    std::vector<int> pre_jobs;                    // preintegration job ids launched for this session
+    std::vector<Frame *> pre_job_frames; std::vector<int> pre_job_kind;
+};
+
+}  // namespace
+
+struct xrvio_ctx {
+    xrvio_params prm;
+    int S = 0, device = 0;
+    cudaStream_t st = nullptr;
+    xvfe::PyrLayout L;
+    xvbe::RigParams rig_h;
+    xvbe::RigParams *rig_d = nullptr;
+    Rig rig;
+    double K[4];
+    double sic[2];
+    std::vector<Session> ses;
+    xrvio_stats stats{};
+    // ---- device image / front-end buffers ----
+    uint8_t *d_raw = nullptr;          // S * kImgQueue * w*h
+    uint8_t *d_stage = nullptr;        // S * w*h  contiguous batch for CLAHE input
+    uint8_t *d_pyr = nullptr;          // S * kPyrSlots * L.total
+    uint8_t *d_pyr_prev_batch = nullptr, *d_pyr_next_batch = nullptr;   // S * L.total contiguous batches for KLT
+    uint8_t *d_lut = nullptr;
+    unsigned long long *d_cand = nullptr; int *d_cand_count = nullptr; unsigned *d_maxval = nullptr;
+    Arena<float> corners; Arena<int> corner_count;
+    Arena<float> klt_prev, klt_next; Arena<int> klt_n; Arena<unsigned char> klt_status;
+    Arena<double> poi_pts; Arena<int> poi_npre, poi_ntot; Arena<unsigned char> poi_veto, poi_keep;
+    // ---- back-end arenas ----
+    Arena<xvbe::PreintJob> pre_jobs; Arena<double> imu; Arena<double> pre_out;
+    Arena<xvbe::SolveDesc> sdesc; Arena<double> states; Arena<unsigned char> fflags; Arena<double> invd;
+    Arena<xvbe::RpeObs> rpe; Arena<xvbe::RotObs> rot; Arena<xvbe::PreRef> pref; Arena<double> pblocks;
+    Arena<int> mframes; Arena<xvbe::SolveOut> sout;
+    Arena<xvbe::MargDesc> mdesc; Arena<int> mrank;
+    Arena<xvbe::TriJob> tjobs; Arena<double> tviews; Arena<double> tout;
+    DevOnly scratch;
+    double *d_prior = nullptr;         // S * 2 * prior_stride doubles, device-resident priors
+    size_t prior_stride = 0;
+    std::vector<double> prior_init_h;
+};
+
+namespace {
+
+inline long long tkey(double t) { return (long long)std::llround(t * 1e6); }
+
+// ---------------------------------------------------------------------------------------------
+// Detail::predict_pose + propagate_state (detail.cpp:15-28,144-177)
+// ---------------------------------------------------------------------------------------------
+void predict_pose(xrvio_ctx *c, Session &s, double t, xrvio_pose &out) {
+    out.valid = 0; out.t = t;
+    for (int k = 0; k < 4; ++k) out.q[k] = 0;
+    for (int k = 0; k < 3; ++k) out.p[k] = 0;
+    if (!s.has_latest) return;
+    double st = s.latest_t;
+    Q4 q = s.latest.q(); V3 p = s.latest.p(), v = s.latest.v();
+    const V3 bg = s.latest.bg(), ba = s.latest.ba();
+    const V3 g = v3(0, 0, -9.80665);
+    while (!s.frontal_imus.empty() && s.frontal_imus.front().t <= st) s.frontal_imus.pop_front();
+    for (const Imu &m : s.frontal_imus) {
+        if (m.t <= t) {
+            const double dt = m.t - st;
+            const V3 acc = g + qrot(q, m.a - ba);
+            p = p + dt * v + (0.5 * dt * dt) * acc;
+            v = v + dt * acc;
+            q = qnormalized(qmul(q, expmap(dt * (m.w - bg))));
+            st = m.t;
+        }
+    }
+    const Q4 qo = qmul(q, ld4(c->prm.q_bo));
+    const V3 po = p + qrot(q, ld3(c->prm.p_bo));
+    st4(out.q, qo); st3(out.p, po);
+    out.valid = 1;
+}
+
+// PreIntegrator::predict (preintegrator.cpp:102-112)
+void pre_predict(const std::vector<double> &pb, const State16 &a, State16 &b) {
+    const V3 g = v3(0, 0, -9.80665);
+    const double dt = pb[xvbe::PB_T];
+    const Q4 dq = ld4(&pb[xvbe::PB_Q]);
+    const V3 dp = ld3(&pb[xvbe::PB_P]), dv = ld3(&pb[xvbe::PB_V]);
+    const V3 v = a.v() + dt * g + qrot(a.q(), dv);
+    const V3 p = a.p() + (0.5 * dt * dt) * g + dt * a.v() + qrot(a.q(), dp);
+    const Q4 q = qmul(a.q(), dq);
+    st4(b.d, q); st3(b.d + 4, p); st3(b.d + 7, v);
+    for (int k = 0; k < 6; ++k) b.d[10 + k] = a.d[10 + k];
+}
+
+int add_preint_job(xrvio_ctx *c, const std::vector<Imu> &data, double t_end, const State16 &bias_from, int flags) {
+    if (c->pre_jobs.reserve(c->pre_jobs.n + 1) != cudaSuccess) return -1;
+    if (c->imu.reserve(c->imu.n + data.size() * 7 + 7) != cudaSuccess) return -1;
+    xvbe::PreintJob j{};
+    j.imu_off = (int)(c->imu.n / 7); j.n = (int)data.size(); j.flags = flags; j.t_end = t_end;
+    for (int k = 0; k < 3; ++k) { j.bg[k] = bias_from.d[10 + k]; j.ba[k] = bias_from.d[13 + k]; }
+    for (const Imu &m : data) {
+        double *o = c->imu.h + c->imu.n;
+        o[0] = m.t; o[1] = m.w.x; o[2] = m.w.y; o[3] = m.w.z; o[4] = m.a.x; o[5] = m.a.y; o[6] = m.a.z;
+        c->imu.n += 7;
+    }
+    return (int)c->pre_jobs.push(j);
+}
+
+int run_preint_jobs(xrvio_ctx *c) {
+    const int n = (int)c->pre_jobs.n;
+    if (n == 0) return XRVIO_OK;
+    CKC(c->pre_out.reserve((size_t)n * XRVIO_PRE_BLOCK));
+    CKC(cudaMemcpyAsync(c->pre_jobs.d, c->pre_jobs.h, n * sizeof(xvbe::PreintJob), cudaMemcpyHostToDevice, c->st));
+    CKC(cudaMemcpyAsync(c->imu.d, c->imu.h, c->imu.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    xvbe::preintegrate(c->pre_jobs.d, n, c->imu.d, c->rig_d, c->pre_out.d, c->st);
+    c->stats.kernels_launched += 1;
+    CKC(cudaMemcpyAsync(c->pre_out.h, c->pre_out.d, (size_t)n * XRVIO_PRE_BLOCK * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CKC(cudaStreamSynchronize(c->st));
+    c->stats.h2d_bytes += n * sizeof(xvbe::PreintJob) + c->imu.n * sizeof(double);
+    c->stats.d2h_bytes += (size_t)n * XRVIO_PRE_BLOCK * sizeof(double);
+    return XRVIO_OK;
+}
+void fetch_pre(xrvio_ctx *c, int job, std::vector<double> &dst) {
+    dst.assign(c->pre_out.h + (size_t)job * XRVIO_PRE_BLOCK, c->pre_out.h + (size_t)(job + 1) * XRVIO_PRE_BLOCK);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Problem builder (what Solver::add_frame_states / add_factor wire into Ceres, solver.cpp:84-174)
+// ---------------------------------------------------------------------------------------------
+struct Builder {
+    xrvio_ctx *c;
+    Session *s;
+    std::vector<Frame *> active, consts;
+    std::vector<Track *> free_lm, const_lm;
+    struct R { Frame *tgt, *ref; Track *tr; bool prior; V3 zt, zr; };
+    struct Ro { Frame *tgt, *ref; V3 zt, zr; };
+    struct P { Frame *i, *j; bool prior; const std::vector<double> *blk; };
+    std::vector<R> rpe; std::vector<Ro> rot; std::vector<P> pre;
+    bool use_marg = false;
+    void add_active(Frame *f) { if (f->tmp == -1) { f->tmp = -2; active.push_back(f); } }
+    void touch(Frame *f) { if (f->tmp == -1) { f->tmp = -3; consts.push_back(f); } }
+    void add_rpe(Frame *f, Track *tr, bool prior) {
+        Frame *ref = tr->refs.front().first;
+        touch(f); touch(ref);
+        if (tr->tmp == -1) { tr->tmp = prior ? -3 : -2; (prior ? const_lm : free_lm).push_back(tr); }
+        rpe.push_back({f, ref, tr, prior, f->bearings[tr->get_keypoint_index(f)], ref->bearings[tr->refs.front().second]});
+    }
+    void add_rot(Frame *f, Track *tr) {
+        Frame *ref = tr->refs.front().first;
+        touch(f); touch(ref);
+        rot.push_back({f, ref, f->bearings[tr->get_keypoint_index(f)], ref->bearings[tr->refs.front().second]});
+    }
+    void add_pre(Frame *i, Frame *j, const std::vector<double> *blk, bool prior) { touch(i); touch(j); pre.push_back({i, j, prior, blk}); }
+};
+
+// Packs one problem into the batch arenas.  Returns the problem index or < 0.
+int pack_problem(xrvio_ctx *c, Session &s, Builder &b, int max_iterations) {
+    // a frame is active (gets columns) iff it was added with add_frame_states and has a free block
+    std::vector<Frame *> frames;
+    for (Frame *f : b.active) if (!(f->fix_pose && f->fix_motion)) frames.push_back(f);
+    const int n_active = (int)frames.size();
+    for (Frame *f : b.active) if (f->fix_pose && f->fix_motion) frames.push_back(f);
+    for (Frame *f : b.consts) frames.push_back(f);
+    if (n_active > XRVIO_MAX_ACTIVE || (int)frames.size() > XRVIO_MAX_FRAMES) { xrvio_set_error("solve problem exceeds XRVIO_MAX_ACTIVE / XRVIO_MAX_FRAMES"); return XRVIO_ERR_LIMIT; }
+    for (size_t i = 0; i < frames.size(); ++i) frames[i]->tmp = (int)i;
+    std::vector<Track *> lms = b.free_lm;
+    lms.insert(lms.end(), b.const_lm.begin(), b.const_lm.end());
+    for (size_t i = 0; i < lms.size(); ++i) lms[i]->tmp = (int)i;
+    if (c->sdesc.reserve(c->sdesc.n + 1) != cudaSuccess || c->states.reserve(c->states.n + frames.size() * 16) != cudaSuccess ||
+        c->fflags.reserve(c->fflags.n + frames.size()) != cudaSuccess || c->invd.reserve(c->invd.n + lms.size() + 1) != cudaSuccess ||
+        c->rpe.reserve(c->rpe.n + b.rpe.size() + 1) != cudaSuccess || c->rot.reserve(c->rot.n + b.rot.size() + 1) != cudaSuccess ||
+        c->pref.reserve(c->pref.n + b.pre.size() + 1) != cudaSuccess || c->pblocks.reserve(c->pblocks.n + (b.pre.size() + 1) * XRVIO_PRE_BLOCK) != cudaSuccess ||
+        c->mframes.reserve(c->mframes.n + XRVIO_MAX_ACTIVE) != cudaSuccess) { xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA; }
+    xvbe::SolveDesc d{};
+    d.frame_off = (int)(c->states.n / 16); d.n_frames = (int)frames.size(); d.n_active = n_active;
+    d.lm_off = (int)c->invd.n; d.n_lm = (int)lms.size(); d.n_lm_free = (int)b.free_lm.size();
+    for (Frame *f : frames) {
+        std::memcpy(c->states.h + c->states.n, f->st.d, 16 * sizeof(double)); c->states.n += 16;
+        c->fflags.push((unsigned char)((f->fix_pose ? 0 : 1) | (f->fix_motion ? 0 : 2)));
+    }
+    for (Track *t : lms) c->invd.push(t->inv_depth);
+    // reprojection residuals sorted by (tgt, ref)
+    std::vector<xvbe::RpeObs> obs(b.rpe.size());
+    for (size_t k = 0; k < b.rpe.size(); ++k) {
+        const Builder::R &r = b.rpe[k];
+        xvbe::RpeObs o{};
+        o.tgt = (short)r.tgt->tmp; o.ref = (short)r.ref->tmp; o.lm = r.tr->tmp; o.prior = r.prior ? 1 : 0;
+        st3(o.zt, r.zt); st3(o.zr, r.zr);
+        obs[k] = o;
+    }
+    std::stable_sort(obs.begin(), obs.end(), [](const xvbe::RpeObs &x, const xvbe::RpeObs &y) { return x.tgt != y.tgt ? x.tgt < y.tgt : x.ref < y.ref; });
+    d.rpe_off = (int)c->rpe.n; d.n_rpe = (int)obs.size();
+    for (auto &o : obs) c->rpe.push(o);
+    d.rot_off = (int)c->rot.n; d.n_rot = (int)b.rot.size();
+    for (auto &r : b.rot) { xvbe::RotObs o{}; o.tgt = (short)r.tgt->tmp; o.ref = (short)r.ref->tmp; st3(o.zt, r.zt); st3(o.zr, r.zr); c->rot.push(o); }
+    d.pre_off = (int)c->pref.n; d.n_pre = (int)b.pre.size();
+    for (auto &p : b.pre) {
+        xvbe::PreRef r{};
+        r.i = (short)p.i->tmp; r.j = (short)p.j->tmp; r.prior = p.prior ? 1 : 0; r.block = (int)(c->pblocks.n / XRVIO_PRE_BLOCK);
+        std::memcpy(c->pblocks.h + c->pblocks.n, p.blk->data(), XRVIO_PRE_BLOCK * sizeof(double)); c->pblocks.n += XRVIO_PRE_BLOCK;
+        c->pref.push(r);
+    }
+    if (b.use_marg) {
+        Map *m = s.sw_map.get();
+        d.marg_k = (int)m->marg.frames.size();
+        d.marg_frames_off = (int)c->mframes.n;
+        for (Frame *f : m->marg.frames) c->mframes.push(f->tmp);
+        d.marg_off = (long long)(((size_t)s.idx * 2 + m->marg.slot) * c->prior_stride);
+    }
+    d.max_iterations = max_iterations;
+    s.prob_frames = frames;
+    s.prob_tracks = lms;
+    for (Frame *f : frames) f->tmp = -1;
+    for (Track *t : lms) t->tmp = -1;
+    return (int)c->sdesc.push(d);
+}
+
+void clear_solve_arenas(xrvio_ctx *c) {
+    c->sdesc.clear(); c->states.clear(); c->fflags.clear(); c->invd.clear(); c->rpe.clear(); c->rot.clear();
+    c->pref.clear(); c->pblocks.clear(); c->mframes.clear();
+}
+
+int run_solves(xrvio_ctx *c) {
+    const int n = (int)c->sdesc.n;
+    if (n == 0) return XRVIO_OK;
+    size_t scratch = 0;
+    for (int p = 0; p < n; ++p) {
+        xvbe::SolveDesc &d = c->sdesc.h[p];
+        d.scratch_off = (long long)scratch;
+        scratch += xvbe::solve_scratch_doubles(d.n_active, d.n_lm_free, d.n_pre, d.marg_k);
+    }
+    CKC(c->scratch.reserve(scratch * sizeof(double)));
+    CKC(c->sout.reserve(n));
+    auto up = [&](void *dst, const void *src, size_t bytes) { c->stats.h2d_bytes += bytes; return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->st) : cudaSuccess; };
+    CKC(up(c->sdesc.d, c->sdesc.h, n * sizeof(xvbe::SolveDesc)));
+    CKC(up(c->states.d, c->states.h, c->states.n * sizeof(double)));
+    CKC(up(c->fflags.d, c->fflags.h, c->fflags.n));
+    CKC(up(c->invd.d, c->invd.h, c->invd.n * sizeof(double)));
+    CKC(up(c->rpe.d, c->rpe.h, c->rpe.n * sizeof(xvbe::RpeObs)));
+    CKC(up(c->rot.d, c->rot.h, c->rot.n * sizeof(xvbe::RotObs)));
+    CKC(up(c->pref.d, c->pref.h, c->pref.n * sizeof(xvbe::PreRef)));
+    CKC(up(c->pblocks.d, c->pblocks.h, c->pblocks.n * sizeof(double)));
+    CKC(up(c->mframes.d, c->mframes.h, c->mframes.n * sizeof(int)));
+    xvbe::SolveBatch b;
+    b.desc = c->sdesc.d; b.states = c->states.d; b.frame_flags = c->fflags.d; b.inv_depth = c->invd.d; b.rpe = c->rpe.d; b.rot = c->rot.d;
+    b.pre = c->pref.d; b.pre_blocks = c->pblocks.d; b.marg_frames = c->mframes.d; b.marg = c->d_prior; b.scratch = c->scratch.as<double>();
+    b.out = c->sout.d;
+    xvbe::solve(b, n, c->rig_d, c->st);
+    c->stats.kernels_launched += 1;
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(c->states.h, c->states.d, c->states.n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    if (c->invd.n) CKC(cudaMemcpyAsync(c->invd.h, c->invd.d, c->invd.n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CKC(cudaMemcpyAsync(c->sout.h, c->sout.d, n * sizeof(xvbe::SolveOut), cudaMemcpyDeviceToHost, c->st));
+    CKC(cudaStreamSynchronize(c->st));
+    c->stats.d2h_bytes += c->states.n * sizeof(double) + c->invd.n * sizeof(double) + n * sizeof(xvbe::SolveOut);
+    return XRVIO_OK;
+}
+
+void writeback(xrvio_ctx *c, Session &s, int prob) {
+    const xvbe::SolveDesc &d = c->sdesc.h[prob];
+    for (int i = 0; i < d.n_active; ++i) std::memcpy(s.prob_frames[i]->st.d, c->states.h + (size_t)(d.frame_off + i) * 16, 16 * sizeof(double));
+    for (int k = 0; k < d.n_lm_free; ++k) s.prob_tracks[k]->inv_depth = c->invd.h[d.lm_off + k];
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int xrvio_default_params(xrvio_params *p, int width, int height) {
+    if (!p || width <= 0 || height <= 0) { xrvio_set_error("xrvio_default_params: bad argument"); return XRVIO_ERR_ARG; }
+    std::memset(p, 0, sizeof(*p));
+    p->width = width; p->height = height;
+    p->fx = 458.654; p->fy = 457.296; p->cx = width / 2.0; p->cy = height / 2.0;      // configs/euroc_sensor.yaml:43
+    const double qbc[4] = {-7.7071797555374275e-03, 1.0499323370587278e-02, 7.0175280029197162e-01, 7.1230146066895372e-01};
+    const double pbc[3] = {-0.0216401454975, -0.064676986768, 0.00981073058949};
+    for (int k = 0; k < 4; ++k) { p->q_bc[k] = qbc[k]; p->q_bi[k] = (k == 3); p->q_bo[k] = (k == 3); }
+    for (int k = 0; k < 3; ++k) p->p_bc[k] = pbc[k];
+    for (int k = 0; k < 3; ++k) {
+        p->cov_g[4 * k] = 2.8791302399999997e-08; p->cov_a[4 * k] = 4.0e-6; p->cov_bg[4 * k] = 3.7608844899999997e-10; p->cov_ba[4 * k] = 9.0e-6;
+    }
+    p->keypoint_cov[0] = p->keypoint_cov[1] = 0.5;
+    p->sliding_window_size = 10; p->subframe_size = 3; p->force_keyframe_landmarks = 35;     // configs/euroc_slam.yaml:6-9
+    p->min_keypoint_distance = 20.0; p->max_keypoint_detection = 200; p->max_init_frames = 60; p->max_frames = 20;
+    p->predict_keypoints = 1; p->clahe_clip_limit = 6.0; p->clahe_width = 8; p->clahe_height = 8;
+    p->init_keyframe_num = 8; p->init_keyframe_gap = 5; p->solver_iteration_limit = 30;
+    p->rotation_misalignment_threshold = 0.02; p->rotation_ransac_threshold = 10.0;
+    return XRVIO_OK;
+}
+
+int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **out) {
+    if (!p || !out || n_sessions <= 0) { xrvio_set_error("xrvio_create: bad argument"); return XRVIO_ERR_ARG; }
+    if (p->sliding_window_size + 2 > XRVIO_MAX_ACTIVE || p->max_keypoint_detection > XRVIO_MAX_CORNERS) { xrvio_set_error("xrvio_create: window / detection limit exceeded"); return XRVIO_ERR_LIMIT; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { xrvio_set_error("xrvio_create: no CUDA device (there is no CPU fallback)"); return XRVIO_ERR_CUDA; }
+    CKC(cudaSetDevice(device));
+    xrvio_ctx *c = new xrvio_ctx();
+    c->prm = *p; c->S = n_sessions; c->device = device;
+    CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    c->L = xvfe::make_pyr_layout(p->width, p->height);
+    c->K[0] = p->fx; c->K[1] = p->fy; c->K[2] = p->cx; c->K[3] = p->cy;
+    c->sic[0] = p->fx / std::sqrt(p->keypoint_cov[0]); c->sic[1] = p->fy / std::sqrt(p->keypoint_cov[1]);      // detail.cpp:107-109
+    xvbe::RigParams &r = c->rig_h;
+    for (int k = 0; k < 4; ++k) { r.cam_q[k] = p->q_bc[k]; r.imu_q[k] = p->q_bi[k]; }
+    for (int k = 0; k < 3; ++k) { r.cam_p[k] = p->p_bc[k]; r.imu_p[k] = p->p_bi[k]; }
+    r.sic[0] = c->sic[0]; r.sic[1] = c->sic[1];
+    for (int k = 0; k < 9; ++k) { r.cov_w[k] = p->cov_g[k]; r.cov_a[k] = p->cov_a[k]; r.cov_bg[k] = p->cov_bg[k]; r.cov_ba[k] = p->cov_ba[k]; }
+    c->rig.q_bc = ld4(p->q_bc); c->rig.p_bc = ld3(p->p_bc);
+    CKC(cudaMalloc((void **)&c->rig_d, sizeof(xvbe::RigParams)));
+    CKC(cudaMemcpy(c->rig_d, &r, sizeof(r), cudaMemcpyHostToDevice));
+    const size_t P = (size_t)p->width * p->height;
+    const int S = n_sessions;
+    CKC(cudaMalloc((void **)&c->d_raw, (size_t)S * kImgQueue * P));
+    CKC(cudaMalloc((void **)&c->d_stage, (size_t)S * P));
+    CKC(cudaMalloc((void **)&c->d_pyr, (size_t)S * kPyrSlots * c->L.total));
+    CKC(cudaMalloc((void **)&c->d_pyr_prev_batch, (size_t)S * c->L.total));
+    CKC(cudaMalloc((void **)&c->d_pyr_next_batch, (size_t)S * c->L.total));
+    CKC(cudaMalloc((void **)&c->d_lut, (size_t)S * p->clahe_width * p->clahe_height * 256));
+    CKC(cudaMalloc((void **)&c->d_cand, (size_t)S * xvfe::kMaxCand * 8));
+    CKC(cudaMalloc((void **)&c->d_cand_count, S * sizeof(int)));
+    CKC(cudaMalloc((void **)&c->d_maxval, S * sizeof(unsigned)));
+    CKC(c->corners.reserve((size_t)S * xvfe::kMaxCorners * 3)); CKC(c->corner_count.reserve(S));
+    CKC(c->klt_prev.reserve((size_t)S * xvfe::kMaxPts * 2)); CKC(c->klt_next.reserve((size_t)S * xvfe::kMaxPts * 2));
+    CKC(c->klt_n.reserve(S)); CKC(c->klt_status.reserve((size_t)S * xvfe::kMaxPts));
+    CKC(c->poi_pts.reserve((size_t)S * xvfe::kMaxPts * 2)); CKC(c->poi_npre.reserve(S)); CKC(c->poi_ntot.reserve(S));
+    CKC(c->poi_veto.reserve((size_t)S * xvfe::kMaxPts)); CKC(c->poi_keep.reserve((size_t)S * xvfe::kMaxPts));
+    const size_t n = (size_t)15 * (p->sliding_window_size + 1);      // the window may briefly hold size + 2 keyframes
+    c->prior_stride = 16 * (p->sliding_window_size + 1) + 2 * n * n + n + 64;
+    CKC(cudaMalloc((void **)&c->d_prior, (size_t)S * 2 * c->prior_stride * sizeof(double)));
+    CKC(cudaMemset(c->d_prior, 0, (size_t)S * 2 * c->prior_stride * sizeof(double)));
+    c->ses.resize(S);
+    for (int i = 0; i < S; ++i) { c->ses[i].idx = i; c->ses[i].ft_map.track_id_counter = &c->ses[i].track_id_counter; }
+    *out = c;
+    return XRVIO_OK;
+}
+
+int xrvio_destroy(xrvio_ctx *c) {
+    if (!c) return XRVIO_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    cudaFree(c->rig_d); cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_pyr); cudaFree(c->d_pyr_prev_batch); cudaFree(c->d_pyr_next_batch);
+    cudaFree(c->d_lut); cudaFree(c->d_cand); cudaFree(c->d_cand_count); cudaFree(c->d_maxval); cudaFree(c->d_prior);
+    cudaStreamDestroy(c->st);
+    delete c;
+    return XRVIO_OK;
+}
+
+int xrvio_push_bootstrap_state(xrvio_ctx *c, int session, double t, const double q[4], const double p[3], const double v[3]) {
+    if (!c || session < 0 || session >= c->S) { xrvio_set_error("bad session"); return XRVIO_ERR_ARG; }
+    State16 s;
+    for (int k = 0; k < 4; ++k) s.d[k] = q[k];
+    for (int k = 0; k < 3; ++k) { s.d[4 + k] = p[k]; s.d[7 + k] = v[k]; }
+    c->ses[session].bootstrap[tkey(t)] = s;
+    return XRVIO_OK;
+}
+
+// Detail::track_imu (detail.cpp:130-142): IMU samples up to the image time belong to the frame;
+// the first later sample releases the frame to the feature tracker.
+int xrvio_push_imu(xrvio_ctx *c, const int *session, const xrvio_imu *samples, int n) {
+    if (!c || !session || !samples || n < 0) { xrvio_set_error("xrvio_push_imu: bad argument"); return XRVIO_ERR_ARG; }
+    for (int i = 0; i < n; ++i) {
+        if (session[i] < 0 || session[i] >= c->S) { xrvio_set_error("bad session"); return XRVIO_ERR_ARG; }
+        Session &s = c->ses[session[i]];
+        Imu m{samples[i].t, ld3(samples[i].w), ld3(samples[i].a)};
+        s.frontal_imus.push_back(m);
+        s.imus.push_back(m);
+        while (!s.imus.empty() && !s.queued.empty()) {
+            if (s.imus.front().t <= s.queued.front()->t) { s.queued.front()->imu.push_back(s.imus.front()); s.imus.pop_front(); }
+            else { s.released.push_back(std::move(s.queued.front())); s.queued.pop_front(); }
+        }
+    }
+    return XRVIO_OK;
+}
+
+// Detail::track_camera (detail.cpp:103-128)
+int xrvio_push_images(xrvio_ctx *c, const int *session, const uint8_t *const *data, const int *stride, const double *t, int n, int on_device) {
+    if (!c || !session || !data || !t || n < 0) { xrvio_set_error("xrvio_push_images: bad argument"); return XRVIO_ERR_ARG; }
+    CKC(cudaSetDevice(c->device));
+    const int w = c->prm.width, h = c->prm.height;
+    for (int i = 0; i < n; ++i) {
+        if (session[i] < 0 || session[i] >= c->S) { xrvio_set_error("bad session"); return XRVIO_ERR_ARG; }
+        Session &s = c->ses[session[i]];
+        if (s.queued.size() + s.released.size() >= (size_t)kImgQueue) { xrvio_set_error("xrvio_push_images: image queue full, call xrvio_step"); return XRVIO_ERR_STATE; }
+        const int slot = s.img_slot_next; s.img_slot_next = (s.img_slot_next + 1) % kImgQueue;
+        uint8_t *dst = c->d_raw + ((size_t)s.idx * kImgQueue + slot) * w * h;
+        const int sp = stride ? stride[i] : w;
+        CKC(cudaMemcpy2DAsync(dst, w, data[i], sp, w, h, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
+        if (!on_device) c->stats.h2d_bytes += (size_t)w * h;
+        auto f = std::make_unique<Frame>();
+        f->id = ++s.frame_id_counter; f->t = t[i]; f->pyr_slot = slot;       // pyr_slot temporarily holds the raw slot
+        s.queued.push_back(std::move(f));
+        xrvio_pose op;
+        predict_pose(c, s, t[i], op);
+        if (t[i] > s.out_t) { s.out_pose = op; s.out_t = t[i]; }
+    }
+    return XRVIO_OK;
+}
+
+int xrvio_get_pose(xrvio_ctx *c, int session, xrvio_pose *pose) {
+    if (!c || !pose || session < 0 || session >= c->S) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    *pose = c->ses[session].out_pose;
+    pose->valid = pose->valid && c->ses[session].sw_map != nullptr;
+    return XRVIO_OK;
+}
+int xrvio_get_latest_state(xrvio_ctx *c, int session, double *t, double state16[16]) {
+    if (!c || session < 0 || session >= c->S) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    Session &s = c->ses[session];
+    if (!s.has_swt_latest) return XRVIO_ERR_STATE;
+    if (t) *t = s.swt_t;
+    if (state16) std::memcpy(state16, s.swt_state.d, sizeof(s.swt_state.d));
+    return XRVIO_OK;
+}
+int xrvio_get_state(xrvio_ctx *c, int session) {
+    if (!c || session < 0 || session >= c->S) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    return c->ses[session].sw_map ? XRVIO_STATE_TRACKING : XRVIO_STATE_INITIALIZING;
+}
+int xrvio_get_landmarks(xrvio_ctx *c, int session, double *xyz, int capacity) {
+    if (!c || session < 0 || session >= c->S) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    Session &s = c->ses[session];
+    if (!s.sw_map) return 0;
+    int n = 0;
+    for (auto &t : s.sw_map->tracks)
+        if (t->valid && !t->refs.empty()) {
+            if (xyz && n < capacity) { V3 x = get_landmark_point(t.get(), c->rig); xyz[3 * n] = x.x; xyz[3 * n + 1] = x.y; xyz[3 * n + 2] = x.z; }
+            n++;
+        }
+    return n;
+}
+int xrvio_get_stats(xrvio_ctx *c, xrvio_stats *st) {
+    if (!c || !st) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    *st = c->stats;
+    return XRVIO_OK;
+}
+
+}  // extern "C"
+
+// the step itself lives in session_step.inl to keep this file readable
+#include "session_step.inl"

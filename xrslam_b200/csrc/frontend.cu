@@ -22,7 +22,8 @@ __device__ __forceinline__ uint8_t sat_u8(int v) { return (uint8_t)min(max(v, 0)
 // K1 CLAHE.  OpenCV clahe.cpp: per-tile histogram -> clip -> redistribute -> cdf LUT; then bilinear
 // blend of the four neighbouring tile LUTs (float).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ lut,
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t *__restrict__ src, const int *__restrict__ sidx,
+                                                         size_t src_stride, uint8_t *__restrict__ lut,
                                                          int w, int h, int tw, int th, int tiles_x, int clip,
                                                          float lut_scale) {
     __shared__ int hist[256];
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t *__restric
     const int tid = threadIdx.x;
     const int tile = blockIdx.x, img = blockIdx.y;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
-    const uint8_t *I = src + (size_t)img * w * h;
+    const uint8_t *I = src + (size_t)(sidx ? sidx[img] : img) * src_stride;
     hist[tid] = 0;
     __syncthreads();
     const int npx = tw * th;
@@ -82,7 +83,9 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t *__restric
     lut[((size_t)img * gridDim.x + tile) * 256 + tid] = sat_u8(cv_round(f));
 }
 
-__global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+__global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t *__restrict__ src, const int *__restrict__ sidx,
+                                                           size_t src_stride, uint8_t *__restrict__ dst,
+                                                           const int *__restrict__ didx, size_t dst_stride,
                                                            const uint8_t *__restrict__ lut, int w, int h, int tiles_x,
                                                            int tiles_y, float inv_tw, float inv_th) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,18 +103,18 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t *__restr
     int ty2 = ty1 + 1;
     float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
     ty1 = max(ty1, 0); ty2 = min(ty2, tiles_y - 1);
-    size_t p = (size_t)img * w * h + (size_t)y * w + x;
-    int v = src[p];
+    const size_t p = (size_t)y * w + x;
+    int v = src[(size_t)(sidx ? sidx[img] : img) * src_stride + p];
     const uint8_t *P1 = L + (size_t)ty1 * tiles_x * 256;
     const uint8_t *P2 = L + (size_t)ty2 * tiles_x * 256;
     float l11 = (float)P1[tx1 * 256 + v], l12 = (float)P1[tx2 * 256 + v];
     float l21 = (float)P2[tx1 * 256 + v], l22 = (float)P2[tx2 * 256 + v];
     float res = (l11 * xa1 + l12 * xa) * ya1 + (l21 * xa1 + l22 * xa) * ya;
-    dst[p] = sat_u8(cv_round(res));
+    dst[(size_t)(didx ? didx[img] : img) * dst_stride + p] = sat_u8(cv_round(res));
 }
 
-void clahe(const uint8_t *src, uint8_t *dst, uint8_t *lut, int n, int w, int h, double clip_limit, int tiles_x,
-           int tiles_y, cudaStream_t st) {
+void clahe(const uint8_t *src, const int *src_idx, size_t src_stride, uint8_t *dst, const int *dst_idx, size_t dst_stride,
+           uint8_t *lut, int n, int w, int h, double clip_limit, int tiles_x, int tiles_y, cudaStream_t st) {
     int wext = (w % tiles_x == 0) ? w : w + (tiles_x - w % tiles_x);
     int hext = (h % tiles_y == 0) ? h : h + (tiles_y - h % tiles_y);
     if (w % tiles_x != 0 || h % tiles_y != 0) { wext = w + (tiles_x - w % tiles_x); hext = h + (tiles_y - h % tiles_y); }
@@ -120,21 +123,23 @@ void clahe(const uint8_t *src, uint8_t *dst, uint8_t *lut, int n, int w, int h, 
     float lut_scale = 255.0f / (float)area;
     int clip = 0;
     if (clip_limit > 0.0) { clip = (int)(clip_limit * area / 256); clip = clip > 1 ? clip : 1; }
-    clahe_lut_kernel<<<dim3(tiles_x * tiles_y, n), 256, 0, st>>>(src, lut, w, h, tw, th, tiles_x, clip, lut_scale);
+    clahe_lut_kernel<<<dim3(tiles_x * tiles_y, n), 256, 0, st>>>(src, src_idx, src_stride, lut, w, h, tw, th, tiles_x, clip, lut_scale);
     float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
-    clahe_apply_kernel<<<dim3((w + 255) / 256, h, n), 256, 0, st>>>(src, dst, lut, w, h, tiles_x, tiles_y, inv_tw, inv_th);
+    clahe_apply_kernel<<<dim3((w + 255) / 256, h, n), 256, 0, st>>>(src, src_idx, src_stride, dst, dst_idx, dst_stride, lut, w, h, tiles_x, tiles_y, inv_tw, inv_th);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2 pyrDown (5x5 Gaussian [1 4 6 4 1]^2 / 256, BORDER_REFLECT_101, rounding (s + 128) >> 8)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pyrdown_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
-                                                       int sw, int sh, int dw, int dh, size_t img_stride) {
+                                                       const int *__restrict__ idx, int sw, int sh, int dw, int dh,
+                                                       size_t img_stride) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= dw || y >= dh) return;
-    const uint8_t *S = src + (size_t)blockIdx.z * img_stride;
-    uint8_t *D = dst + (size_t)blockIdx.z * img_stride;
+    const size_t item = idx ? idx[blockIdx.z] : blockIdx.z;
+    const uint8_t *S = src + item * img_stride;
+    uint8_t *D = dst + item * img_stride;
     const int wts[5] = {1, 4, 6, 4, 1};
     int acc = 0;
 #pragma unroll
@@ -152,10 +157,10 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const uint8_t *__restrict_
     D[(size_t)y * dw + x] = (uint8_t)((acc + 128) >> 8);
 }
 
-void pyramid(uint8_t *pyr, int n, const PyrLayout &L, cudaStream_t st) {
+void pyramid(uint8_t *pyr, const int *idx, int n, const PyrLayout &L, cudaStream_t st) {
     for (int l = 1; l < kPyrLevels; ++l) {
         dim3 grid((L.w[l] + 31) / 32, (L.h[l] + 7) / 8, n);
-        pyrdown_kernel<<<grid, 256, 0, st>>>(pyr + L.off[l - 1], pyr + L.off[l], L.w[l - 1], L.h[l - 1], L.w[l], L.h[l], L.total);
+        pyrdown_kernel<<<grid, 256, 0, st>>>(pyr + L.off[l - 1], pyr + L.off[l], idx, L.w[l - 1], L.h[l - 1], L.w[l], L.h[l], L.total);
     }
 }
 
@@ -256,11 +261,12 @@ __device__ __forceinline__ void harris_tile(const uint8_t *__restrict__ I, int w
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) harris_max_kernel(const uint8_t *__restrict__ img, size_t img_stride, int w, int h,
+__global__ void __launch_bounds__(256) harris_max_kernel(const uint8_t *__restrict__ img, const int *__restrict__ idx,
+                                                          size_t img_stride, int w, int h,
                                                           unsigned int *__restrict__ maxval) {
     __shared__ float resp[HT_H][HT_W];
     __shared__ float wmax[8];
-    const uint8_t *I = img + (size_t)blockIdx.z * img_stride;
+    const uint8_t *I = img + (size_t)(idx ? idx[blockIdx.z] : blockIdx.z) * img_stride;
     harris_tile<0>(I, w, h, blockIdx.x * HT_W, blockIdx.y * HT_H, resp);
     float m = 0.f;
     for (int i = threadIdx.x; i < HT_W * HT_H; i += blockDim.x) m = fmaxf(m, resp[i / HT_W][i % HT_W]);
@@ -273,12 +279,13 @@ __global__ void __launch_bounds__(256) harris_max_kernel(const uint8_t *__restri
     }
 }
 
-__global__ void __launch_bounds__(256) harris_nms_kernel(const uint8_t *__restrict__ img, size_t img_stride, int w, int h,
+__global__ void __launch_bounds__(256) harris_nms_kernel(const uint8_t *__restrict__ img, const int *__restrict__ idx,
+                                                          size_t img_stride, int w, int h,
                                                           const unsigned int *__restrict__ maxval, float quality,
                                                           unsigned long long *__restrict__ cand,
                                                           int *__restrict__ cand_count) {
     __shared__ float resp[HT_H + 2][HT_W + 2];
-    const uint8_t *I = img + (size_t)blockIdx.z * img_stride;
+    const uint8_t *I = img + (size_t)(idx ? idx[blockIdx.z] : blockIdx.z) * img_stride;
     const int bx = blockIdx.x * HT_W, by = blockIdx.y * HT_H;
     harris_tile<1>(I, w, h, bx, by, resp);
     const float thr = (float)((double)__uint_as_float(maxval[blockIdx.z]) * (double)quality);
@@ -376,14 +383,14 @@ __global__ void __launch_bounds__(1024) corner_select_kernel(unsigned long long 
     }
 }
 
-void gftt_harris(const uint8_t *img, size_t img_stride, int n, int w, int h, int max_corners, float quality,
+void gftt_harris(const uint8_t *img, const int *idx, size_t img_stride, int n, int w, int h, int max_corners, float quality,
                  float min_distance, float *corners, int *count, unsigned long long *cand, int *cand_count,
                  unsigned int *maxval, cudaStream_t st) {
     cudaMemsetAsync(maxval, 0, sizeof(unsigned int) * n, st);
     cudaMemsetAsync(cand_count, 0, sizeof(int) * n, st);
     dim3 grid((w + HT_W - 1) / HT_W, (h + HT_H - 1) / HT_H, n);
-    harris_max_kernel<<<grid, 256, 0, st>>>(img, img_stride, w, h, maxval);
-    harris_nms_kernel<<<grid, 256, 0, st>>>(img, img_stride, w, h, maxval, quality, cand, cand_count);
+    harris_max_kernel<<<grid, 256, 0, st>>>(img, idx, img_stride, w, h, maxval);
+    harris_nms_kernel<<<grid, 256, 0, st>>>(img, idx, img_stride, w, h, maxval, quality, cand, cand_count);
     int cell = (int)lrintf(min_distance);
     int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
     size_t smem = (size_t)((gw * gh + 1) & ~1) * sizeof(short) + (size_t)gw * gh * 8 * sizeof(short2);
@@ -533,7 +540,9 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
 }
 
 __global__ void __launch_bounds__(32 * KLT_WARPS) klt_kernel(const uint8_t *__restrict__ prev_pyr,
-                                                              const uint8_t *__restrict__ next_pyr, PyrLayout L,
+                                                              const uint8_t *__restrict__ next_pyr,
+                                                              const int *__restrict__ pidx, const int *__restrict__ nidx,
+                                                              PyrLayout L,
                                                               const float *__restrict__ prev_pts,
                                                               float *__restrict__ next_pts,
                                                               const int *__restrict__ npts,
@@ -543,8 +552,8 @@ __global__ void __launch_bounds__(32 * KLT_WARPS) klt_kernel(const uint8_t *__re
     const int warp = threadIdx.x >> 5;
     const int pt = blockIdx.x * KLT_WARPS + warp;
     if (pt >= npts[img]) return;
-    const uint8_t *P = prev_pyr + (size_t)img * L.total;
-    const uint8_t *N = next_pyr + (size_t)img * L.total;
+    const uint8_t *P = prev_pyr + (size_t)(pidx ? pidx[img] : img) * L.total;
+    const uint8_t *N = next_pyr + (size_t)(nidx ? nidx[img] : img) * L.total;
     const size_t o = ((size_t)img * kMaxPts + pt) * 2;
     const float px = prev_pts[o], py = prev_pts[o + 1];
     const float gx = next_pts[o], gy = next_pts[o + 1];
@@ -569,10 +578,11 @@ __global__ void __launch_bounds__(32 * KLT_WARPS) klt_kernel(const uint8_t *__re
     }
 }
 
-void klt_track(const uint8_t *prev_pyr, const uint8_t *next_pyr, int n, const PyrLayout &L, const float *prev_pts,
+void klt_track(const uint8_t *prev_pyr, const uint8_t *next_pyr, const int *prev_idx, const int *next_idx, int n,
+               const PyrLayout &L, const float *prev_pts,
                float *next_pts, const int *npts, uint8_t *status, cudaStream_t st) {
     dim3 grid(kMaxPts / KLT_WARPS, n);
-    klt_kernel<<<grid, 32 * KLT_WARPS, 0, st>>>(prev_pyr, next_pyr, L, prev_pts, next_pts, npts, status);
+    klt_kernel<<<grid, 32 * KLT_WARPS, 0, st>>>(prev_pyr, next_pyr, prev_idx, next_idx, L, prev_pts, next_pts, npts, status);
 }
 
 // ------------------------------------------------------------------------------------------------

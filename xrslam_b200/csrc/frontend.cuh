@@ -31,22 +31,24 @@ inline PyrLayout make_pyr_layout(int w, int h) {
 }
 
 // ---- K1: CLAHE.  src/dst: n images of h*w bytes.  lut: n * tiles * 256 bytes scratch.
-void clahe(const uint8_t *src, uint8_t *dst, uint8_t *lut, int n, int w, int h, double clip_limit, int tiles_x,
-           int tiles_y, cudaStream_t st);
+// Batch item i reads image src + (src_idx ? src_idx[i] : i) * src_stride and writes dst + (dst_idx ? ...) * dst_stride.
+void clahe(const uint8_t *src, const int *src_idx, size_t src_stride, uint8_t *dst, const int *dst_idx, size_t dst_stride,
+           uint8_t *lut, int n, int w, int h, double clip_limit, int tiles_x, int tiles_y, cudaStream_t st);
 // ---- K2: pyramid levels 1..3 from level 0 (already in pyr + off[0]).  pyr: n * L.total bytes.
-void pyramid(uint8_t *pyr, int n, const PyrLayout &L, cudaStream_t st);
+void pyramid(uint8_t *pyr, const int *idx /* pyramid index per batch item, may be null */, int n, const PyrLayout &L, cudaStream_t st);
 // Scharr derivative image of one level (only for parity tests; KLT recomputes derivatives on chip).
 void scharr(const uint8_t *img, int16_t *deriv, int n, int w, int h, cudaStream_t st);
 // ---- K3: GFTT with Harris response.  img: n images (stride `img_stride` bytes between images).
 // corners: n * kMaxCorners * 3 floats (x, y, response); count: n ints.
 // scratch: cand (n * kMaxCand * 8 bytes), cand_count (n ints), maxval (n uint32)
-void gftt_harris(const uint8_t *img, size_t img_stride, int n, int w, int h, int max_corners, float quality,
+void gftt_harris(const uint8_t *img, const int *idx, size_t img_stride, int n, int w, int h, int max_corners, float quality,
                  float min_distance, float *corners, int *count, unsigned long long *cand, int *cand_count,
                  unsigned int *maxval, cudaStream_t st);
 // ---- K4: pyramidal LK forward + gates + backward + 0.5 px check (opencv_image.cpp:75-154).
 // prev_pyr / next_pyr: n pyramids.  pts: n * kMaxPts * 2 floats.  npts: n ints.
 // next_pts in: initial guess (gyro prediction); out: tracked position.  status out: n * kMaxPts bytes.
-void klt_track(const uint8_t *prev_pyr, const uint8_t *next_pyr, int n, const PyrLayout &L, const float *prev_pts,
+void klt_track(const uint8_t *prev_pyr, const uint8_t *next_pyr, const int *prev_idx, const int *next_idx, int n,
+               const PyrLayout &L, const float *prev_pts,
                float *next_pts, const int *npts, uint8_t *status, cudaStream_t st);
 // ---- K5: Poisson-disk filter.  For each of n lists: the first n_preset points are pre-seeded, the
 // rest are tested in order; keep[i] = 1 if accepted.  mode 0: insert_points semantics (detect);

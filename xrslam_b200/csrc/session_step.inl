@@ -1,0 +1,792 @@
+// xrvio_step: batched FeatureTracker::work + FrontendWorker::work (included by capi_session.cu).
+
+namespace {
+
+struct StepBuffers {       // small index arrays living in the context (allocated lazily)
+    Arena<int> idx_raw, idx_next, idx_prev;
+};
+StepBuffers &sb(xrvio_ctx *c) {
+    static std::map<xrvio_ctx *, std::unique_ptr<StepBuffers>> m;     // contexts are few; freed at process exit
+    auto &p = m[c];
+    if (!p) p = std::make_unique<StepBuffers>();
+    return *p;
+}
+
+int run_poisson(xrvio_ctx *c, int n, bool with_veto) {
+    const size_t pb = (size_t)n * xvfe::kMaxPts;
+    CKC(cudaMemcpyAsync(c->poi_pts.d, c->poi_pts.h, pb * 2 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CKC(cudaMemcpyAsync(c->poi_npre.d, c->poi_npre.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CKC(cudaMemcpyAsync(c->poi_ntot.d, c->poi_ntot.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    if (with_veto) CKC(cudaMemcpyAsync(c->poi_veto.d, c->poi_veto.h, pb, cudaMemcpyHostToDevice, c->st));
+    xvfe::poisson_filter(c->poi_pts.d, c->poi_npre.d, c->poi_ntot.d, with_veto ? c->poi_veto.d : nullptr, c->poi_keep.d, n,
+                         c->prm.min_keypoint_distance, c->st);
+    c->stats.kernels_launched += 1;
+    CKC(cudaMemcpyAsync(c->poi_keep.h, c->poi_keep.d, pb, cudaMemcpyDeviceToHost, c->st));
+    CKC(cudaStreamSynchronize(c->st));
+    c->stats.h2d_bytes += pb * 2 * sizeof(double) + 2 * n * sizeof(int) + (with_veto ? pb : 0);
+    c->stats.d2h_bytes += pb;
+    return XRVIO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FeatureTracker::work for one released frame of every session in `act`
+// ---------------------------------------------------------------------------------------------
+int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
+    const int n = (int)act.size();
+    const int w = c->prm.width, h = c->prm.height;
+    const size_t P = (size_t)w * h;
+    StepBuffers &B = sb(c);
+    CKC(B.idx_raw.reserve(n)); CKC(B.idx_next.reserve(n)); CKC(B.idx_prev.reserve(n));
+    // ---- phase A: CLAHE + pyramid + GFTT on the new image; preintegration (no Jacobian / covariance) ----
+    c->pre_jobs.clear(); c->imu.clear();
+    for (int i = 0; i < n; ++i) {
+        Session &s = *act[i];
+        s.cur = std::move(s.released.front());
+        s.released.pop_front();
+        Frame *f = s.cur.get();
+        const int raw_slot = f->pyr_slot;
+        f->pyr_slot = s.pyr_next; s.pyr_next = (s.pyr_next + 1) % kPyrSlots;
+        B.idx_raw.h[i] = s.idx * kImgQueue + raw_slot;
+        B.idx_next.h[i] = s.idx * kPyrSlots + f->pyr_slot;
+        s.fe_has_last = s.ft_map.frame_num() > 0;
+        s.last = s.fe_has_last ? s.ft_map.frames.back().get() : nullptr;
+        s.pre_job = -1;
+        const bool is_init = s.has_swt_latest;
+        if (s.fe_has_last) {
+            if (is_init) {
+                // feature_tracker.cpp:50-76: the last optimised frame takes the back end's state; later
+                // frames would be re-propagated (none exist in the synchronous pipeline)
+                long idx = s.ft_map.frame_index_by_id(s.swt_frame_id);
+                if (idx >= 0) {
+                    s.ft_map.frames[idx]->st = s.swt_state;
+                    if ((size_t)idx + 1 != s.ft_map.frame_num()) { xrvio_set_error("front end ran ahead of the back end (asynchronous mode is not supported)"); return XRVIO_ERR_STATE; }
+                } else s.has_latest = false;
+            }
+            // IMU stitching (feature_tracker.cpp:77-88)
+            if (!s.last->imu.empty()) {
+                if (f->imu.empty() || (f->imu.front().t - s.last->t > 1.0e-5)) {
+                    Imu m = s.last->imu.back();
+                    m.t = s.last->t;
+                    f->imu.insert(f->imu.begin(), m);
+                }
+            }
+            if (!f->imu.empty()) {
+                s.pre_job = add_preint_job(c, f->imu, f->t, s.last->st, 0);
+                if (s.pre_job < 0) { xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA; }
+            }
+        }
+    }
+    CKC(cudaMemcpyAsync(B.idx_raw.d, B.idx_raw.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CKC(cudaMemcpyAsync(B.idx_next.d, B.idx_next.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    xvfe::clahe(c->d_raw, B.idx_raw.d, P, c->d_pyr, B.idx_next.d, c->L.total, c->d_lut, n, w, h, c->prm.clahe_clip_limit,
+                c->prm.clahe_width, c->prm.clahe_height, c->st);
+    xvfe::pyramid(c->d_pyr, B.idx_next.d, n, c->L, c->st);
+    xvfe::gftt_harris(c->d_pyr, B.idx_next.d, c->L.total, n, w, h, c->prm.max_keypoint_detection, 1.0e-3f, 20.0f, c->corners.d,
+                      c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->st);
+    c->stats.kernels_launched += 2 + 3 + 3;
+    CKC(cudaMemcpyAsync(c->corners.h, c->corners.d, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CKC(cudaMemcpyAsync(c->corner_count.h, c->corner_count.d, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    c->stats.d2h_bytes += (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float) + n * sizeof(int);
+    { int rc = run_preint_jobs(c); if (rc) return rc; }     // also synchronises the stream
+    if (c->pre_jobs.n == 0) CKC(cudaStreamSynchronize(c->st));
+    CKC(cudaGetLastError());
+    // ---- phase B: pyramidal LK (previous pyramid -> new pyramid), gyro-predicted initial guess ----
+    int n_klt = 0;
+    for (int i = 0; i < n; ++i) {
+        Session &s = *act[i];
+        Frame *f = s.cur.get();
+        c->klt_n.h[i] = 0;
+        B.idx_prev.h[i] = B.idx_next.h[i];
+        if (!s.fe_has_last) continue;
+        if (s.pre_job >= 0) fetch_pre(c, s.pre_job, f->pre); else f->pre.assign(XRVIO_PRE_BLOCK, 0.0);
+        Frame *last = s.last;
+        const int np = (int)last->keypoint_num();
+        if (np > xvfe::kMaxPts) { xrvio_set_error("more than XRVIO_MAX_PTS keypoints in a frame"); return XRVIO_ERR_LIMIT; }
+        c->klt_n.h[i] = np;
+        B.idx_prev.h[i] = s.idx * kPyrSlots + last->pyr_slot;
+        s.klt_next.assign((size_t)np * 2, 0.0);
+        // frame.cpp:82-93: delta_key_q = (q_cb^-1 q_ib dq q_ib'^-1 q_cb')^-1
+        Q4 dkq = q4(0, 0, 0, 1);
+        if (c->prm.predict_keypoints && s.pre_job >= 0) {
+            const Q4 qbc = ld4(c->prm.q_bc), qbi = ld4(c->prm.q_bi);
+            dkq = qconj(qmul(qmul(qmul(qmul(qconj(qbc), qbi), ld4(&f->pre[xvbe::PB_Q])), qconj(qbi)), qbc));
+        }
+        for (int k = 0; k < np; ++k) {
+            double px[2], pr[2];
+            apply_k(last->bearings[k], c->K, px);
+            if (c->prm.predict_keypoints) apply_k(qrot(dkq, last->bearings[k]), c->K, pr);
+            else { pr[0] = px[0]; pr[1] = px[1]; }
+            float *pp = c->klt_prev.h + ((size_t)i * xvfe::kMaxPts + k) * 2;
+            float *nn = c->klt_next.h + ((size_t)i * xvfe::kMaxPts + k) * 2;
+            pp[0] = (float)px[0]; pp[1] = (float)px[1];
+            nn[0] = (float)pr[0]; nn[1] = (float)pr[1];
+            s.klt_next[2 * k] = pr[0]; s.klt_next[2 * k + 1] = pr[1];
+        }
+        n_klt += np;
+    }
+    if (n_klt > 0) {
+        const size_t pb = (size_t)n * xvfe::kMaxPts * 2 * sizeof(float);
+        CKC(cudaMemcpyAsync(c->klt_prev.d, c->klt_prev.h, pb, cudaMemcpyHostToDevice, c->st));
+        CKC(cudaMemcpyAsync(c->klt_next.d, c->klt_next.h, pb, cudaMemcpyHostToDevice, c->st));
+        CKC(cudaMemcpyAsync(c->klt_n.d, c->klt_n.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+        CKC(cudaMemcpyAsync(B.idx_prev.d, B.idx_prev.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+        xvfe::klt_track(c->d_pyr, c->d_pyr, B.idx_prev.d, B.idx_next.d, n, c->L, c->klt_prev.d, c->klt_next.d, c->klt_n.d, c->klt_status.d, c->st);
+        c->stats.kernels_launched += 1;
+        CKC(cudaMemcpyAsync(c->klt_next.h, c->klt_next.d, pb, cudaMemcpyDeviceToHost, c->st));
+        CKC(cudaMemcpyAsync(c->klt_status.h, c->klt_status.d, (size_t)n * xvfe::kMaxPts, cudaMemcpyDeviceToHost, c->st));
+        CKC(cudaStreamSynchronize(c->st));
+        c->stats.h2d_bytes += 2 * pb + 2 * n * sizeof(int);
+        c->stats.d2h_bytes += pb + (size_t)n * xvfe::kMaxPts;
+    }
+    // ---- phase C: Frame::track_keypoints after the LK call (frame.cpp:99-173) ----
+    bool any_track = false;
+    for (int i = 0; i < n; ++i) {
+        Session &s = *act[i];
+        c->poi_npre.h[i] = 0; c->poi_ntot.h[i] = 0;
+        if (!s.fe_has_last) continue;
+        Frame *f = s.cur.get();
+        Frame *last = s.last;
+        const int np = (int)last->keypoint_num();
+        s.klt_status.assign(np, 0);
+        for (int k = 0; k < np; ++k) {
+            const unsigned char st = c->klt_status.h[(size_t)i * xvfe::kMaxPts + k];
+            s.klt_status[k] = st;
+            if (st) {
+                const float *nn = c->klt_next.h + ((size_t)i * xvfe::kMaxPts + k) * 2;
+                s.klt_next[2 * k] = (double)nn[0]; s.klt_next[2 * k + 1] = (double)nn[1];
+            }
+        }
+        s.next_bearings.resize(np);
+        for (int k = 0; k < np; ++k) s.next_bearings[k] = remove_k(&s.klt_next[2 * k], c->K);
+        // essential-matrix RANSAC mask (frame.cpp:108-114): all ones for n >= 5, all zeros otherwise
+        if (np < 5) std::fill(s.klt_status.begin(), s.klt_status.end(), 0);
+        std::vector<char> mask;
+        M3 R = find_rotation_matrix(last->bearings, s.next_bearings, mask, (M_PI / 180.0) * c->prm.rotation_ransac_threshold);
+        std::vector<double> angles;
+        for (int k = 0; k < np; ++k)
+            if (mask[k]) angles.push_back(std::acos(dot(R * last->bearings[k], s.next_bearings[k])) * 180 / M_PI);
+        std::sort(angles.begin(), angles.end());
+        const double misalignment = angles.empty() ? 0.0 : angles[angles.size() * 7 / 10];
+        if (misalignment < c->prm.rotation_misalignment_threshold) f->no_translation = true;
+        // order by track length (frame.cpp:136-150)
+        s.order.clear();
+        for (int k = 0; k < np; ++k) {
+            if (!s.klt_status[k]) continue;
+            Track *tr = last->tracks[k];
+            if (!tr) continue;
+            s.order.emplace_back(k, (int)tr->keypoint_num());
+        }
+        std::stable_sort(s.order.begin(), s.order.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.second > b.second; });
+        if ((int)s.order.size() > xvfe::kMaxPts) { xrvio_set_error("too many tracked keypoints"); return XRVIO_ERR_LIMIT; }
+        c->poi_ntot.h[i] = (int)s.order.size();
+        for (size_t q = 0; q < s.order.size(); ++q) {
+            const int k = s.order[q].first;
+            double *pp = c->poi_pts.h + ((size_t)i * xvfe::kMaxPts + q) * 2;
+            pp[0] = s.klt_next[2 * k]; pp[1] = s.klt_next[2 * k + 1];
+            Track *tr = last->tracks[k];
+            c->poi_veto.h[(size_t)i * xvfe::kMaxPts + q] = (tr && tr->trash) ? 1 : 0;
+        }
+        any_track = any_track || !s.order.empty();
+    }
+    if (any_track) { int rc = run_poisson(c, n, true); if (rc) return rc; }
+    for (int i = 0; i < n; ++i) {
+        Session &s = *act[i];
+        if (!s.fe_has_last) continue;
+        Frame *f = s.cur.get();
+        Frame *last = s.last;
+        const int np = (int)last->keypoint_num();
+        // tracks that were never created for a keypoint (get_track(i) == nullptr at :142) keep their status
+        for (size_t q = 0; q < s.order.size(); ++q)
+            if (!c->poi_keep.h[(size_t)i * xvfe::kMaxPts + q]) s.klt_status[s.order[q].first] = 0;
+        for (int k = 0; k < np; ++k) {
+            if (!s.klt_status[k]) continue;
+            const int nk = (int)f->keypoint_num();
+            f->append_keypoint(s.next_bearings[k]);
+            Track *tr = frame_get_track(last, k, nullptr);
+            f->map = &s.ft_map;          // add_keypoint only needs the frame; map is attached below
+            track_add_keypoint(tr, f, nk);
+        }
+        if (s.has_swt_latest) {
+            // feature_tracker.cpp:93-116
+            pre_predict(f->pre, last->st, f->st);
+            s.has_latest = true; s.latest_t = f->t; s.latest = f->st;
+        }
+    }
+    // ---- phase D: Frame::detect_keypoints (frame.cpp:55-72, opencv_image.cpp:46-72) ----
+    for (int i = 0; i < n; ++i) {
+        Session &s = *act[i];
+        Frame *f = s.cur.get();
+        const int npre = (int)f->keypoint_num();
+        const int nc = c->corner_count.h[i];
+        if (npre + nc > xvfe::kMaxPts) { xrvio_set_error("too many keypoints for the Poisson filter"); return XRVIO_ERR_LIMIT; }
+        c->poi_npre.h[i] = npre; c->poi_ntot.h[i] = npre + nc;
+        for (int k = 0; k < npre; ++k) apply_k(f->bearings[k], c->K, c->poi_pts.h + ((size_t)i * xvfe::kMaxPts + k) * 2);
+        // GFTT corners arrive strongest first; std::sort by response (opencv_image.cpp:47-50) keeps that order
+        for (int k = 0; k < nc; ++k) {
+            const float *cr = c->corners.h + ((size_t)i * xvfe::kMaxCorners + k) * 3;
+            double *pp = c->poi_pts.h + ((size_t)i * xvfe::kMaxPts + npre + k) * 2;
+            pp[0] = (double)cr[0]; pp[1] = (double)cr[1];
+        }
+        s.n_corners = nc;
+    }
+    { int rc = run_poisson(c, n, false); if (rc) return rc; }
+    for (int i = 0; i < n; ++i) {
+        Session &s = *act[i];
+        Frame *f = s.cur.get();
+        const int npre = c->poi_npre.h[i];
+        for (int k = 0; k < s.n_corners; ++k) {
+            if (!c->poi_keep.h[(size_t)i * xvfe::kMaxPts + npre + k]) continue;
+            const double *pp = c->poi_pts.h + ((size_t)i * xvfe::kMaxPts + npre + k) * 2;
+            if (pp[0] < 20 || pp[1] < 20 || pp[0] >= w - 20 || pp[1] >= h - 20) continue;
+            f->append_keypoint(remove_k(pp, c->K));
+        }
+        // attach + trim (feature_tracker.cpp:130-135)
+        const bool is_init = s.has_swt_latest;
+        s.ft_map.attach_frame(std::move(s.cur));
+        const size_t max_frames = is_init ? c->prm.max_frames : c->prm.max_init_frames;
+        while (s.ft_map.frame_num() > max_frames && is_init && s.ft_map.frames[0]->id < s.swt_frame_id) {
+            map_untrack_frame(&s.ft_map, s.ft_map.frames[0].get(), c->rig);
+            s.ft_map.detach_frame(0);
+        }
+        c->stats.frames_processed++;
+    }
+    return XRVIO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Back end helpers
+// ---------------------------------------------------------------------------------------------
+int run_triangulation(xrvio_ctx *c) {
+    const int n = (int)c->tjobs.n;
+    if (n == 0) return XRVIO_OK;
+    CKC(c->tout.reserve((size_t)n * 4));
+    CKC(cudaMemcpyAsync(c->tjobs.d, c->tjobs.h, n * sizeof(xvbe::TriJob), cudaMemcpyHostToDevice, c->st));
+    CKC(cudaMemcpyAsync(c->tviews.d, c->tviews.h, c->tviews.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    xvbe::triangulate(c->tjobs.d, n, c->tviews.d, c->tout.d, c->st);
+    c->stats.kernels_launched += 1;
+    CKC(cudaMemcpyAsync(c->tout.h, c->tout.d, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CKC(cudaStreamSynchronize(c->st));
+    c->stats.h2d_bytes += n * sizeof(xvbe::TriJob) + c->tviews.n * sizeof(double);
+    c->stats.d2h_bytes += (size_t)n * 4 * sizeof(double);
+    return XRVIO_OK;
+}
+int add_tri_job(xrvio_ctx *c, Track *tr) {          // Track::triangulate input (track.cpp:46-62)
+    if (c->tjobs.reserve(c->tjobs.n + 1) != cudaSuccess || c->tviews.reserve(c->tviews.n + tr->refs.size() * 16) != cudaSuccess) return -1;
+    xvbe::TriJob j{(int)(c->tviews.n / 16), (int)tr->refs.size()};
+    for (auto &r : tr->refs) {
+        Q4 q; V3 p;
+        camera_pose(r.first, c->rig, q, p);
+        double *o = c->tviews.h + c->tviews.n;
+        st4(o, q); st3(o + 4, p); st3(o + 7, r.first->bearings[r.second]);
+        for (int k = 10; k < 16; ++k) o[k] = 0;
+        c->tviews.n += 16;
+    }
+    return (int)c->tjobs.push(j);
+}
+
+// Initializer::mirror_keyframe_map (initializer.cpp:22-76) + ground-truth states
+bool bootstrap_mirror(xrvio_ctx *c, Session &s, long long init_frame_id) {
+    Map &ft = s.ft_map;
+    const long last = ft.frame_index_by_id(init_frame_id);
+    const long gap = c->prm.init_keyframe_gap, dist = gap * (c->prm.init_keyframe_num - 1);
+    if (last < dist) return false;
+    const long first = last - dist;
+    std::vector<long> idxs;
+    for (int i = 0; i < c->prm.init_keyframe_num; ++i) idxs.push_back(first + i * gap);
+    for (long ix : idxs)
+        if (s.bootstrap.find(tkey(ft.frames[ix]->t)) == s.bootstrap.end()) return false;
+    auto m = std::make_unique<Map>();
+    m->track_id_counter = &s.track_id_counter;
+    for (long ix : idxs) m->attach_frame(ft.frames[ix]->clone());
+    for (size_t j = 1; j < m->frame_num(); ++j) {
+        Frame *oi = ft.frames[idxs[j - 1]].get(), *oj = ft.frames[idxs[j]].get();
+        Frame *ni = m->frames[j - 1].get(), *nj = m->frames[j].get();
+        for (size_t ki = 0; ki < oi->keypoint_num(); ++ki)
+            if (Track *tr = oi->tracks[ki]) {
+                int kj = tr->get_keypoint_index(oj);
+                if (kj >= 0) track_add_keypoint(frame_get_track(ni, (int)ki, nullptr), nj, kj);
+            }
+        nj->imu.clear();
+        for (long f = idxs[j - 1]; f < idxs[j]; ++f) {
+            const auto &od = ft.frames[f + 1]->imu;
+            nj->imu.insert(nj->imu.end(), od.begin(), od.end());
+        }
+    }
+    for (auto &f : m->frames) {
+        const State16 &g = s.bootstrap[tkey(f->t)];
+        f->st = g;
+        for (int k = 10; k < 16; ++k) f->st.d[k] = 0.0;
+    }
+    s.sw_map = std::move(m);
+    return true;
+}
+
+// SlidingWindowTracker::mirror_frame up to the preintegration (sliding_window_tracker.cpp:31-75)
+bool mirror_frame(xrvio_ctx *c, Session &s, long long frame_id) {
+    Map *m = s.sw_map.get();
+    Map &ft = s.ft_map;
+    Frame *keyframe = m->frames.back().get();
+    Frame *new_i = keyframe->subframes.empty() ? keyframe : keyframe->subframes.back().get();
+    const long ii = ft.frame_index_by_id(new_i->id), jj = ft.frame_index_by_id(frame_id);
+    if (ii < 0 || jj < 0) return false;
+    Frame *old_i = ft.frames[ii].get(), *old_j = ft.frames[jj].get();
+    std::unique_ptr<Frame> curr = old_j->clone();
+    for (long index = jj - 1; index > ii; --index) {
+        const auto &od = ft.frames[index]->imu;
+        curr->imu.insert(curr->imu.begin(), od.begin(), od.end());
+    }
+    m->attach_frame(std::move(curr));
+    Frame *new_j = m->frames.back().get();
+    for (size_t ki = 0; ki < old_i->keypoint_num(); ++ki)
+        if (Track *tr = old_i->tracks[ki]) {
+            int kj = tr->get_keypoint_index(old_j);
+            if (kj >= 0) {
+                Track *nt = frame_get_track(new_i, (int)ki, m);
+                track_add_keypoint(nt, new_j, kj);
+                tr->trash = nt->trash && !nt->is_static;
+            }
+        }
+    std::vector<Track *> prune;
+    for (auto &t : m->tracks) if (t->trash && !t->is_static) prune.push_back(t.get());
+    for (Track *t : prune) map_erase_track(m, t, c->rig);
+    s.new_i = new_i; s.new_j = new_j;
+    return true;
+}
+
+// SlidingWindowTracker::manage_keyframe (sliding_window_tracker.cpp:145-223)
+bool manage_keyframe(xrvio_ctx *c, Session &s) {
+    Map *m = s.sw_map.get();
+    Frame *ki = m->frames[m->frame_num() - 2].get();
+    Frame *nj = m->frames[m->frame_num() - 1].get();
+    if (!ki->subframes.empty()) {
+        if (ki->subframes.back()->no_translation) {
+            if (!nj->no_translation) {
+                ki->subframes.back()->keyframe = true;
+                std::unique_ptr<Frame> f = std::move(ki->subframes.back());
+                ki->subframes.pop_back();
+                m->attach_frame(std::move(f), (long)m->frame_num() - 1);
+                nj->keyframe = true;
+                return true;
+            }
+        } else {
+            if (nj->no_translation) {
+                std::unique_ptr<Frame> lifted = std::move(ki->subframes.back());
+                ki->subframes.pop_back();
+                lifted->keyframe = true;
+                lifted->subframes.push_back(m->detach_frame(m->frame_num() - 1));
+                m->attach_frame(std::move(lifted));
+                return true;
+            } else if ((int)ki->subframes.size() >= c->prm.subframe_size) {
+                nj->keyframe = true;
+                return true;
+            }
+        }
+    }
+    int cnt = 0;
+    for (size_t k = 0; k < nj->keypoint_num(); ++k)
+        if (Track *t = nj->tracks[k]) if (t->valid && t->triangulated && t->is_static) cnt++;
+    if (cnt < c->prm.force_keyframe_landmarks) { nj->keyframe = true; return true; }
+    ki->subframes.push_back(m->detach_frame(m->frame_num() - 1));
+    return false;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
+    // ---- phase E: mirror + preintegration with Jacobians and covariance ----
+    c->pre_jobs.clear(); c->imu.clear();
+    for (Session *sp : act) {
+        Session &s = *sp;
+        s.be_mode = 0; s.pre_jobs.clear(); s.pre_job_frames.clear(); s.prob1 = s.prob2 = -1; s.is_keyframe = false;
+        const long long frame_id = s.ft_map.frames.back()->id;
+        if (!s.sw_map) {
+            if (!bootstrap_mirror(c, s, frame_id)) continue;
+            s.be_mode = 1;
+            Map *m = s.sw_map.get();
+            for (size_t j = 1; j < m->frame_num(); ++j) {
+                Frame *fi = m->frames[j - 1].get(), *fj = m->frames[j].get();
+                if (fj->imu.empty()) { s.pre_jobs.push_back(-1); continue; }
+                s.pre_jobs.push_back(add_preint_job(c, fj->imu, fj->t, fi->st, 3));
+            }
+        } else {
+            s.be_mode = 2;
+            if (!mirror_frame(c, s, frame_id)) { s.be_mode = 3; continue; }     // frame slid out: track() still runs
+            s.pre_jobs.push_back(s.new_j->imu.empty() ? -1 : add_preint_job(c, s.new_j->imu, s.new_j->t, s.new_i->st, 3));
+        }
+    }
+    { int rc = run_preint_jobs(c); if (rc) return rc; }
+    // ---- phase F: bootstrap triangulation; localize / initial BA problems ----
+    c->tjobs.clear(); c->tviews.clear();
+    for (Session *sp : act) {
+        Session &s = *sp;
+        if (s.be_mode != 1) continue;
+        Map *m = s.sw_map.get();
+        s.tri_tracks.clear(); s.tri_off = (int)c->tjobs.n;
+        for (auto &t : m->tracks)
+            if (t->keypoint_num() >= 2) { if (add_tri_job(c, t.get()) < 0) { xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA; } s.tri_tracks.push_back(t.get()); }
+    }
+    { int rc = run_triangulation(c); if (rc) return rc; }
+    clear_solve_arenas(c);
+    for (Session *sp : act) {
+        Session &s = *sp;
+        if (s.be_mode == 1) {
+            Map *m = s.sw_map.get();
+            for (size_t k = 0; k < s.tri_tracks.size(); ++k) {
+                const double *o = c->tout.h + (size_t)(s.tri_off + k) * 4;
+                if (o[3] > 0) {
+                    Track *t = s.tri_tracks[k];
+                    t->life = 1;
+                    set_landmark_point(t, v3(o[0], o[1], o[2]), c->rig);
+                    t->triangulated = true; t->valid = true;
+                }
+            }
+            // initializer.cpp:97-130: frame 0 pose fixed, all landmarks, reprojection + preintegration factors
+            m->frames[0]->fix_pose = true;
+            Builder b{c, &s};
+            for (auto &f : m->frames) b.add_active(f.get());
+            for (auto &f : m->frames)
+                for (size_t j = 0; j < f->keypoint_num(); ++j) {
+                    Track *t = f->tracks[j];
+                    if (!t || !(t->valid && t->triangulated)) continue;
+                    if (f.get() == t->first_frame()) continue;
+                    b.add_rpe(f.get(), t, false);
+                }
+            for (size_t j = 1; j < m->frame_num(); ++j) {
+                Frame *fi = m->frames[j - 1].get(), *fj = m->frames[j].get();
+                if (s.pre_jobs[j - 1] < 0) continue;
+                fetch_pre(c, s.pre_jobs[j - 1], fj->pre);
+                b.add_pre(fi, fj, &fj->pre, false);
+            }
+            s.prob1 = pack_problem(c, s, b, c->prm.solver_iteration_limit);
+            if (s.prob1 < 0) return s.prob1;
+        } else if (s.be_mode == 2) {
+            // mirror_frame tail (:76-79) + localize_newframe (:119-143)
+            Map *m = s.sw_map.get();
+            Frame *fj = s.new_j, *fi = s.new_i;
+            if (s.pre_jobs[0] >= 0) { fetch_pre(c, s.pre_jobs[0], fj->pre); pre_predict(fj->pre, fi->st, fj->st); }
+            Builder b{c, &s};
+            b.add_active(fj);
+            if (s.pre_jobs[0] >= 0) b.add_pre(fi, fj, &fj->pre, true);
+            for (size_t k = 0; k < fj->keypoint_num(); ++k)
+                if (Track *t = fj->tracks[k]) if (t->valid && t->triangulated && t->is_static) b.add_rpe(fj, t, true);
+            (void)m;
+            s.prob1 = pack_problem(c, s, b, c->prm.solver_iteration_limit);
+            if (s.prob1 < 0) return s.prob1;
+        }
+    }
+    { int rc = run_solves(c); if (rc) return rc; }
+    c->tjobs.clear(); c->tviews.clear();
+    for (Session *sp : act) {
+        Session &s = *sp;
+        if (s.prob1 < 0) continue;
+        std::vector<Frame *> pf = s.prob_frames;      // writeback uses the packing order
+        writeback(c, s, s.prob1);
+        if (s.be_mode == 1) {
+            for (auto &f : s.sw_map->frames) f->keyframe = true;
+            c->stats.window_solves++;
+        } else {
+            c->stats.localize_solves++;
+            // ---- manage_keyframe + track_landmark (sliding_window_tracker.cpp:145-245) ----
+            s.is_keyframe = manage_keyframe(c, s);
+            if (s.is_keyframe) {
+                Frame *nj = s.sw_map->frames.back().get();
+                s.tri_tracks.clear(); s.tri_off = (int)c->tjobs.n;
+                for (size_t k = 0; k < nj->keypoint_num(); ++k)
+                    if (Track *t = nj->tracks[k]) if (!t->triangulated) { if (add_tri_job(c, t) < 0) { xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA; } s.tri_tracks.push_back(t); }
+            }
+        }
+    }
+    { int rc = run_triangulation(c); if (rc) return rc; }
+    // ---- phase H: preintegration for refine_window / refine_subwindow ----
+    c->pre_jobs.clear(); c->imu.clear();
+    for (Session *sp : act) {
+        Session &s = *sp;
+        if (s.be_mode != 2) continue;
+        Map *m = s.sw_map.get();
+        s.pre_jobs.clear(); s.pre_job_frames.clear();
+        if (s.is_keyframe) {
+            for (size_t k = 0; k < s.tri_tracks.size(); ++k) {
+                Track *t = s.tri_tracks[k];
+                const double *o = c->tout.h + (size_t)(s.tri_off + k) * 4;
+                if (o[3] > 0) { t->life = 1; set_landmark_point(t, v3(o[0], o[1], o[2]), c->rig); t->triangulated = true; t->valid = true; t->is_static = true; }
+                else { t->inv_depth = -1.0; t->triangulated = false; t->valid = false; }
+            }
+            // refine_window: keyframe_preintegration with the subframes' IMU data merged (:298-321)
+            for (size_t j = 1; j < m->frame_num(); ++j) {
+                Frame *fi = m->frames[j - 1].get(), *fj = m->frames[j].get();
+                fj->kf_imu.clear();
+                for (auto &sf : fi->subframes) fj->kf_imu.insert(fj->kf_imu.end(), sf->imu.begin(), sf->imu.end());
+                fj->kf_imu.insert(fj->kf_imu.end(), fj->imu.begin(), fj->imu.end());
+                s.pre_jobs.push_back(fj->kf_imu.empty() ? -1 : add_preint_job(c, fj->kf_imu, fj->t, fi->st, 3));
+                s.pre_job_frames.push_back(fj);
+            }
+        } else {
+            Frame *frame = m->frames.back().get();
+            if (frame->subframes.empty()) continue;
+            if (frame->subframes[0]->no_translation && frame->subframes.size() >= 9) {
+                // compaction of long pure-rotation runs (:374-391)
+                for (size_t i = frame->subframes.size() / 3; i > 0; --i) {
+                    Frame *tgt = frame->subframes[i * 3 - 1].get();
+                    std::vector<Imu> data;
+                    for (size_t j = i * 3 - 1; j > (i - 1) * 3; --j) {
+                        Frame *src = frame->subframes[j - 1].get();
+                        data.insert(data.begin(), src->imu.begin(), src->imu.end());
+                        map_untrack_frame(m, src, c->rig);
+                        frame->subframes.erase(frame->subframes.begin() + (j - 1));
+                    }
+                    tgt->imu.insert(tgt->imu.begin(), data.begin(), data.end());
+                }
+            }
+            // NOTE: every subframe is integrated with its predecessor's bias *before* the solve (:402-405,:437-441)
+            for (size_t i = 0; i < frame->subframes.size(); ++i) {
+                Frame *sf = frame->subframes[i].get();
+                Frame *prev = i == 0 ? frame : frame->subframes[i - 1].get();
+                s.pre_jobs.push_back(sf->imu.empty() ? -1 : add_preint_job(c, sf->imu, sf->t, prev->st, 3));
+                s.pre_job_frames.push_back(sf);
+            }
+        }
+    }
+    { int rc = run_preint_jobs(c); if (rc) return rc; }
+    // ---- refine_window / refine_subwindow problems ----
+    clear_solve_arenas(c);
+    for (Session *sp : act) {
+        Session &s = *sp;
+        s.prob2 = -1;
+        if (s.be_mode != 2) continue;
+        Map *m = s.sw_map.get();
+        if (s.is_keyframe) {
+            if (!m->marg.present) {
+                // estimation/marginalization_factor.h:18-33: zero information except 1e15 on frame-0 q and p
+                const int K = (int)m->frame_num() - 1;
+                const size_t n = (size_t)15 * K;
+                std::vector<double> a(16 * K + 2 * n * n + n, 0.0);
+                for (int k = 0; k < K; ++k) std::memcpy(&a[16 * k], m->frames[k]->st.d, 16 * sizeof(double));
+                double *S = &a[16 * K], *A0 = S + n * n + n;
+                for (int k = 0; k < 6; ++k) { S[k * n + k] = 1.0e15; A0[k * n + k] = 1.0e30; }
+                m->marg.frames.clear();
+                for (int k = 0; k < K; ++k) m->marg.frames.push_back(m->frames[k].get());
+                m->marg.slot = 0; m->marg.present = true;
+                CKC(cudaMemcpyAsync(c->d_prior + ((size_t)s.idx * 2) * c->prior_stride, a.data(), a.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+                CKC(cudaStreamSynchronize(c->st));
+                c->stats.h2d_bytes += a.size() * sizeof(double);
+            }
+            Builder b{c, &s};
+            for (auto &f : m->frames) b.add_active(f.get());
+            b.use_marg = true;
+            for (auto &f : m->frames)
+                for (size_t j = 0; j < f->keypoint_num(); ++j) {
+                    Track *t = f->tracks[j];
+                    if (!t || !(t->valid && t->triangulated && t->is_static)) continue;
+                    Frame *ff = t->first_frame();
+                    if (!ff->keyframe || f.get() == ff) continue;
+                    b.add_rpe(f.get(), t, false);
+                }
+            for (size_t j = 1; j < m->frame_num(); ++j) {
+                if (s.pre_jobs[j - 1] < 0) continue;
+                Frame *fj = s.pre_job_frames[j - 1];
+                fetch_pre(c, s.pre_jobs[j - 1], fj->kf_pre);
+                b.add_pre(m->frames[j - 1].get(), fj, &fj->kf_pre, false);
+            }
+            s.prob2 = pack_problem(c, s, b, c->prm.solver_iteration_limit);
+            if (s.prob2 < 0) return s.prob2;
+        } else {
+            Frame *frame = m->frames.back().get();
+            if (frame->subframes.empty()) continue;
+            Builder b{c, &s};
+            frame->fix_pose = frame->fix_motion = true;
+            b.add_active(frame);
+            const bool rbranch = frame->subframes[0]->no_translation;
+            for (size_t i = 0; i < frame->subframes.size(); ++i) {
+                Frame *sf = frame->subframes[i].get();
+                Frame *prev = i == 0 ? frame : frame->subframes[i - 1].get();
+                b.add_active(sf);
+                if (s.pre_jobs[i] >= 0) { fetch_pre(c, s.pre_jobs[i], sf->pre); b.add_pre(prev, sf, &sf->pre, false); }
+                if (!rbranch)
+                    for (size_t k = 0; k < sf->keypoint_num(); ++k)
+                        if (Track *t = sf->tracks[k]) if (t->valid && t->triangulated && t->is_static) {
+                            if (t->first_frame()->keyframe) b.add_rpe(sf, t, true);
+                            // else branch (:451-454) is unreachable with the default configuration
+                        }
+            }
+            if (rbranch) {
+                Frame *lastsf = frame->subframes.back().get();
+                for (size_t k = 0; k < lastsf->keypoint_num(); ++k)
+                    if (Track *t = lastsf->tracks[k]) if (t->valid) {
+                        if (t->triangulated) { if (t->is_static) b.add_rpe(lastsf, t, true); }
+                        else b.add_rot(lastsf, t);
+                    }
+            }
+            s.prob2 = pack_problem(c, s, b, c->prm.solver_iteration_limit);
+            frame->fix_pose = frame->fix_motion = false;
+            if (s.prob2 < 0) return s.prob2;
+        }
+    }
+    { int rc = run_solves(c); if (rc) return rc; }
+    for (Session *sp : act) {
+        Session &s = *sp;
+        if (s.prob2 < 0) continue;
+        writeback(c, s, s.prob2);
+        Map *m = s.sw_map.get();
+        if (s.is_keyframe) {
+            c->stats.window_solves++;
+            c->stats.last_window_cost_initial = c->sout.h[s.prob2].initial_cost;
+            c->stats.last_window_cost_final = c->sout.h[s.prob2].final_cost;
+            // validity gates (sliding_window_tracker.cpp:325-357)
+            for (auto &tp : m->tracks) {
+                Track *t = tp.get();
+                if (t->triangulated) {
+                    bool ok = true;
+                    const V3 x = get_landmark_point(t, c->rig);
+                    double rpe = 0.0, cnt = 0.0;
+                    for (auto &r : t->refs) {
+                        Frame *f = r.first;
+                        if (!f->keyframe) continue;
+                        Q4 q; V3 p;
+                        camera_pose(f, c->rig, q, p);
+                        const V3 y = qrot(qconj(q), x - p);
+                        if (!(y.z > 1.0e-3 && y.z <= 50)) { ok = false; break; }
+                        double a[2], bb[2];
+                        apply_k(y, c->K, a); apply_k(f->bearings[r.second], c->K, bb);
+                        rpe += std::sqrt((a[0] - bb[0]) * (a[0] - bb[0]) + (a[1] - bb[1]) * (a[1] - bb[1]));
+                        cnt += 1.0;
+                    }
+                    ok = ok && (rpe / std::max(cnt, 1.0) < 3.0);
+                    t->valid = ok;
+                } else t->inv_depth = -1.0;
+            }
+            for (auto &tp : m->tracks) if (!tp->valid) tp->trash = true;
+        } else c->stats.subwindow_solves++;
+    }
+    // ---- slide_window: marginalise frame 0 while the window is too long (:360-368, map.cpp:51-63) ----
+    while (true) {
+        c->mdesc.clear();
+        clear_solve_arenas(c);
+        size_t scratch = 0;
+        std::vector<Session *> ms;
+        for (Session *sp : act) {
+            Session &s = *sp;
+            if (s.be_mode != 2 || !s.is_keyframe) continue;
+            Map *m = s.sw_map.get();
+            if ((int)m->frame_num() <= c->prm.sliding_window_size) continue;
+            Frame *victim = m->frames[0].get();
+            for (auto &sf : victim->subframes) map_untrack_frame(m, sf.get(), c->rig);
+            const int N = (int)m->frame_num();
+            if (N > XRVIO_MAX_ACTIVE) { xrvio_set_error("window longer than XRVIO_MAX_ACTIVE at marginalisation"); return XRVIO_ERR_LIMIT; }
+            CKC(c->mdesc.reserve(c->mdesc.n + 1)); CKC(c->states.reserve(c->states.n + N * 16));
+            for (int i = 0; i < N; ++i) m->frames[i]->tmp = (i == 0) ? N - 1 : i - 1;       // victim last
+            xvbe::MargDesc d{};
+            d.frame_off = (int)(c->states.n / 16); d.n_frames = N;
+            for (int i = 1; i < N; ++i) { std::memcpy(c->states.h + c->states.n, m->frames[i]->st.d, 128); c->states.n += 16; }
+            std::memcpy(c->states.h + c->states.n, victim->st.d, 128); c->states.n += 16;
+            // observations of the victim's valid tracks whose first frame is a keyframe (:234-256)
+            std::vector<Track *> lms;
+            std::vector<xvbe::RpeObs> obs;
+            for (size_t j = 0; j < victim->keypoint_num(); ++j) {
+                Track *t = victim->tracks[j];
+                if (!t || !t->valid) continue;
+                Frame *ref = t->first_frame();
+                if (!ref->keyframe || ref->map != m) continue;
+                const int lm = (int)lms.size();
+                bool used = false;
+                for (auto &r : t->refs) {
+                    Frame *tg = r.first;
+                    if (tg == ref || tg->map != m) continue;         // subframes are not in frame_indices
+                    xvbe::RpeObs o{};
+                    o.tgt = (short)tg->tmp; o.ref = (short)ref->tmp; o.lm = lm; o.prior = 0;
+                    st3(o.zt, tg->bearings[r.second]); st3(o.zr, ref->bearings[t->refs.front().second]);
+                    obs.push_back(o);
+                    used = true;
+                }
+                if (used) lms.push_back(t);
+            }
+            std::stable_sort(obs.begin(), obs.end(), [](const xvbe::RpeObs &x, const xvbe::RpeObs &y) { return x.tgt != y.tgt ? x.tgt < y.tgt : x.ref < y.ref; });
+            CKC(c->invd.reserve(c->invd.n + lms.size() + 1)); CKC(c->rpe.reserve(c->rpe.n + obs.size() + 1));
+            CKC(c->pref.reserve(c->pref.n + 2)); CKC(c->pblocks.reserve(c->pblocks.n + 2 * XRVIO_PRE_BLOCK)); CKC(c->mframes.reserve(c->mframes.n + N));
+            d.lm_off = (int)c->invd.n; d.n_lm = (int)lms.size();
+            for (Track *t : lms) c->invd.push(t->inv_depth);
+            d.rpe_off = (int)c->rpe.n; d.n_rpe = (int)obs.size();
+            for (auto &o : obs) c->rpe.push(o);
+            d.pre_off = (int)c->pref.n; d.n_pre = 0;
+            if (N > 1 && !m->frames[1]->kf_pre.empty()) {
+                xvbe::PreRef r{};
+                r.i = (short)victim->tmp; r.j = (short)m->frames[1]->tmp; r.prior = 0; r.block = (int)(c->pblocks.n / XRVIO_PRE_BLOCK);
+                std::memcpy(c->pblocks.h + c->pblocks.n, m->frames[1]->kf_pre.data(), XRVIO_PRE_BLOCK * sizeof(double)); c->pblocks.n += XRVIO_PRE_BLOCK;
+                c->pref.push(r);
+                d.n_pre = 1;
+            }
+            d.marg_k = (int)m->marg.frames.size(); d.marg_frames_off = (int)c->mframes.n;
+            for (Frame *f : m->marg.frames) c->mframes.push(f->tmp);
+            d.marg_off = (long long)(((size_t)s.idx * 2 + m->marg.slot) * c->prior_stride);
+            d.out_off = (long long)(((size_t)s.idx * 2 + (1 - m->marg.slot)) * c->prior_stride);
+            d.scratch_off = (long long)scratch;
+            scratch += xvbe::marg_scratch_doubles(N, d.n_lm);
+            for (int i = 0; i < N; ++i) m->frames[i]->tmp = -1;
+            c->mdesc.push(d);
+            ms.push_back(&s);
+        }
+        if (ms.empty()) break;
+        const int nm = (int)ms.size();
+        CKC(c->scratch.reserve(scratch * sizeof(double)));
+        CKC(c->mrank.reserve(nm));
+        CKC(cudaMemcpyAsync(c->mdesc.d, c->mdesc.h, nm * sizeof(xvbe::MargDesc), cudaMemcpyHostToDevice, c->st));
+        CKC(cudaMemcpyAsync(c->states.d, c->states.h, c->states.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        if (c->invd.n) CKC(cudaMemcpyAsync(c->invd.d, c->invd.h, c->invd.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        if (c->rpe.n) CKC(cudaMemcpyAsync(c->rpe.d, c->rpe.h, c->rpe.n * sizeof(xvbe::RpeObs), cudaMemcpyHostToDevice, c->st));
+        if (c->pref.n) CKC(cudaMemcpyAsync(c->pref.d, c->pref.h, c->pref.n * sizeof(xvbe::PreRef), cudaMemcpyHostToDevice, c->st));
+        if (c->pblocks.n) CKC(cudaMemcpyAsync(c->pblocks.d, c->pblocks.h, c->pblocks.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        CKC(cudaMemcpyAsync(c->mframes.d, c->mframes.h, c->mframes.n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+        c->stats.h2d_bytes += nm * sizeof(xvbe::MargDesc) + c->states.n * 8 + c->invd.n * 8 + c->rpe.n * sizeof(xvbe::RpeObs) + c->pblocks.n * 8;
+        xvbe::MargBatch mb;
+        mb.desc = c->mdesc.d; mb.states = c->states.d; mb.inv_depth = c->invd.d; mb.rpe = c->rpe.d; mb.pre = c->pref.d; mb.pre_blocks = c->pblocks.d;
+        mb.marg_frames = c->mframes.d; mb.marg = c->d_prior; mb.out = c->d_prior; mb.scratch = c->scratch.as<double>(); mb.rank_out = c->mrank.d;
+        xvbe::marginalize(mb, nm, c->rig_d, c->st);
+        c->stats.kernels_launched += 1;
+        CKC(cudaGetLastError());
+        CKC(cudaMemcpyAsync(c->mrank.h, c->mrank.d, nm * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CKC(cudaStreamSynchronize(c->st));
+        c->stats.d2h_bytes += nm * sizeof(int);
+        for (Session *sp : ms) {
+            Session &s = *sp;
+            Map *m = s.sw_map.get();
+            Frame *victim = m->frames[0].get();
+            m->marg.slot = 1 - m->marg.slot;
+            m->marg.frames.clear();
+            for (size_t i = 1; i < m->frame_num(); ++i) m->marg.frames.push_back(m->frames[i].get());
+            for (size_t i = 0; i < victim->keypoint_num(); ++i)
+                if (Track *t = victim->tracks[i]) track_remove_keypoint(t, victim, c->rig);
+            m->frames.pop_front();
+            c->stats.marginalizations++;
+        }
+    }
+    // ---- FrontendWorker latest state (frontend_worker.cpp:48-51,72-75) ----
+    for (Session *sp : act) {
+        Session &s = *sp;
+        if (s.be_mode == 0 || !s.sw_map) continue;
+        Map *m = s.sw_map.get();
+        Frame *f = m->frames.back().get();
+        if (!f->subframes.empty()) f = f->subframes.back().get();
+        s.has_swt_latest = true; s.swt_t = f->t; s.swt_frame_id = s.ft_map.frames.back()->id; s.swt_state = f->st;
+    }
+    return XRVIO_OK;
+}
+
+}  // namespace
+
+extern "C" int xrvio_step(xrvio_ctx *c) {
+    if (!c) { xrvio_set_error("xrvio_step: null context"); return XRVIO_ERR_ARG; }
+    CKC(cudaSetDevice(c->device));
+    while (true) {
+        std::vector<Session *> act;
+        for (auto &s : c->ses) if (!s.released.empty()) act.push_back(&s);
+        if (act.empty()) break;
+        int rc = front_end_round(c, act);
+        if (rc) return rc;
+        rc = back_end_round(c, act);
+        if (rc) return rc;
+    }
+    CKC(cudaStreamSynchronize(c->st));
+    return XRVIO_OK;
+}
