@@ -207,6 +207,11 @@ int xrvio_get_latest_state(xrvio_ctx *ctx, int session, double *t, double state1
 int xrvio_get_state(xrvio_ctx *ctx, int session);                           /* XRVIO_STATE_* or < 0 */
 int xrvio_get_landmarks(xrvio_ctx *ctx, int session, double *xyz, int capacity);   /* returns count */
 int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *stats);
+/* Per-kernel-family device time measured with CUDA events on the launch stream (off by default).
+ * Families: 0 clahe 1 pyramid 2 gftt 3 klt 4 poisson 5 preintegration 6 solve 7 marginalize 8 triangulate.
+ * Returns the number of families. */
+int xrvio_set_profiling(xrvio_ctx *ctx, int enable);
+int xrvio_get_kernel_times(xrvio_ctx *ctx, double *ms, long long *launches, int capacity);
 
 #ifdef __cplusplus
 }

@@ -267,6 +267,17 @@ class Context:
         n = lib.xrvio_get_landmarks(self._h, int(session), _p(xyz), capacity)
         return xyz[:min(n, capacity)]
 
+    KERNEL_FAMILIES = ('clahe', 'pyramid', 'gftt', 'klt', 'poisson', 'preintegrate', 'solve', 'marginalize', 'triangulate')
+
+    def set_profiling(self, on=True):
+        lib.check(lib.xrvio_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        ms = np.zeros(16)
+        ln = np.zeros(16, np.int64)
+        n = lib.xrvio_get_kernel_times(self._h, _p(ms), _p(ln), 16)
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(self.KERNEL_FAMILIES[:n])}
+
     def stats(self):
         s = np.zeros(1, stats_dtype)
         lib.check(lib.xrvio_get_stats(self._h, _p(s)))

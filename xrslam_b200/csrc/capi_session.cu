@@ -139,6 +139,13 @@ struct xrvio_ctx {
     Arena<xvbe::MargDesc> mdesc; Arena<int> mrank;
     Arena<xvbe::TriJob> tjobs; Arena<double> tviews; Arena<double> tout;
     DevOnly scratch;
+    // ---- optional per-kernel-family timing with CUDA events on the launch stream ----
+    bool prof = false;
+    struct ProfEv { int fam; cudaEvent_t a, b; };
+    std::vector<ProfEv> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[16] = {0};
+    long long prof_launches[16] = {0};
     double *d_prior = nullptr;         // S * 2 * prior_stride doubles, device-resident priors
     size_t prior_stride = 0;
     std::vector<double> prior_init_h;
@@ -147,6 +154,31 @@ struct xrvio_ctx {
 namespace {
 
 inline long long tkey(double t) { return (long long)std::llround(t * 1e6); }
+
+// kernel families for xrvio_get_kernel_times
+enum { FAM_CLAHE = 0, FAM_PYRAMID, FAM_GFTT, FAM_KLT, FAM_POISSON, FAM_PREINT, FAM_SOLVE, FAM_MARG, FAM_TRI, FAM_COUNT };
+cudaEvent_t prof_event(xrvio_ctx *c) {
+    if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+    xrvio_ctx *c; int fam; int launches; cudaEvent_t a{};
+    ProfScope(xrvio_ctx *c_, int fam_, int launches_) : c(c_), fam(fam_), launches(launches_) {
+        if (c->prof) { a = prof_event(c); cudaEventRecord(a, c->st); }
+    }
+    ~ProfScope() {
+        c->prof_launches[fam] += launches;
+        if (c->prof) { cudaEvent_t b = prof_event(c); cudaEventRecord(b, c->st); c->prof_pending.push_back({fam, a, b}); }
+    }
+};
+void prof_collect(xrvio_ctx *c) {     // call after the stream has been synchronised
+    for (auto &e : c->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->prof_ms[e.fam] += ms;
+        c->prof_pool.push_back(e.a); c->prof_pool.push_back(e.b);
+    }
+    c->prof_pending.clear();
+}
 
 // ---------------------------------------------------------------------------------------------
 // Detail::predict_pose + propagate_state (detail.cpp:15-28,144-177)
@@ -210,7 +242,7 @@ int run_preint_jobs(xrvio_ctx *c) {
     CKC(c->pre_out.reserve((size_t)n * XRVIO_PRE_BLOCK));
     CKC(cudaMemcpyAsync(c->pre_jobs.d, c->pre_jobs.h, n * sizeof(xvbe::PreintJob), cudaMemcpyHostToDevice, c->st));
     CKC(cudaMemcpyAsync(c->imu.d, c->imu.h, c->imu.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    xvbe::preintegrate(c->pre_jobs.d, n, c->imu.d, c->rig_d, c->pre_out.d, c->st);
+    { ProfScope ps(c, FAM_PREINT, 1); xvbe::preintegrate(c->pre_jobs.d, n, c->imu.d, c->rig_d, c->pre_out.d, c->st); }
     c->stats.kernels_launched += 1;
     CKC(cudaMemcpyAsync(c->pre_out.h, c->pre_out.d, (size_t)n * XRVIO_PRE_BLOCK * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CKC(cudaStreamSynchronize(c->st));
@@ -343,7 +375,7 @@ int run_solves(xrvio_ctx *c) {
     b.desc = c->sdesc.d; b.states = c->states.d; b.frame_flags = c->fflags.d; b.inv_depth = c->invd.d; b.rpe = c->rpe.d; b.rot = c->rot.d;
     b.pre = c->pref.d; b.pre_blocks = c->pblocks.d; b.marg_frames = c->mframes.d; b.marg = c->d_prior; b.scratch = c->scratch.as<double>();
     b.out = c->sout.d;
-    xvbe::solve(b, n, c->rig_d, c->st);
+    { ProfScope ps(c, FAM_SOLVE, 1); xvbe::solve(b, n, c->rig_d, c->st); }
     c->stats.kernels_launched += 1;
     CKC(cudaGetLastError());
     CKC(cudaMemcpyAsync(c->states.h, c->states.d, c->states.n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
@@ -523,6 +555,18 @@ int xrvio_get_landmarks(xrvio_ctx *c, int session, double *xyz, int capacity) {
             n++;
         }
     return n;
+}
+int xrvio_set_profiling(xrvio_ctx *c, int enable) {
+    if (!c) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    c->prof = enable != 0;
+    return XRVIO_OK;
+}
+int xrvio_get_kernel_times(xrvio_ctx *c, double *ms, long long *launches, int capacity) {
+    if (!c || !ms || !launches) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    cudaStreamSynchronize(c->st);
+    prof_collect(c);
+    for (int k = 0; k < capacity && k < 16; ++k) { ms[k] = c->prof_ms[k]; launches[k] = c->prof_launches[k]; }
+    return FAM_COUNT;
 }
 int xrvio_get_stats(xrvio_ctx *c, xrvio_stats *st) {
     if (!c || !st) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }

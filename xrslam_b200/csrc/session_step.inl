@@ -18,8 +18,9 @@ int run_poisson(xrvio_ctx *c, int n, bool with_veto) {
     CKC(cudaMemcpyAsync(c->poi_npre.d, c->poi_npre.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
     CKC(cudaMemcpyAsync(c->poi_ntot.d, c->poi_ntot.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
     if (with_veto) CKC(cudaMemcpyAsync(c->poi_veto.d, c->poi_veto.h, pb, cudaMemcpyHostToDevice, c->st));
-    xvfe::poisson_filter(c->poi_pts.d, c->poi_npre.d, c->poi_ntot.d, with_veto ? c->poi_veto.d : nullptr, c->poi_keep.d, n,
-                         c->prm.min_keypoint_distance, c->st);
+    { ProfScope ps(c, FAM_POISSON, 1);
+      xvfe::poisson_filter(c->poi_pts.d, c->poi_npre.d, c->poi_ntot.d, with_veto ? c->poi_veto.d : nullptr, c->poi_keep.d, n,
+                           c->prm.min_keypoint_distance, c->st); }
     c->stats.kernels_launched += 1;
     CKC(cudaMemcpyAsync(c->poi_keep.h, c->poi_keep.d, pb, cudaMemcpyDeviceToHost, c->st));
     CKC(cudaStreamSynchronize(c->st));
@@ -78,11 +79,13 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
     }
     CKC(cudaMemcpyAsync(B.idx_raw.d, B.idx_raw.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
     CKC(cudaMemcpyAsync(B.idx_next.d, B.idx_next.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
-    xvfe::clahe(c->d_raw, B.idx_raw.d, P, c->d_pyr, B.idx_next.d, c->L.total, c->d_lut, n, w, h, c->prm.clahe_clip_limit,
-                c->prm.clahe_width, c->prm.clahe_height, c->st);
-    xvfe::pyramid(c->d_pyr, B.idx_next.d, n, c->L, c->st);
-    xvfe::gftt_harris(c->d_pyr, B.idx_next.d, c->L.total, n, w, h, c->prm.max_keypoint_detection, 1.0e-3f, 20.0f, c->corners.d,
-                      c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->st);
+    { ProfScope ps(c, FAM_CLAHE, 2);
+      xvfe::clahe(c->d_raw, B.idx_raw.d, P, c->d_pyr, B.idx_next.d, c->L.total, c->d_lut, n, w, h, c->prm.clahe_clip_limit,
+                  c->prm.clahe_width, c->prm.clahe_height, c->st); }
+    { ProfScope ps(c, FAM_PYRAMID, 3); xvfe::pyramid(c->d_pyr, B.idx_next.d, n, c->L, c->st); }
+    { ProfScope ps(c, FAM_GFTT, 3);
+      xvfe::gftt_harris(c->d_pyr, B.idx_next.d, c->L.total, n, w, h, c->prm.max_keypoint_detection, 1.0e-3f, 20.0f, c->corners.d,
+                        c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->st); }
     c->stats.kernels_launched += 2 + 3 + 3;
     CKC(cudaMemcpyAsync(c->corners.h, c->corners.d, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     CKC(cudaMemcpyAsync(c->corner_count.h, c->corner_count.d, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -130,7 +133,8 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
         CKC(cudaMemcpyAsync(c->klt_next.d, c->klt_next.h, pb, cudaMemcpyHostToDevice, c->st));
         CKC(cudaMemcpyAsync(c->klt_n.d, c->klt_n.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
         CKC(cudaMemcpyAsync(B.idx_prev.d, B.idx_prev.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
-        xvfe::klt_track(c->d_pyr, c->d_pyr, B.idx_prev.d, B.idx_next.d, n, c->L, c->klt_prev.d, c->klt_next.d, c->klt_n.d, c->klt_status.d, c->st);
+        { ProfScope ps(c, FAM_KLT, 1);
+          xvfe::klt_track(c->d_pyr, c->d_pyr, B.idx_prev.d, B.idx_next.d, n, c->L, c->klt_prev.d, c->klt_next.d, c->klt_n.d, c->klt_status.d, c->st); }
         c->stats.kernels_launched += 1;
         CKC(cudaMemcpyAsync(c->klt_next.h, c->klt_next.d, pb, cudaMemcpyDeviceToHost, c->st));
         CKC(cudaMemcpyAsync(c->klt_status.h, c->klt_status.d, (size_t)n * xvfe::kMaxPts, cudaMemcpyDeviceToHost, c->st));
@@ -262,7 +266,7 @@ int run_triangulation(xrvio_ctx *c) {
     CKC(c->tout.reserve((size_t)n * 4));
     CKC(cudaMemcpyAsync(c->tjobs.d, c->tjobs.h, n * sizeof(xvbe::TriJob), cudaMemcpyHostToDevice, c->st));
     CKC(cudaMemcpyAsync(c->tviews.d, c->tviews.h, c->tviews.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    xvbe::triangulate(c->tjobs.d, n, c->tviews.d, c->tout.d, c->st);
+    { ProfScope ps(c, FAM_TRI, 1); xvbe::triangulate(c->tjobs.d, n, c->tviews.d, c->tout.d, c->st); }
     c->stats.kernels_launched += 1;
     CKC(cudaMemcpyAsync(c->tout.h, c->tout.d, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CKC(cudaStreamSynchronize(c->st));
@@ -742,7 +746,7 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
         xvbe::MargBatch mb;
         mb.desc = c->mdesc.d; mb.states = c->states.d; mb.inv_depth = c->invd.d; mb.rpe = c->rpe.d; mb.pre = c->pref.d; mb.pre_blocks = c->pblocks.d;
         mb.marg_frames = c->mframes.d; mb.marg = c->d_prior; mb.out = c->d_prior; mb.scratch = c->scratch.as<double>(); mb.rank_out = c->mrank.d;
-        xvbe::marginalize(mb, nm, c->rig_d, c->st);
+        { ProfScope ps(c, FAM_MARG, 1); xvbe::marginalize(mb, nm, c->rig_d, c->st); }
         c->stats.kernels_launched += 1;
         CKC(cudaGetLastError());
         CKC(cudaMemcpyAsync(c->mrank.h, c->mrank.d, nm * sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -786,6 +790,7 @@ extern "C" int xrvio_step(xrvio_ctx *c) {
         if (rc) return rc;
         rc = back_end_round(c, act);
         if (rc) return rc;
+        if (c->prof) prof_collect(c);
     }
     CKC(cudaStreamSynchronize(c->st));
     return XRVIO_OK;
