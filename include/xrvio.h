@@ -212,6 +212,8 @@ int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *stats);
  * Returns the number of families. */
 int xrvio_set_profiling(xrvio_ctx *ctx, int enable);
 int xrvio_get_kernel_times(xrvio_ctx *ctx, double *ms, long long *launches, int capacity);
+/* Host wall time accumulated per internal step phase (diagnostics; up to 32 slots). */
+int xrvio_get_phase_times(xrvio_ctx *ctx, double *ms, int capacity);
 
 #ifdef __cplusplus
 }

@@ -278,6 +278,11 @@ class Context:
         n = lib.xrvio_get_kernel_times(self._h, _p(ms), _p(ln), 16)
         return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(self.KERNEL_FAMILIES[:n])}
 
+    def phase_times(self):
+        ms = np.zeros(32)
+        lib.xrvio_get_phase_times(self._h, _p(ms), 32)
+        return ms
+
     def stats(self):
         s = np.zeros(1, stats_dtype)
         lib.check(lib.xrvio_get_stats(self._h, _p(s)))

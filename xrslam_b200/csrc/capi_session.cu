@@ -13,6 +13,10 @@
 #include "backend.cuh"
 #include "frontend.cuh"
 #include "session_host.hpp"
+#include "thread_pool.hpp"
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <unordered_set>
@@ -69,8 +73,28 @@ struct DevOnly {
 constexpr int kImgQueue = 4;       // frames per session that may wait on the device between steps
 constexpr int kPyrSlots = 3;       // pyramid buffers per session (previous, next, spare)
 
+// Per-session staging written by worker threads, merged into the batch arenas by the main thread.
+struct Staged {
+    std::vector<xvbe::PreintJob> pj; std::vector<double> imu;       // imu_off is session-local until merged
+    std::vector<xvbe::TriJob> tj; std::vector<double> tv;
+    bool has_prob = false;
+    xvbe::SolveDesc d{};
+    std::vector<double> states, invd, pblocks;
+    std::vector<unsigned char> flags;
+    std::vector<xvbe::RpeObs> rpe; std::vector<xvbe::RotObs> rot; std::vector<xvbe::PreRef> pref;
+    std::vector<int> mframes;
+    // marginalisation job
+    bool has_marg = false;
+    xvbe::MargDesc md{};
+    void clear_jobs() { pj.clear(); imu.clear(); tj.clear(); tv.clear(); }
+    void clear_prob() { has_prob = false; has_marg = false; states.clear(); invd.clear(); pblocks.clear(); flags.clear(); rpe.clear(); rot.clear(); pref.clear(); mframes.clear(); }
+};
+
 struct Session {
     int idx = 0;
+    Staged stg;
+    int rc = 0; std::string err;
+    int pre_base = 0, tri_base = 0;               // global index of this session's first staged job after a merge
     Map ft_map;                                   // FeatureTracker::map
     std::unique_ptr<Map> sw_map;                  // SlidingWindowTracker::map (null while INITIALIZING)
     std::deque<std::unique_ptr<Frame>> queued;    // Detail::frames (waiting for IMU)
@@ -100,6 +124,7 @@ struct Session {
     bool is_keyframe = false;
     Frame *new_i = nullptr, *new_j = nullptr;
     int prob1 = -1, prob2 = -1, marg_job = -1;
+    std::vector<int> sort_cnt;
     std::vector<Frame *> prob_frames;             // frame order of the last built problem
     std::vector<Track *> prob_tracks;
     std::vector<Track *> tri_tracks; int tri_off = 0;
@@ -120,6 +145,7 @@ struct xrvio_ctx {
     double K[4];
     double sic[2];
     std::vector<Session> ses;
+    std::unique_ptr<ThreadPool> pool;
     xrvio_stats stats{};
     // ---- device image / front-end buffers ----
     uint8_t *d_raw = nullptr;          // S * kImgQueue * w*h
@@ -145,6 +171,7 @@ struct xrvio_ctx {
     std::vector<ProfEv> prof_pending;
     std::vector<cudaEvent_t> prof_pool;
     double prof_ms[16] = {0};
+    double phase_ms[32] = {0};         // host wall time per step phase (diagnostics)
     long long prof_launches[16] = {0};
     double *d_prior = nullptr;         // S * 2 * prior_stride doubles, device-resident priors
     size_t prior_stride = 0;
@@ -154,6 +181,12 @@ struct xrvio_ctx {
 namespace {
 
 inline long long tkey(double t) { return (long long)std::llround(t * 1e6); }
+
+struct PhaseTimer {
+    xrvio_ctx *c; int id; std::chrono::steady_clock::time_point t0;
+    PhaseTimer(xrvio_ctx *c_, int id_) : c(c_), id(id_), t0(std::chrono::steady_clock::now()) {}
+    ~PhaseTimer() { c->phase_ms[id] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 // kernel families for xrvio_get_kernel_times
 enum { FAM_CLAHE = 0, FAM_PYRAMID, FAM_GFTT, FAM_KLT, FAM_POISSON, FAM_PREINT, FAM_SOLVE, FAM_MARG, FAM_TRI, FAM_COUNT };
@@ -222,18 +255,32 @@ void pre_predict(const std::vector<double> &pb, const State16 &a, State16 &b) {
     for (int k = 0; k < 6; ++k) b.d[10 + k] = a.d[10 + k];
 }
 
-int add_preint_job(xrvio_ctx *c, const std::vector<Imu> &data, double t_end, const State16 &bias_from, int flags) {
-    if (c->pre_jobs.reserve(c->pre_jobs.n + 1) != cudaSuccess) return -1;
-    if (c->imu.reserve(c->imu.n + data.size() * 7 + 7) != cudaSuccess) return -1;
+// stage a preintegration job in the session (thread-safe across sessions); returns the session-local index
+int add_preint_job(Session &s, const std::vector<Imu> &data, double t_end, const State16 &bias_from, int flags) {
     xvbe::PreintJob j{};
-    j.imu_off = (int)(c->imu.n / 7); j.n = (int)data.size(); j.flags = flags; j.t_end = t_end;
+    j.imu_off = (int)(s.stg.imu.size() / 7); j.n = (int)data.size(); j.flags = flags; j.t_end = t_end;
     for (int k = 0; k < 3; ++k) { j.bg[k] = bias_from.d[10 + k]; j.ba[k] = bias_from.d[13 + k]; }
     for (const Imu &m : data) {
-        double *o = c->imu.h + c->imu.n;
-        o[0] = m.t; o[1] = m.w.x; o[2] = m.w.y; o[3] = m.w.z; o[4] = m.a.x; o[5] = m.a.y; o[6] = m.a.z;
-        c->imu.n += 7;
+        const double o[7] = {m.t, m.w.x, m.w.y, m.w.z, m.a.x, m.a.y, m.a.z};
+        s.stg.imu.insert(s.stg.imu.end(), o, o + 7);
     }
-    return (int)c->pre_jobs.push(j);
+    s.stg.pj.push_back(j);
+    return (int)s.stg.pj.size() - 1;
+}
+// merge the staged preintegration jobs of the active sessions into the batch arenas
+int merge_preint_jobs(xrvio_ctx *c, std::vector<Session *> &act) {
+    c->pre_jobs.clear(); c->imu.clear();
+    size_t nj = 0, ni = 0;
+    for (Session *s : act) { nj += s->stg.pj.size(); ni += s->stg.imu.size(); }
+    if (c->pre_jobs.reserve(nj + 1) != cudaSuccess || c->imu.reserve(ni + 7) != cudaSuccess) { xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA; }
+    for (Session *s : act) {
+        s->pre_base = (int)c->pre_jobs.n;
+        const int imu_base = (int)(c->imu.n / 7);
+        for (xvbe::PreintJob j : s->stg.pj) { j.imu_off += imu_base; c->pre_jobs.push(j); }
+        if (!s->stg.imu.empty()) { std::memcpy(c->imu.h + c->imu.n, s->stg.imu.data(), s->stg.imu.size() * sizeof(double)); c->imu.n += s->stg.imu.size(); }
+        s->stg.pj.clear(); s->stg.imu.clear();
+    }
+    return XRVIO_OK;
 }
 
 int run_preint_jobs(xrvio_ctx *c) {
@@ -283,66 +330,106 @@ struct Builder {
     void add_pre(Frame *i, Frame *j, const std::vector<double> *blk, bool prior) { touch(i); touch(j); pre.push_back({i, j, prior, blk}); }
 };
 
-// Packs one problem into the batch arenas.  Returns the problem index or < 0.
+// Packs one problem into the session's staging buffers (thread-safe across sessions).  Returns 0 or < 0.
 int pack_problem(xrvio_ctx *c, Session &s, Builder &b, int max_iterations) {
+    Staged &g = s.stg;
+    g.clear_prob();
     // a frame is active (gets columns) iff it was added with add_frame_states and has a free block
-    std::vector<Frame *> frames;
+    std::vector<Frame *> &frames = s.prob_frames;
+    frames.clear();
     for (Frame *f : b.active) if (!(f->fix_pose && f->fix_motion)) frames.push_back(f);
     const int n_active = (int)frames.size();
     for (Frame *f : b.active) if (f->fix_pose && f->fix_motion) frames.push_back(f);
     for (Frame *f : b.consts) frames.push_back(f);
-    if (n_active > XRVIO_MAX_ACTIVE || (int)frames.size() > XRVIO_MAX_FRAMES) { xrvio_set_error("solve problem exceeds XRVIO_MAX_ACTIVE / XRVIO_MAX_FRAMES"); return XRVIO_ERR_LIMIT; }
+    if (n_active > XRVIO_MAX_ACTIVE || (int)frames.size() > XRVIO_MAX_FRAMES) { s.err = "solve problem exceeds XRVIO_MAX_ACTIVE / XRVIO_MAX_FRAMES"; return XRVIO_ERR_LIMIT; }
     for (size_t i = 0; i < frames.size(); ++i) frames[i]->tmp = (int)i;
-    std::vector<Track *> lms = b.free_lm;
+    std::vector<Track *> &lms = s.prob_tracks;
+    lms = b.free_lm;
     lms.insert(lms.end(), b.const_lm.begin(), b.const_lm.end());
     for (size_t i = 0; i < lms.size(); ++i) lms[i]->tmp = (int)i;
-    if (c->sdesc.reserve(c->sdesc.n + 1) != cudaSuccess || c->states.reserve(c->states.n + frames.size() * 16) != cudaSuccess ||
-        c->fflags.reserve(c->fflags.n + frames.size()) != cudaSuccess || c->invd.reserve(c->invd.n + lms.size() + 1) != cudaSuccess ||
-        c->rpe.reserve(c->rpe.n + b.rpe.size() + 1) != cudaSuccess || c->rot.reserve(c->rot.n + b.rot.size() + 1) != cudaSuccess ||
-        c->pref.reserve(c->pref.n + b.pre.size() + 1) != cudaSuccess || c->pblocks.reserve(c->pblocks.n + (b.pre.size() + 1) * XRVIO_PRE_BLOCK) != cudaSuccess ||
-        c->mframes.reserve(c->mframes.n + XRVIO_MAX_ACTIVE) != cudaSuccess) { xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA; }
     xvbe::SolveDesc d{};
-    d.frame_off = (int)(c->states.n / 16); d.n_frames = (int)frames.size(); d.n_active = n_active;
-    d.lm_off = (int)c->invd.n; d.n_lm = (int)lms.size(); d.n_lm_free = (int)b.free_lm.size();
-    for (Frame *f : frames) {
-        std::memcpy(c->states.h + c->states.n, f->st.d, 16 * sizeof(double)); c->states.n += 16;
-        c->fflags.push((unsigned char)((f->fix_pose ? 0 : 1) | (f->fix_motion ? 0 : 2)));
+    d.n_frames = (int)frames.size(); d.n_active = n_active;
+    d.n_lm = (int)lms.size(); d.n_lm_free = (int)b.free_lm.size();
+    g.states.resize(frames.size() * 16);
+    g.flags.resize(frames.size());
+    for (size_t i = 0; i < frames.size(); ++i) {
+        std::memcpy(&g.states[i * 16], frames[i]->st.d, 16 * sizeof(double));
+        g.flags[i] = (unsigned char)((frames[i]->fix_pose ? 0 : 1) | (frames[i]->fix_motion ? 0 : 2));
     }
-    for (Track *t : lms) c->invd.push(t->inv_depth);
-    // reprojection residuals sorted by (tgt, ref)
-    std::vector<xvbe::RpeObs> obs(b.rpe.size());
-    for (size_t k = 0; k < b.rpe.size(); ++k) {
-        const Builder::R &r = b.rpe[k];
-        xvbe::RpeObs o{};
-        o.tgt = (short)r.tgt->tmp; o.ref = (short)r.ref->tmp; o.lm = r.tr->tmp; o.prior = r.prior ? 1 : 0;
-        st3(o.zt, r.zt); st3(o.zr, r.zr);
-        obs[k] = o;
+    g.invd.resize(lms.size());
+    for (size_t i = 0; i < lms.size(); ++i) g.invd[i] = lms[i]->inv_depth;
+    // reprojection residuals ordered by (tgt, ref): counting sort over the (<= 96 x 96) key space
+    const int nf = (int)frames.size();
+    g.rpe.resize(b.rpe.size());
+    {
+        std::vector<int> &cnt = s.sort_cnt;
+        cnt.assign((size_t)nf * nf + 1, 0);
+        for (const Builder::R &r : b.rpe) cnt[(size_t)r.tgt->tmp * nf + r.ref->tmp + 1]++;
+        for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+        for (const Builder::R &r : b.rpe) {
+            xvbe::RpeObs &o = g.rpe[cnt[(size_t)r.tgt->tmp * nf + r.ref->tmp]++];
+            o.tgt = (short)r.tgt->tmp; o.ref = (short)r.ref->tmp; o.lm = r.tr->tmp; o.prior = r.prior ? 1 : 0; o.pad = 0;
+            st3(o.zt, r.zt); st3(o.zr, r.zr);
+        }
     }
-    std::stable_sort(obs.begin(), obs.end(), [](const xvbe::RpeObs &x, const xvbe::RpeObs &y) { return x.tgt != y.tgt ? x.tgt < y.tgt : x.ref < y.ref; });
-    d.rpe_off = (int)c->rpe.n; d.n_rpe = (int)obs.size();
-    for (auto &o : obs) c->rpe.push(o);
-    d.rot_off = (int)c->rot.n; d.n_rot = (int)b.rot.size();
-    for (auto &r : b.rot) { xvbe::RotObs o{}; o.tgt = (short)r.tgt->tmp; o.ref = (short)r.ref->tmp; st3(o.zt, r.zt); st3(o.zr, r.zr); c->rot.push(o); }
-    d.pre_off = (int)c->pref.n; d.n_pre = (int)b.pre.size();
-    for (auto &p : b.pre) {
+    d.n_rpe = (int)g.rpe.size();
+    d.n_rot = (int)b.rot.size();
+    for (auto &r : b.rot) { xvbe::RotObs o{}; o.tgt = (short)r.tgt->tmp; o.ref = (short)r.ref->tmp; st3(o.zt, r.zt); st3(o.zr, r.zr); g.rot.push_back(o); }
+    d.n_pre = (int)b.pre.size();
+    g.pblocks.resize(b.pre.size() * XRVIO_PRE_BLOCK);
+    for (size_t k = 0; k < b.pre.size(); ++k) {
+        const Builder::P &p = b.pre[k];
         xvbe::PreRef r{};
-        r.i = (short)p.i->tmp; r.j = (short)p.j->tmp; r.prior = p.prior ? 1 : 0; r.block = (int)(c->pblocks.n / XRVIO_PRE_BLOCK);
-        std::memcpy(c->pblocks.h + c->pblocks.n, p.blk->data(), XRVIO_PRE_BLOCK * sizeof(double)); c->pblocks.n += XRVIO_PRE_BLOCK;
-        c->pref.push(r);
+        r.i = (short)p.i->tmp; r.j = (short)p.j->tmp; r.prior = p.prior ? 1 : 0; r.block = (int)k;
+        std::memcpy(&g.pblocks[k * XRVIO_PRE_BLOCK], p.blk->data(), XRVIO_PRE_BLOCK * sizeof(double));
+        g.pref.push_back(r);
     }
     if (b.use_marg) {
         Map *m = s.sw_map.get();
         d.marg_k = (int)m->marg.frames.size();
-        d.marg_frames_off = (int)c->mframes.n;
-        for (Frame *f : m->marg.frames) c->mframes.push(f->tmp);
+        for (Frame *f : m->marg.frames) g.mframes.push_back(f->tmp);
         d.marg_off = (long long)(((size_t)s.idx * 2 + m->marg.slot) * c->prior_stride);
     }
     d.max_iterations = max_iterations;
-    s.prob_frames = frames;
-    s.prob_tracks = lms;
     for (Frame *f : frames) f->tmp = -1;
     for (Track *t : lms) t->tmp = -1;
-    return (int)c->sdesc.push(d);
+    g.d = d;
+    g.has_prob = true;
+    return 0;
+}
+
+// merge the staged problems of the active sessions into the batch arenas; sets s.probN (global index or -1)
+int merge_problems(xrvio_ctx *c, std::vector<Session *> &act, int which) {
+    size_t nst = 0, nl = 0, nr = 0, nro = 0, np = 0, npb = 0, nmf = 0, nprob = 0;
+    for (Session *s : act) {
+        const Staged &g = s->stg;
+        if (!g.has_prob) continue;
+        nprob++; nst += g.states.size(); nl += g.invd.size(); nr += g.rpe.size(); nro += g.rot.size(); np += g.pref.size(); npb += g.pblocks.size(); nmf += g.mframes.size();
+    }
+    c->sdesc.clear(); c->states.clear(); c->fflags.clear(); c->invd.clear(); c->rpe.clear(); c->rot.clear(); c->pref.clear(); c->pblocks.clear(); c->mframes.clear();
+    if (c->sdesc.reserve(nprob + 1) != cudaSuccess || c->states.reserve(nst + 16) != cudaSuccess || c->fflags.reserve(nst / 16 + 1) != cudaSuccess ||
+        c->invd.reserve(nl + 1) != cudaSuccess || c->rpe.reserve(nr + 1) != cudaSuccess || c->rot.reserve(nro + 1) != cudaSuccess ||
+        c->pref.reserve(np + 1) != cudaSuccess || c->pblocks.reserve(npb + XRVIO_PRE_BLOCK) != cudaSuccess || c->mframes.reserve(nmf + 1) != cudaSuccess) {
+        xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA;
+    }
+    for (Session *sp : act) {
+        Session &s = *sp;
+        Staged &g = s.stg;
+        int &slot = which == 1 ? s.prob1 : s.prob2;
+        slot = -1;
+        if (!g.has_prob) continue;
+        xvbe::SolveDesc d = g.d;
+        d.frame_off = (int)(c->states.n / 16); d.lm_off = (int)c->invd.n; d.rpe_off = (int)c->rpe.n; d.rot_off = (int)c->rot.n;
+        d.pre_off = (int)c->pref.n; d.marg_frames_off = (int)c->mframes.n;
+        const int blk_base = (int)(c->pblocks.n / XRVIO_PRE_BLOCK);
+        auto app = [](auto &arena, const auto &v) { if (!v.empty()) { std::memcpy(arena.h + arena.n, v.data(), v.size() * sizeof(v[0])); arena.n += v.size(); } };
+        app(c->states, g.states); app(c->fflags, g.flags); app(c->invd, g.invd); app(c->rpe, g.rpe); app(c->rot, g.rot);
+        for (xvbe::PreRef r : g.pref) { r.block += blk_base; c->pref.push(r); }
+        app(c->pblocks, g.pblocks); app(c->mframes, g.mframes);
+        slot = (int)c->sdesc.push(d);
+        g.has_prob = false;
+    }
+    return XRVIO_OK;
 }
 
 void clear_solve_arenas(xrvio_ctx *c) {
@@ -459,6 +546,12 @@ int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **
     CKC(cudaMalloc((void **)&c->d_prior, (size_t)S * 2 * c->prior_stride * sizeof(double)));
     CKC(cudaMemset(c->d_prior, 0, (size_t)S * 2 * c->prior_stride * sizeof(double)));
     c->ses.resize(S);
+    {
+        unsigned hc = std::thread::hardware_concurrency();
+        int nt = (int)std::min<unsigned>(hc ? hc : 4u, 32u);
+        if (const char *e = std::getenv("XRVIO_HOST_THREADS")) nt = std::max(1, std::atoi(e));
+        c->pool = std::make_unique<ThreadPool>(std::min(nt, S));
+    }
     for (int i = 0; i < S; ++i) { c->ses[i].idx = i; c->ses[i].ft_map.track_id_counter = &c->ses[i].track_id_counter; }
     *out = c;
     return XRVIO_OK;
@@ -506,6 +599,7 @@ int xrvio_push_imu(xrvio_ctx *c, const int *session, const xrvio_imu *samples, i
 int xrvio_push_images(xrvio_ctx *c, const int *session, const uint8_t *const *data, const int *stride, const double *t, int n, int on_device) {
     if (!c || !session || !data || !t || n < 0) { xrvio_set_error("xrvio_push_images: bad argument"); return XRVIO_ERR_ARG; }
     CKC(cudaSetDevice(c->device));
+    PhaseTimer pt_(c, 30);
     const int w = c->prm.width, h = c->prm.height;
     for (int i = 0; i < n; ++i) {
         if (session[i] < 0 || session[i] >= c->S) { xrvio_set_error("bad session"); return XRVIO_ERR_ARG; }
@@ -567,6 +661,11 @@ int xrvio_get_kernel_times(xrvio_ctx *c, double *ms, long long *launches, int ca
     prof_collect(c);
     for (int k = 0; k < capacity && k < 16; ++k) { ms[k] = c->prof_ms[k]; launches[k] = c->prof_launches[k]; }
     return FAM_COUNT;
+}
+int xrvio_get_phase_times(xrvio_ctx *c, double *ms, int capacity) {
+    if (!c || !ms) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    for (int k = 0; k < capacity && k < 32; ++k) ms[k] = c->phase_ms[k];
+    return 32;
 }
 int xrvio_get_stats(xrvio_ctx *c, xrvio_stats *st) {
     if (!c || !st) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }

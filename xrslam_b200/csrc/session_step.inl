@@ -12,6 +12,14 @@ StepBuffers &sb(xrvio_ctx *c) {
     return *p;
 }
 
+// run body(i) for every active session on the host thread pool; first error wins
+template <class F> int for_sessions(xrvio_ctx *c, std::vector<Session *> &act, F body) {
+    for (Session *s : act) s->rc = 0;
+    c->pool->parallel_for((int)act.size(), [&](int i) { if (act[i]->rc == 0) { int rc = body(i, *act[i]); if (rc) act[i]->rc = rc; } });
+    for (Session *s : act) if (s->rc) { xrvio_set_error(s->err.empty() ? "session error" : s->err); return s->rc; }
+    return XRVIO_OK;
+}
+
 int run_poisson(xrvio_ctx *c, int n, bool with_veto) {
     const size_t pb = (size_t)n * xvfe::kMaxPts;
     CKC(cudaMemcpyAsync(c->poi_pts.d, c->poi_pts.h, pb * 2 * sizeof(double), cudaMemcpyHostToDevice, c->st));
@@ -38,10 +46,10 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
     const size_t P = (size_t)w * h;
     StepBuffers &B = sb(c);
     CKC(B.idx_raw.reserve(n)); CKC(B.idx_next.reserve(n)); CKC(B.idx_prev.reserve(n));
+    PhaseTimer *pt = new PhaseTimer(c, 0);
     // ---- phase A: CLAHE + pyramid + GFTT on the new image; preintegration (no Jacobian / covariance) ----
-    c->pre_jobs.clear(); c->imu.clear();
-    for (int i = 0; i < n; ++i) {
-        Session &s = *act[i];
+    { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
+        s.stg.clear_jobs();
         s.cur = std::move(s.released.front());
         s.released.pop_front();
         Frame *f = s.cur.get();
@@ -60,7 +68,7 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
                 long idx = s.ft_map.frame_index_by_id(s.swt_frame_id);
                 if (idx >= 0) {
                     s.ft_map.frames[idx]->st = s.swt_state;
-                    if ((size_t)idx + 1 != s.ft_map.frame_num()) { xrvio_set_error("front end ran ahead of the back end (asynchronous mode is not supported)"); return XRVIO_ERR_STATE; }
+                    if ((size_t)idx + 1 != s.ft_map.frame_num()) { s.err = "front end ran ahead of the back end (asynchronous mode is not supported)"; return XRVIO_ERR_STATE; }
                 } else s.has_latest = false;
             }
             // IMU stitching (feature_tracker.cpp:77-88)
@@ -72,11 +80,12 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
                 }
             }
             if (!f->imu.empty()) {
-                s.pre_job = add_preint_job(c, f->imu, f->t, s.last->st, 0);
-                if (s.pre_job < 0) { xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA; }
+                s.pre_job = add_preint_job(s, f->imu, f->t, s.last->st, 0);
             }
         }
-    }
+        return 0; }); if (rc) return rc; }
+    { int rc = merge_preint_jobs(c, act); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 1);
     CKC(cudaMemcpyAsync(B.idx_raw.d, B.idx_raw.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
     CKC(cudaMemcpyAsync(B.idx_next.d, B.idx_next.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
     { ProfScope ps(c, FAM_CLAHE, 2);
@@ -93,18 +102,18 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
     { int rc = run_preint_jobs(c); if (rc) return rc; }     // also synchronises the stream
     if (c->pre_jobs.n == 0) CKC(cudaStreamSynchronize(c->st));
     CKC(cudaGetLastError());
+    delete pt; pt = new PhaseTimer(c, 2);
     // ---- phase B: pyramidal LK (previous pyramid -> new pyramid), gyro-predicted initial guess ----
-    int n_klt = 0;
-    for (int i = 0; i < n; ++i) {
-        Session &s = *act[i];
+    std::atomic<int> n_klt_a{0};
+    { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
         Frame *f = s.cur.get();
         c->klt_n.h[i] = 0;
         B.idx_prev.h[i] = B.idx_next.h[i];
-        if (!s.fe_has_last) continue;
-        if (s.pre_job >= 0) fetch_pre(c, s.pre_job, f->pre); else f->pre.assign(XRVIO_PRE_BLOCK, 0.0);
+        if (!s.fe_has_last) return 0;
+        if (s.pre_job >= 0) fetch_pre(c, s.pre_base + s.pre_job, f->pre); else f->pre.assign(XRVIO_PRE_BLOCK, 0.0);
         Frame *last = s.last;
         const int np = (int)last->keypoint_num();
-        if (np > xvfe::kMaxPts) { xrvio_set_error("more than XRVIO_MAX_PTS keypoints in a frame"); return XRVIO_ERR_LIMIT; }
+        if (np > xvfe::kMaxPts) { s.err = "more than XRVIO_MAX_PTS keypoints in a frame"; return XRVIO_ERR_LIMIT; }
         c->klt_n.h[i] = np;
         B.idx_prev.h[i] = s.idx * kPyrSlots + last->pyr_slot;
         s.klt_next.assign((size_t)np * 2, 0.0);
@@ -125,8 +134,10 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
             nn[0] = (float)pr[0]; nn[1] = (float)pr[1];
             s.klt_next[2 * k] = pr[0]; s.klt_next[2 * k + 1] = pr[1];
         }
-        n_klt += np;
-    }
+        n_klt_a += np;
+    return 0; }); if (rc) return rc; }
+    const int n_klt = n_klt_a.load();
+    delete pt; pt = new PhaseTimer(c, 3);
     if (n_klt > 0) {
         const size_t pb = (size_t)n * xvfe::kMaxPts * 2 * sizeof(float);
         CKC(cudaMemcpyAsync(c->klt_prev.d, c->klt_prev.h, pb, cudaMemcpyHostToDevice, c->st));
@@ -142,12 +153,12 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
         c->stats.h2d_bytes += 2 * pb + 2 * n * sizeof(int);
         c->stats.d2h_bytes += pb + (size_t)n * xvfe::kMaxPts;
     }
+    delete pt; pt = new PhaseTimer(c, 4);
     // ---- phase C: Frame::track_keypoints after the LK call (frame.cpp:99-173) ----
-    bool any_track = false;
-    for (int i = 0; i < n; ++i) {
-        Session &s = *act[i];
+    std::atomic<int> any_track_a{0};
+    { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
         c->poi_npre.h[i] = 0; c->poi_ntot.h[i] = 0;
-        if (!s.fe_has_last) continue;
+        if (!s.fe_has_last) return 0;
         Frame *f = s.cur.get();
         Frame *last = s.last;
         const int np = (int)last->keypoint_num();
@@ -181,7 +192,7 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
             s.order.emplace_back(k, (int)tr->keypoint_num());
         }
         std::stable_sort(s.order.begin(), s.order.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.second > b.second; });
-        if ((int)s.order.size() > xvfe::kMaxPts) { xrvio_set_error("too many tracked keypoints"); return XRVIO_ERR_LIMIT; }
+        if ((int)s.order.size() > xvfe::kMaxPts) { s.err = "too many tracked keypoints"; return XRVIO_ERR_LIMIT; }
         c->poi_ntot.h[i] = (int)s.order.size();
         for (size_t q = 0; q < s.order.size(); ++q) {
             const int k = s.order[q].first;
@@ -190,12 +201,14 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
             Track *tr = last->tracks[k];
             c->poi_veto.h[(size_t)i * xvfe::kMaxPts + q] = (tr && tr->trash) ? 1 : 0;
         }
-        any_track = any_track || !s.order.empty();
-    }
+        if (!s.order.empty()) any_track_a = 1;
+    return 0; }); if (rc) return rc; }
+    const bool any_track = any_track_a.load() != 0;
+    delete pt; pt = new PhaseTimer(c, 5);
     if (any_track) { int rc = run_poisson(c, n, true); if (rc) return rc; }
-    for (int i = 0; i < n; ++i) {
-        Session &s = *act[i];
-        if (!s.fe_has_last) continue;
+    delete pt; pt = new PhaseTimer(c, 6);
+    { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
+        if (!s.fe_has_last) return 0;
         Frame *f = s.cur.get();
         Frame *last = s.last;
         const int np = (int)last->keypoint_num();
@@ -215,14 +228,14 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
             pre_predict(f->pre, last->st, f->st);
             s.has_latest = true; s.latest_t = f->t; s.latest = f->st;
         }
-    }
+        return 0; }); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 7);
     // ---- phase D: Frame::detect_keypoints (frame.cpp:55-72, opencv_image.cpp:46-72) ----
-    for (int i = 0; i < n; ++i) {
-        Session &s = *act[i];
+    { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
         Frame *f = s.cur.get();
         const int npre = (int)f->keypoint_num();
         const int nc = c->corner_count.h[i];
-        if (npre + nc > xvfe::kMaxPts) { xrvio_set_error("too many keypoints for the Poisson filter"); return XRVIO_ERR_LIMIT; }
+        if (npre + nc > xvfe::kMaxPts) { s.err = "too many keypoints for the Poisson filter"; return XRVIO_ERR_LIMIT; }
         c->poi_npre.h[i] = npre; c->poi_ntot.h[i] = npre + nc;
         for (int k = 0; k < npre; ++k) apply_k(f->bearings[k], c->K, c->poi_pts.h + ((size_t)i * xvfe::kMaxPts + k) * 2);
         // GFTT corners arrive strongest first; std::sort by response (opencv_image.cpp:47-50) keeps that order
@@ -232,10 +245,11 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
             pp[0] = (double)cr[0]; pp[1] = (double)cr[1];
         }
         s.n_corners = nc;
-    }
+        return 0; }); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 8);
     { int rc = run_poisson(c, n, false); if (rc) return rc; }
-    for (int i = 0; i < n; ++i) {
-        Session &s = *act[i];
+    delete pt; pt = new PhaseTimer(c, 9);
+    { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
         Frame *f = s.cur.get();
         const int npre = c->poi_npre.h[i];
         for (int k = 0; k < s.n_corners; ++k) {
@@ -252,8 +266,9 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
             map_untrack_frame(&s.ft_map, s.ft_map.frames[0].get(), c->rig);
             s.ft_map.detach_frame(0);
         }
-        c->stats.frames_processed++;
-    }
+    return 0; }); if (rc) return rc; }
+    c->stats.frames_processed += n;
+    delete pt;
     return XRVIO_OK;
 }
 
@@ -274,18 +289,30 @@ int run_triangulation(xrvio_ctx *c) {
     c->stats.d2h_bytes += (size_t)n * 4 * sizeof(double);
     return XRVIO_OK;
 }
-int add_tri_job(xrvio_ctx *c, Track *tr) {          // Track::triangulate input (track.cpp:46-62)
-    if (c->tjobs.reserve(c->tjobs.n + 1) != cudaSuccess || c->tviews.reserve(c->tviews.n + tr->refs.size() * 16) != cudaSuccess) return -1;
-    xvbe::TriJob j{(int)(c->tviews.n / 16), (int)tr->refs.size()};
+void add_tri_job(xrvio_ctx *c, Session &s, Track *tr) {          // Track::triangulate input (track.cpp:46-62), staged
+    xvbe::TriJob j{(int)(s.stg.tv.size() / 16), (int)tr->refs.size()};
     for (auto &r : tr->refs) {
         Q4 q; V3 p;
         camera_pose(r.first, c->rig, q, p);
-        double *o = c->tviews.h + c->tviews.n;
+        double o[16] = {0};
         st4(o, q); st3(o + 4, p); st3(o + 7, r.first->bearings[r.second]);
-        for (int k = 10; k < 16; ++k) o[k] = 0;
-        c->tviews.n += 16;
+        s.stg.tv.insert(s.stg.tv.end(), o, o + 16);
     }
-    return (int)c->tjobs.push(j);
+    s.stg.tj.push_back(j);
+}
+int merge_tri_jobs(xrvio_ctx *c, std::vector<Session *> &act) {
+    c->tjobs.clear(); c->tviews.clear();
+    size_t nj = 0, nv = 0;
+    for (Session *s : act) { nj += s->stg.tj.size(); nv += s->stg.tv.size(); }
+    if (c->tjobs.reserve(nj + 1) != cudaSuccess || c->tviews.reserve(nv + 16) != cudaSuccess) { xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA; }
+    for (Session *s : act) {
+        s->tri_base = (int)c->tjobs.n;
+        const int vb = (int)(c->tviews.n / 16);
+        for (xvbe::TriJob j : s->stg.tj) { j.obs_off += vb; c->tjobs.push(j); }
+        if (!s->stg.tv.empty()) { std::memcpy(c->tviews.h + c->tviews.n, s->stg.tv.data(), s->stg.tv.size() * sizeof(double)); c->tviews.n += s->stg.tv.size(); }
+        s->stg.tj.clear(); s->stg.tv.clear();
+    }
+    return XRVIO_OK;
 }
 
 // Initializer::mirror_keyframe_map (initializer.cpp:22-76) + ground-truth states
@@ -400,46 +427,49 @@ bool manage_keyframe(xrvio_ctx *c, Session &s) {
 namespace {
 
 int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
+    PhaseTimer *pt = new PhaseTimer(c, 10);
     // ---- phase E: mirror + preintegration with Jacobians and covariance ----
-    c->pre_jobs.clear(); c->imu.clear();
-    for (Session *sp : act) {
-        Session &s = *sp;
+    { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
+        s.stg.clear_jobs();
         s.be_mode = 0; s.pre_jobs.clear(); s.pre_job_frames.clear(); s.prob1 = s.prob2 = -1; s.is_keyframe = false;
         const long long frame_id = s.ft_map.frames.back()->id;
         if (!s.sw_map) {
-            if (!bootstrap_mirror(c, s, frame_id)) continue;
+            if (!bootstrap_mirror(c, s, frame_id)) return 0;
             s.be_mode = 1;
             Map *m = s.sw_map.get();
             for (size_t j = 1; j < m->frame_num(); ++j) {
                 Frame *fi = m->frames[j - 1].get(), *fj = m->frames[j].get();
-                if (fj->imu.empty()) { s.pre_jobs.push_back(-1); continue; }
-                s.pre_jobs.push_back(add_preint_job(c, fj->imu, fj->t, fi->st, 3));
+                s.pre_jobs.push_back(fj->imu.empty() ? -1 : add_preint_job(s, fj->imu, fj->t, fi->st, 3));
             }
         } else {
             s.be_mode = 2;
-            if (!mirror_frame(c, s, frame_id)) { s.be_mode = 3; continue; }     // frame slid out: track() still runs
-            s.pre_jobs.push_back(s.new_j->imu.empty() ? -1 : add_preint_job(c, s.new_j->imu, s.new_j->t, s.new_i->st, 3));
+            if (!mirror_frame(c, s, frame_id)) { s.be_mode = 3; return 0; }
+            s.pre_jobs.push_back(s.new_j->imu.empty() ? -1 : add_preint_job(s, s.new_j->imu, s.new_j->t, s.new_i->st, 3));
         }
-    }
+        return 0; }); if (rc) return rc; }
+    { int rc = merge_preint_jobs(c, act); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 11);
     { int rc = run_preint_jobs(c); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 12);
     // ---- phase F: bootstrap triangulation; localize / initial BA problems ----
-    c->tjobs.clear(); c->tviews.clear();
-    for (Session *sp : act) {
-        Session &s = *sp;
-        if (s.be_mode != 1) continue;
-        Map *m = s.sw_map.get();
-        s.tri_tracks.clear(); s.tri_off = (int)c->tjobs.n;
-        for (auto &t : m->tracks)
-            if (t->keypoint_num() >= 2) { if (add_tri_job(c, t.get()) < 0) { xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA; } s.tri_tracks.push_back(t.get()); }
+    bool any_boot = false;
+    for (Session *sp : act) any_boot = any_boot || sp->be_mode == 1;
+    if (any_boot) {
+        { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
+            if (s.be_mode != 1) return 0;
+            s.tri_tracks.clear();
+            for (auto &t : s.sw_map->tracks)
+                if (t->keypoint_num() >= 2) { add_tri_job(c, s, t.get()); s.tri_tracks.push_back(t.get()); }
+            return 0; }); if (rc) return rc; }
+        { int rc = merge_tri_jobs(c, act); if (rc) return rc; }
+        { int rc = run_triangulation(c); if (rc) return rc; }
     }
-    { int rc = run_triangulation(c); if (rc) return rc; }
-    clear_solve_arenas(c);
-    for (Session *sp : act) {
-        Session &s = *sp;
+    { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
+        s.stg.clear_prob();
         if (s.be_mode == 1) {
             Map *m = s.sw_map.get();
             for (size_t k = 0; k < s.tri_tracks.size(); ++k) {
-                const double *o = c->tout.h + (size_t)(s.tri_off + k) * 4;
+                const double *o = c->tout.h + (size_t)(s.tri_base + k) * 4;
                 if (o[3] > 0) {
                     Track *t = s.tri_tracks[k];
                     t->life = 1;
@@ -461,60 +491,60 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
             for (size_t j = 1; j < m->frame_num(); ++j) {
                 Frame *fi = m->frames[j - 1].get(), *fj = m->frames[j].get();
                 if (s.pre_jobs[j - 1] < 0) continue;
-                fetch_pre(c, s.pre_jobs[j - 1], fj->pre);
+                fetch_pre(c, s.pre_base + s.pre_jobs[j - 1], fj->pre);
                 b.add_pre(fi, fj, &fj->pre, false);
             }
-            s.prob1 = pack_problem(c, s, b, c->prm.solver_iteration_limit);
-            if (s.prob1 < 0) return s.prob1;
+            return pack_problem(c, s, b, c->prm.solver_iteration_limit);
         } else if (s.be_mode == 2) {
             // mirror_frame tail (:76-79) + localize_newframe (:119-143)
-            Map *m = s.sw_map.get();
             Frame *fj = s.new_j, *fi = s.new_i;
-            if (s.pre_jobs[0] >= 0) { fetch_pre(c, s.pre_jobs[0], fj->pre); pre_predict(fj->pre, fi->st, fj->st); }
+            if (s.pre_jobs[0] >= 0) { fetch_pre(c, s.pre_base + s.pre_jobs[0], fj->pre); pre_predict(fj->pre, fi->st, fj->st); }
             Builder b{c, &s};
             b.add_active(fj);
             if (s.pre_jobs[0] >= 0) b.add_pre(fi, fj, &fj->pre, true);
             for (size_t k = 0; k < fj->keypoint_num(); ++k)
                 if (Track *t = fj->tracks[k]) if (t->valid && t->triangulated && t->is_static) b.add_rpe(fj, t, true);
-            (void)m;
-            s.prob1 = pack_problem(c, s, b, c->prm.solver_iteration_limit);
-            if (s.prob1 < 0) return s.prob1;
+            return pack_problem(c, s, b, c->prm.solver_iteration_limit);
         }
-    }
+        return 0; }); if (rc) return rc; }
+    { int rc = merge_problems(c, act, 1); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 13);
     { int rc = run_solves(c); if (rc) return rc; }
-    c->tjobs.clear(); c->tviews.clear();
-    for (Session *sp : act) {
-        Session &s = *sp;
-        if (s.prob1 < 0) continue;
-        std::vector<Frame *> pf = s.prob_frames;      // writeback uses the packing order
+    delete pt; pt = new PhaseTimer(c, 14);
+    std::atomic<long long> n_win{0}, n_loc{0}, n_sub{0};
+    { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
+        s.stg.clear_jobs();
+        if (s.prob1 < 0) return 0;
         writeback(c, s, s.prob1);
         if (s.be_mode == 1) {
             for (auto &f : s.sw_map->frames) f->keyframe = true;
-            c->stats.window_solves++;
+            n_win++;
         } else {
-            c->stats.localize_solves++;
+            n_loc++;
             // ---- manage_keyframe + track_landmark (sliding_window_tracker.cpp:145-245) ----
             s.is_keyframe = manage_keyframe(c, s);
             if (s.is_keyframe) {
                 Frame *nj = s.sw_map->frames.back().get();
-                s.tri_tracks.clear(); s.tri_off = (int)c->tjobs.n;
+                s.tri_tracks.clear();
                 for (size_t k = 0; k < nj->keypoint_num(); ++k)
-                    if (Track *t = nj->tracks[k]) if (!t->triangulated) { if (add_tri_job(c, t) < 0) { xrvio_set_error("arena allocation failed"); return XRVIO_ERR_CUDA; } s.tri_tracks.push_back(t); }
+                    if (Track *t = nj->tracks[k]) if (!t->triangulated) { add_tri_job(c, s, t); s.tri_tracks.push_back(t); }
             }
         }
-    }
+        return 0; }); if (rc) return rc; }
+    { int rc = merge_tri_jobs(c, act); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 15);
     { int rc = run_triangulation(c); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 16);
     // ---- phase H: preintegration for refine_window / refine_subwindow ----
-    c->pre_jobs.clear(); c->imu.clear();
-    for (Session *sp : act) {
-        Session &s = *sp;
-        if (s.be_mode != 2) continue;
+    { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
+        s.stg.clear_jobs();
+        if (s.be_mode != 2) return 0;
         Map *m = s.sw_map.get();
         s.pre_jobs.clear(); s.pre_job_frames.clear();
         if (s.is_keyframe) {
             for (size_t k = 0; k < s.tri_tracks.size(); ++k) {
                 Track *t = s.tri_tracks[k];
-                const double *o = c->tout.h + (size_t)(s.tri_off + k) * 4;
+                const double *o = c->tout.h + (size_t)(s.tri_base + k) * 4;
                 if (o[3] > 0) { t->life = 1; set_landmark_point(t, v3(o[0], o[1], o[2]), c->rig); t->triangulated = true; t->valid = true; t->is_static = true; }
                 else { t->inv_depth = -1.0; t->triangulated = false; t->valid = false; }
             }
@@ -524,12 +554,12 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
                 fj->kf_imu.clear();
                 for (auto &sf : fi->subframes) fj->kf_imu.insert(fj->kf_imu.end(), sf->imu.begin(), sf->imu.end());
                 fj->kf_imu.insert(fj->kf_imu.end(), fj->imu.begin(), fj->imu.end());
-                s.pre_jobs.push_back(fj->kf_imu.empty() ? -1 : add_preint_job(c, fj->kf_imu, fj->t, fi->st, 3));
+                s.pre_jobs.push_back(fj->kf_imu.empty() ? -1 : add_preint_job(s, fj->kf_imu, fj->t, fi->st, 3));
                 s.pre_job_frames.push_back(fj);
             }
         } else {
             Frame *frame = m->frames.back().get();
-            if (frame->subframes.empty()) continue;
+            if (frame->subframes.empty()) return 0;
             if (frame->subframes[0]->no_translation && frame->subframes.size() >= 9) {
                 // compaction of long pure-rotation runs (:374-391)
                 for (size_t i = frame->subframes.size() / 3; i > 0; --i) {
@@ -544,39 +574,43 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
                     tgt->imu.insert(tgt->imu.begin(), data.begin(), data.end());
                 }
             }
-            // NOTE: every subframe is integrated with its predecessor's bias *before* the solve (:402-405,:437-441)
+            // every subframe is integrated with its predecessor's bias before the solve (:402-405,:437-441)
             for (size_t i = 0; i < frame->subframes.size(); ++i) {
                 Frame *sf = frame->subframes[i].get();
                 Frame *prev = i == 0 ? frame : frame->subframes[i - 1].get();
-                s.pre_jobs.push_back(sf->imu.empty() ? -1 : add_preint_job(c, sf->imu, sf->t, prev->st, 3));
+                s.pre_jobs.push_back(sf->imu.empty() ? -1 : add_preint_job(s, sf->imu, sf->t, prev->st, 3));
                 s.pre_job_frames.push_back(sf);
             }
         }
-    }
+        return 0; }); if (rc) return rc; }
+    { int rc = merge_preint_jobs(c, act); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 17);
     { int rc = run_preint_jobs(c); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 18);
     // ---- refine_window / refine_subwindow problems ----
-    clear_solve_arenas(c);
+    // initial priors (estimation/marginalization_factor.h:18-33): zero information except 1e15 on frame-0 q and p
     for (Session *sp : act) {
         Session &s = *sp;
-        s.prob2 = -1;
-        if (s.be_mode != 2) continue;
+        if (s.be_mode != 2 || !s.is_keyframe || s.sw_map->marg.present) continue;
+        Map *m = s.sw_map.get();
+        const int K = (int)m->frame_num() - 1;
+        const size_t n = (size_t)15 * K;
+        std::vector<double> a(16 * K + 2 * n * n + n, 0.0);
+        for (int k = 0; k < K; ++k) std::memcpy(&a[16 * k], m->frames[k]->st.d, 16 * sizeof(double));
+        double *S = &a[16 * K], *A0 = S + n * n + n;
+        for (int k = 0; k < 6; ++k) { S[k * n + k] = 1.0e15; A0[k * n + k] = 1.0e30; }
+        m->marg.frames.clear();
+        for (int k = 0; k < K; ++k) m->marg.frames.push_back(m->frames[k].get());
+        m->marg.slot = 0; m->marg.present = true;
+        CKC(cudaMemcpyAsync(c->d_prior + ((size_t)s.idx * 2) * c->prior_stride, a.data(), a.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        CKC(cudaStreamSynchronize(c->st));
+        c->stats.h2d_bytes += a.size() * sizeof(double);
+    }
+    { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
+        s.stg.clear_prob();
+        if (s.be_mode != 2) return 0;
         Map *m = s.sw_map.get();
         if (s.is_keyframe) {
-            if (!m->marg.present) {
-                // estimation/marginalization_factor.h:18-33: zero information except 1e15 on frame-0 q and p
-                const int K = (int)m->frame_num() - 1;
-                const size_t n = (size_t)15 * K;
-                std::vector<double> a(16 * K + 2 * n * n + n, 0.0);
-                for (int k = 0; k < K; ++k) std::memcpy(&a[16 * k], m->frames[k]->st.d, 16 * sizeof(double));
-                double *S = &a[16 * K], *A0 = S + n * n + n;
-                for (int k = 0; k < 6; ++k) { S[k * n + k] = 1.0e15; A0[k * n + k] = 1.0e30; }
-                m->marg.frames.clear();
-                for (int k = 0; k < K; ++k) m->marg.frames.push_back(m->frames[k].get());
-                m->marg.slot = 0; m->marg.present = true;
-                CKC(cudaMemcpyAsync(c->d_prior + ((size_t)s.idx * 2) * c->prior_stride, a.data(), a.size() * sizeof(double), cudaMemcpyHostToDevice, c->st));
-                CKC(cudaStreamSynchronize(c->st));
-                c->stats.h2d_bytes += a.size() * sizeof(double);
-            }
             Builder b{c, &s};
             for (auto &f : m->frames) b.add_active(f.get());
             b.use_marg = true;
@@ -591,109 +625,107 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
             for (size_t j = 1; j < m->frame_num(); ++j) {
                 if (s.pre_jobs[j - 1] < 0) continue;
                 Frame *fj = s.pre_job_frames[j - 1];
-                fetch_pre(c, s.pre_jobs[j - 1], fj->kf_pre);
+                fetch_pre(c, s.pre_base + s.pre_jobs[j - 1], fj->kf_pre);
                 b.add_pre(m->frames[j - 1].get(), fj, &fj->kf_pre, false);
             }
-            s.prob2 = pack_problem(c, s, b, c->prm.solver_iteration_limit);
-            if (s.prob2 < 0) return s.prob2;
-        } else {
-            Frame *frame = m->frames.back().get();
-            if (frame->subframes.empty()) continue;
-            Builder b{c, &s};
-            frame->fix_pose = frame->fix_motion = true;
-            b.add_active(frame);
-            const bool rbranch = frame->subframes[0]->no_translation;
-            for (size_t i = 0; i < frame->subframes.size(); ++i) {
-                Frame *sf = frame->subframes[i].get();
-                Frame *prev = i == 0 ? frame : frame->subframes[i - 1].get();
-                b.add_active(sf);
-                if (s.pre_jobs[i] >= 0) { fetch_pre(c, s.pre_jobs[i], sf->pre); b.add_pre(prev, sf, &sf->pre, false); }
-                if (!rbranch)
-                    for (size_t k = 0; k < sf->keypoint_num(); ++k)
-                        if (Track *t = sf->tracks[k]) if (t->valid && t->triangulated && t->is_static) {
-                            if (t->first_frame()->keyframe) b.add_rpe(sf, t, true);
-                            // else branch (:451-454) is unreachable with the default configuration
-                        }
-            }
-            if (rbranch) {
-                Frame *lastsf = frame->subframes.back().get();
-                for (size_t k = 0; k < lastsf->keypoint_num(); ++k)
-                    if (Track *t = lastsf->tracks[k]) if (t->valid) {
-                        if (t->triangulated) { if (t->is_static) b.add_rpe(lastsf, t, true); }
-                        else b.add_rot(lastsf, t);
-                    }
-            }
-            s.prob2 = pack_problem(c, s, b, c->prm.solver_iteration_limit);
-            frame->fix_pose = frame->fix_motion = false;
-            if (s.prob2 < 0) return s.prob2;
+            return pack_problem(c, s, b, c->prm.solver_iteration_limit);
         }
-    }
+        Frame *frame = m->frames.back().get();
+        if (frame->subframes.empty()) return 0;
+        Builder b{c, &s};
+        frame->fix_pose = frame->fix_motion = true;
+        b.add_active(frame);
+        const bool rbranch = frame->subframes[0]->no_translation;
+        for (size_t i = 0; i < frame->subframes.size(); ++i) {
+            Frame *sf = frame->subframes[i].get();
+            Frame *prev = i == 0 ? frame : frame->subframes[i - 1].get();
+            b.add_active(sf);
+            if (s.pre_jobs[i] >= 0) { fetch_pre(c, s.pre_base + s.pre_jobs[i], sf->pre); b.add_pre(prev, sf, &sf->pre, false); }
+            if (!rbranch)
+                for (size_t k = 0; k < sf->keypoint_num(); ++k)
+                    if (Track *t = sf->tracks[k]) if (t->valid && t->triangulated && t->is_static) {
+                        if (t->first_frame()->keyframe) b.add_rpe(sf, t, true);
+                        // else branch (:451-454) is unreachable with the default configuration
+                    }
+        }
+        if (rbranch) {
+            Frame *lastsf = frame->subframes.back().get();
+            for (size_t k = 0; k < lastsf->keypoint_num(); ++k)
+                if (Track *t = lastsf->tracks[k]) if (t->valid) {
+                    if (t->triangulated) { if (t->is_static) b.add_rpe(lastsf, t, true); }
+                    else b.add_rot(lastsf, t);
+                }
+        }
+        const int rc2 = pack_problem(c, s, b, c->prm.solver_iteration_limit);
+        frame->fix_pose = frame->fix_motion = false;
+        return rc2; }); if (rc) return rc; }
+    { int rc = merge_problems(c, act, 2); if (rc) return rc; }
+    delete pt; pt = new PhaseTimer(c, 19);
     { int rc = run_solves(c); if (rc) return rc; }
-    for (Session *sp : act) {
-        Session &s = *sp;
-        if (s.prob2 < 0) continue;
+    delete pt; pt = new PhaseTimer(c, 20);
+    { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
+        if (s.prob2 < 0) return 0;
         writeback(c, s, s.prob2);
         Map *m = s.sw_map.get();
-        if (s.is_keyframe) {
-            c->stats.window_solves++;
-            c->stats.last_window_cost_initial = c->sout.h[s.prob2].initial_cost;
-            c->stats.last_window_cost_final = c->sout.h[s.prob2].final_cost;
-            // validity gates (sliding_window_tracker.cpp:325-357)
-            for (auto &tp : m->tracks) {
-                Track *t = tp.get();
-                if (t->triangulated) {
-                    bool ok = true;
-                    const V3 x = get_landmark_point(t, c->rig);
-                    double rpe = 0.0, cnt = 0.0;
-                    for (auto &r : t->refs) {
-                        Frame *f = r.first;
-                        if (!f->keyframe) continue;
-                        Q4 q; V3 p;
-                        camera_pose(f, c->rig, q, p);
-                        const V3 y = qrot(qconj(q), x - p);
-                        if (!(y.z > 1.0e-3 && y.z <= 50)) { ok = false; break; }
-                        double a[2], bb[2];
-                        apply_k(y, c->K, a); apply_k(f->bearings[r.second], c->K, bb);
-                        rpe += std::sqrt((a[0] - bb[0]) * (a[0] - bb[0]) + (a[1] - bb[1]) * (a[1] - bb[1]));
-                        cnt += 1.0;
-                    }
-                    ok = ok && (rpe / std::max(cnt, 1.0) < 3.0);
-                    t->valid = ok;
-                } else t->inv_depth = -1.0;
-            }
-            for (auto &tp : m->tracks) if (!tp->valid) tp->trash = true;
-        } else c->stats.subwindow_solves++;
-    }
+        if (!s.is_keyframe) { n_sub++; return 0; }
+        n_win++;
+        // validity gates (sliding_window_tracker.cpp:325-357)
+        for (auto &tp : m->tracks) {
+            Track *t = tp.get();
+            if (t->triangulated) {
+                bool ok = true;
+                const V3 x = get_landmark_point(t, c->rig);
+                double rpe = 0.0, cnt = 0.0;
+                for (auto &r : t->refs) {
+                    Frame *f = r.first;
+                    if (!f->keyframe) continue;
+                    Q4 q; V3 p;
+                    camera_pose(f, c->rig, q, p);
+                    const V3 y = qrot(qconj(q), x - p);
+                    if (!(y.z > 1.0e-3 && y.z <= 50)) { ok = false; break; }
+                    double a[2], bb[2];
+                    apply_k(y, c->K, a); apply_k(f->bearings[r.second], c->K, bb);
+                    rpe += std::sqrt((a[0] - bb[0]) * (a[0] - bb[0]) + (a[1] - bb[1]) * (a[1] - bb[1]));
+                    cnt += 1.0;
+                }
+                ok = ok && (rpe / std::max(cnt, 1.0) < 3.0);
+                t->valid = ok;
+            } else t->inv_depth = -1.0;
+        }
+        for (auto &tp : m->tracks) if (!tp->valid) tp->trash = true;
+        return 0; }); if (rc) return rc; }
+    for (Session *sp : act)
+        if (sp->prob2 >= 0 && sp->is_keyframe) {
+            c->stats.last_window_cost_initial = c->sout.h[sp->prob2].initial_cost;
+            c->stats.last_window_cost_final = c->sout.h[sp->prob2].final_cost;
+        }
+    c->stats.window_solves += n_win; c->stats.localize_solves += n_loc; c->stats.subwindow_solves += n_sub;
+    delete pt; pt = new PhaseTimer(c, 21);
     // ---- slide_window: marginalise frame 0 while the window is too long (:360-368, map.cpp:51-63) ----
     while (true) {
-        c->mdesc.clear();
-        clear_solve_arenas(c);
-        size_t scratch = 0;
-        std::vector<Session *> ms;
-        for (Session *sp : act) {
-            Session &s = *sp;
-            if (s.be_mode != 2 || !s.is_keyframe) continue;
+        { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
+            Staged &g = s.stg;
+            g.clear_prob();
+            if (s.be_mode != 2 || !s.is_keyframe) return 0;
             Map *m = s.sw_map.get();
-            if ((int)m->frame_num() <= c->prm.sliding_window_size) continue;
+            if ((int)m->frame_num() <= c->prm.sliding_window_size) return 0;
             Frame *victim = m->frames[0].get();
             for (auto &sf : victim->subframes) map_untrack_frame(m, sf.get(), c->rig);
             const int N = (int)m->frame_num();
-            if (N > XRVIO_MAX_ACTIVE) { xrvio_set_error("window longer than XRVIO_MAX_ACTIVE at marginalisation"); return XRVIO_ERR_LIMIT; }
-            CKC(c->mdesc.reserve(c->mdesc.n + 1)); CKC(c->states.reserve(c->states.n + N * 16));
+            if (N > XRVIO_MAX_ACTIVE) { s.err = "window longer than XRVIO_MAX_ACTIVE at marginalisation"; return XRVIO_ERR_LIMIT; }
             for (int i = 0; i < N; ++i) m->frames[i]->tmp = (i == 0) ? N - 1 : i - 1;       // victim last
             xvbe::MargDesc d{};
-            d.frame_off = (int)(c->states.n / 16); d.n_frames = N;
-            for (int i = 1; i < N; ++i) { std::memcpy(c->states.h + c->states.n, m->frames[i]->st.d, 128); c->states.n += 16; }
-            std::memcpy(c->states.h + c->states.n, victim->st.d, 128); c->states.n += 16;
+            d.n_frames = N;
+            g.states.resize((size_t)N * 16);
+            for (int i = 1; i < N; ++i) std::memcpy(&g.states[(size_t)(i - 1) * 16], m->frames[i]->st.d, 128);
+            std::memcpy(&g.states[(size_t)(N - 1) * 16], victim->st.d, 128);
             // observations of the victim's valid tracks whose first frame is a keyframe (:234-256)
-            std::vector<Track *> lms;
-            std::vector<xvbe::RpeObs> obs;
             for (size_t j = 0; j < victim->keypoint_num(); ++j) {
                 Track *t = victim->tracks[j];
                 if (!t || !t->valid) continue;
                 Frame *ref = t->first_frame();
                 if (!ref->keyframe || ref->map != m) continue;
-                const int lm = (int)lms.size();
+                const int lm = (int)g.invd.size();
                 bool used = false;
                 for (auto &r : t->refs) {
                     Frame *tg = r.first;
@@ -701,38 +733,55 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
                     xvbe::RpeObs o{};
                     o.tgt = (short)tg->tmp; o.ref = (short)ref->tmp; o.lm = lm; o.prior = 0;
                     st3(o.zt, tg->bearings[r.second]); st3(o.zr, ref->bearings[t->refs.front().second]);
-                    obs.push_back(o);
+                    g.rpe.push_back(o);
                     used = true;
                 }
-                if (used) lms.push_back(t);
+                if (used) g.invd.push_back(t->inv_depth);
             }
-            std::stable_sort(obs.begin(), obs.end(), [](const xvbe::RpeObs &x, const xvbe::RpeObs &y) { return x.tgt != y.tgt ? x.tgt < y.tgt : x.ref < y.ref; });
-            CKC(c->invd.reserve(c->invd.n + lms.size() + 1)); CKC(c->rpe.reserve(c->rpe.n + obs.size() + 1));
-            CKC(c->pref.reserve(c->pref.n + 2)); CKC(c->pblocks.reserve(c->pblocks.n + 2 * XRVIO_PRE_BLOCK)); CKC(c->mframes.reserve(c->mframes.n + N));
-            d.lm_off = (int)c->invd.n; d.n_lm = (int)lms.size();
-            for (Track *t : lms) c->invd.push(t->inv_depth);
-            d.rpe_off = (int)c->rpe.n; d.n_rpe = (int)obs.size();
-            for (auto &o : obs) c->rpe.push(o);
-            d.pre_off = (int)c->pref.n; d.n_pre = 0;
+            std::stable_sort(g.rpe.begin(), g.rpe.end(), [](const xvbe::RpeObs &x, const xvbe::RpeObs &y) { return x.tgt != y.tgt ? x.tgt < y.tgt : x.ref < y.ref; });
+            d.n_lm = (int)g.invd.size(); d.n_rpe = (int)g.rpe.size(); d.n_pre = 0;
             if (N > 1 && !m->frames[1]->kf_pre.empty()) {
                 xvbe::PreRef r{};
-                r.i = (short)victim->tmp; r.j = (short)m->frames[1]->tmp; r.prior = 0; r.block = (int)(c->pblocks.n / XRVIO_PRE_BLOCK);
-                std::memcpy(c->pblocks.h + c->pblocks.n, m->frames[1]->kf_pre.data(), XRVIO_PRE_BLOCK * sizeof(double)); c->pblocks.n += XRVIO_PRE_BLOCK;
-                c->pref.push(r);
+                r.i = (short)victim->tmp; r.j = (short)m->frames[1]->tmp; r.prior = 0; r.block = 0;
+                g.pblocks = m->frames[1]->kf_pre;
+                g.pref.push_back(r);
                 d.n_pre = 1;
             }
-            d.marg_k = (int)m->marg.frames.size(); d.marg_frames_off = (int)c->mframes.n;
-            for (Frame *f : m->marg.frames) c->mframes.push(f->tmp);
+            d.marg_k = (int)m->marg.frames.size();
+            for (Frame *f : m->marg.frames) g.mframes.push_back(f->tmp);
             d.marg_off = (long long)(((size_t)s.idx * 2 + m->marg.slot) * c->prior_stride);
             d.out_off = (long long)(((size_t)s.idx * 2 + (1 - m->marg.slot)) * c->prior_stride);
-            d.scratch_off = (long long)scratch;
-            scratch += xvbe::marg_scratch_doubles(N, d.n_lm);
             for (int i = 0; i < N; ++i) m->frames[i]->tmp = -1;
-            c->mdesc.push(d);
-            ms.push_back(&s);
+            g.md = d; g.has_marg = true;
+            return 0; }); if (rc) return rc; }
+        c->mdesc.clear();
+        clear_solve_arenas(c);
+        size_t scratch = 0, nst = 0, nl = 0, nr = 0, np = 0, npb = 0, nmf = 0;
+        std::vector<Session *> ms;
+        for (Session *sp : act) if (sp->stg.has_marg) {
+            ms.push_back(sp);
+            const Staged &g = sp->stg;
+            nst += g.states.size(); nl += g.invd.size(); nr += g.rpe.size(); np += g.pref.size(); npb += g.pblocks.size(); nmf += g.mframes.size();
         }
         if (ms.empty()) break;
         const int nm = (int)ms.size();
+        CKC(c->mdesc.reserve(nm)); CKC(c->states.reserve(nst + 16)); CKC(c->invd.reserve(nl + 1)); CKC(c->rpe.reserve(nr + 1));
+        CKC(c->pref.reserve(np + 1)); CKC(c->pblocks.reserve(npb + XRVIO_PRE_BLOCK)); CKC(c->mframes.reserve(nmf + 1));
+        for (Session *sp : ms) {
+            Staged &g = sp->stg;
+            xvbe::MargDesc d = g.md;
+            d.frame_off = (int)(c->states.n / 16); d.lm_off = (int)c->invd.n; d.rpe_off = (int)c->rpe.n; d.pre_off = (int)c->pref.n;
+            d.marg_frames_off = (int)c->mframes.n;
+            const int blk_base = (int)(c->pblocks.n / XRVIO_PRE_BLOCK);
+            auto app = [](auto &arena, const auto &v) { if (!v.empty()) { std::memcpy(arena.h + arena.n, v.data(), v.size() * sizeof(v[0])); arena.n += v.size(); } };
+            app(c->states, g.states); app(c->invd, g.invd); app(c->rpe, g.rpe);
+            for (xvbe::PreRef r : g.pref) { r.block += blk_base; c->pref.push(r); }
+            app(c->pblocks, g.pblocks); app(c->mframes, g.mframes);
+            d.scratch_off = (long long)scratch;
+            scratch += xvbe::marg_scratch_doubles(d.n_frames, d.n_lm);
+            c->mdesc.push(d);
+            g.has_marg = false;
+        }
         CKC(c->scratch.reserve(scratch * sizeof(double)));
         CKC(c->mrank.reserve(nm));
         CKC(cudaMemcpyAsync(c->mdesc.d, c->mdesc.h, nm * sizeof(xvbe::MargDesc), cudaMemcpyHostToDevice, c->st));
@@ -752,19 +801,20 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
         CKC(cudaMemcpyAsync(c->mrank.h, c->mrank.d, nm * sizeof(int), cudaMemcpyDeviceToHost, c->st));
         CKC(cudaStreamSynchronize(c->st));
         c->stats.d2h_bytes += nm * sizeof(int);
-        for (Session *sp : ms) {
-            Session &s = *sp;
+        c->pool->parallel_for(nm, [&](int i) {
+            Session &s = *ms[i];
             Map *m = s.sw_map.get();
             Frame *victim = m->frames[0].get();
             m->marg.slot = 1 - m->marg.slot;
             m->marg.frames.clear();
-            for (size_t i = 1; i < m->frame_num(); ++i) m->marg.frames.push_back(m->frames[i].get());
-            for (size_t i = 0; i < victim->keypoint_num(); ++i)
-                if (Track *t = victim->tracks[i]) track_remove_keypoint(t, victim, c->rig);
+            for (size_t k = 1; k < m->frame_num(); ++k) m->marg.frames.push_back(m->frames[k].get());
+            for (size_t k = 0; k < victim->keypoint_num(); ++k)
+                if (Track *t = victim->tracks[k]) track_remove_keypoint(t, victim, c->rig);
             m->frames.pop_front();
-            c->stats.marginalizations++;
-        }
+        });
+        c->stats.marginalizations += nm;
     }
+    delete pt; pt = new PhaseTimer(c, 22);
     // ---- FrontendWorker latest state (frontend_worker.cpp:48-51,72-75) ----
     for (Session *sp : act) {
         Session &s = *sp;
@@ -774,6 +824,7 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
         if (!f->subframes.empty()) f = f->subframes.back().get();
         s.has_swt_latest = true; s.swt_t = f->t; s.swt_frame_id = s.ft_map.frames.back()->id; s.swt_state = f->st;
     }
+    delete pt;
     return XRVIO_OK;
 }
 
