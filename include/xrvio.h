@@ -86,7 +86,8 @@ typedef struct xrvio_pre_ref {    /* preintegration residual (preintegration_fac
 /* One sliding-window problem.  Frames [0,n_active) are the free ones (<= XRVIO_MAX_ACTIVE), the
  * rest are constant reference frames.  Landmarks [0,n_lm_free) are free.  rpe must be sorted by
  * (tgt, ref).  Marginalisation prior arena (doubles at marg_off): lin[16K] S[(15K)^2] infovec[15K]
- * A0[(15K)^2] (A0 = S^T S is filled by the library in xrvio_op_solve). */
+ * A0[(15K)^2] rank[1]  (A0 = S^T S is filled by the library in xrvio_op_solve; rank = number of leading
+ * non-zero rows of S, 0 = unknown -> all rows are used). */
 typedef struct xrvio_solve_desc {
     int frame_off, n_frames, n_active;
     int lm_off, n_lm, n_lm_free;
@@ -113,9 +114,11 @@ typedef struct xrvio_marg_desc {
     int pre_off, n_pre;
     int marg_k, marg_frames_off;
     long long marg_off;
-    long long out_off;            /* new prior: lin[16(N-1)] S[n^2] infovec[n] A0[n^2], n = 15(N-1) */
+    long long out_off;            /* new prior: lin[16(N-1)] S[n^2] infovec[n] A0[n^2] rank[1], n = 15(N-1) */
     long long scratch_off;        /* filled by the library */
-    int pad[2];
+    int eigen_form;               /* != 0: rows of S are refined to sqrt(lambda_i) v_i^T (eigen form of the reference); 0: rows of
+                                     the rank-revealing Cholesky factor (same S^T S, same prior cost and Jacobian) */
+    int pad;
 } xrvio_marg_desc;
 
 typedef struct xrvio_tri_job { int obs_off, n_obs; } xrvio_tri_job;   /* views: 16 doubles each: q_wc, p_wc, bearing */
@@ -178,6 +181,8 @@ typedef struct xrvio_params {
     int init_keyframe_num, init_keyframe_gap;
     int solver_iteration_limit;
     double rotation_misalignment_threshold, rotation_ransac_threshold;
+    int prior_eigen_form;         /* 1: marginalisation prior kept in eigen form (see xrvio_marg_desc.eigen_form); default 0 */
+    int pad;
 } xrvio_params;
 
 typedef struct xrvio_imu { double t, w[3], a[3]; } xrvio_imu;

@@ -40,7 +40,7 @@ def unpack_preblock(b):
 def marg_arena(prior_lin, S, infovec):
     K = len(prior_lin)
     n = 15 * K
-    return np.concatenate([np.asarray(prior_lin).reshape(-1), np.asarray(S).reshape(-1), np.asarray(infovec).reshape(-1), np.zeros(n * n)])
+    return np.concatenate([np.asarray(prior_lin).reshape(-1), np.asarray(S).reshape(-1), np.asarray(infovec).reshape(-1), np.zeros(n * n + 1)])
 
 
 class PackedProblems:
@@ -149,7 +149,7 @@ def solve_problem_cuda(pb):
     return out[0]
 
 
-def marginalize_cuda(states, prior, pre_factors, obs, inv_depth, cam_q, cam_p, imu_q, imu_p, sic, index=0):
+def marginalize_cuda(states, prior, pre_factors, obs, inv_depth, cam_q, cam_p, imu_q, imu_p, sic, index=0, eigen_form=True):
     """Drop-in for oracle.marginalization.marginalize (index 0 only) using xrvio_op_marginalize."""
     assert index == 0
     N = states.shape[0]
@@ -177,14 +177,15 @@ def marginalize_cuda(states, prior, pre_factors, obs, inv_depth, cam_q, cam_p, i
     marg = marg_arena(prior.lin, prior.sqrt_inv_cov, prior.infovec)
     mframes = inv_order[prior.frames].astype(np.int32)
     n1 = 15 * (N - 1)
-    n_out = 16 * (N - 1) + 2 * n1 * n1 + n1
+    n_out = 16 * (N - 1) + 2 * n1 * n1 + n1 + 1
     d = desc[0]
     d['n_frames'], d['n_lm'], d['n_rpe'], d['n_pre'], d['marg_k'] = N, len(inv_depth), len(rpe), len(pre), K
+    d['eigen_form'] = 1 if eigen_form else 0
     out, rank = capi.op_marginalize(rig, desc, np.ascontiguousarray(states[order]), np.ascontiguousarray(inv_depth, np.float64),
                                     rpe, pre, blocks, mframes, marg, n_out)
     lin = out[:16 * (N - 1)].reshape(N - 1, 16)
     S = out[16 * (N - 1):16 * (N - 1) + n1 * n1].reshape(n1, n1)
     info = out[16 * (N - 1) + n1 * n1:16 * (N - 1) + n1 * n1 + n1]
-    A0 = out[16 * (N - 1) + n1 * n1 + n1:].reshape(n1, n1)
+    A0 = out[16 * (N - 1) + n1 * n1 + n1:16 * (N - 1) + 2 * n1 * n1 + n1].reshape(n1, n1)
     newp = MargPrior(frames=np.arange(N - 1), lin=lin.copy(), sqrt_inv_cov=S.copy(), infovec=info.copy())
     return newp, A0, int(rank[0])

@@ -238,6 +238,13 @@ def test_marginalization_matches_oracle(xrvio, golden_problems):
     off = GG - np.diag(np.diag(GG))
     assert np.abs(off).max() / np.abs(np.diag(GG)).max() < 1e-9
     assert np.allclose(np.sort(np.diag(GG)), np.sort(lam[lam > 1e-8])[-rank:], rtol=1e-6) or rank != int((lam > 1e-8).sum())
+    # the plain rank-revealing Cholesky form (session default) defines the same prior: same S^T S, S^T infovec, |infovec|^2
+    got2, A02, rank2 = bridge.marginalize_cuda(*args, eigen_form=False)
+    H2 = got2.sqrt_inv_cov.T @ got2.sqrt_inv_cov
+    assert np.abs(H2 - Href).max() / scale < 1e-9 and np.abs(A02 - H2).max() / scale < 1e-12
+    b2 = got2.sqrt_inv_cov.T @ got2.infovec
+    assert np.abs(b2 - bref).max() / np.abs(bref).max() < 1e-7
+    assert abs(got2.infovec @ got2.infovec - ref.infovec @ ref.infovec) / (ref.infovec @ ref.infovec) < 1e-6
 
 
 # ---------------------------------------------------------------- T

@@ -52,7 +52,7 @@ solve_out_dtype = np.dtype([("iterations", "i4"), ("termination", "i4"), ("n_suc
                             ("initial_cost", "f8"), ("final_cost", "f8"), ("cost_trace", "f8", MAX_ITER)], align=True)
 marg_desc_dtype = np.dtype([("frame_off", "i4"), ("n_frames", "i4"), ("lm_off", "i4"), ("n_lm", "i4"), ("rpe_off", "i4"),
                             ("n_rpe", "i4"), ("pre_off", "i4"), ("n_pre", "i4"), ("marg_k", "i4"), ("marg_frames_off", "i4"),
-                            ("marg_off", "i8"), ("out_off", "i8"), ("scratch_off", "i8"), ("pad", "i4", 2)], align=True)
+                            ("marg_off", "i8"), ("out_off", "i8"), ("scratch_off", "i8"), ("eigen_form", "i4"), ("pad", "i4")], align=True)
 tri_job_dtype = np.dtype([("obs_off", "i4"), ("n_obs", "i4")], align=True)
 
 assert rig_dtype.itemsize == 8 * (4 + 3 + 4 + 3 + 2 + 36)
@@ -192,7 +192,7 @@ params_dtype = np.dtype([("width", "i4"), ("height", "i4"), ("fx", "f8"), ("fy",
                          ("max_frames", "i4"), ("predict_keypoints", "i4"), ("clahe_clip_limit", "f8"), ("clahe_width", "i4"),
                          ("clahe_height", "i4"), ("init_keyframe_num", "i4"), ("init_keyframe_gap", "i4"),
                          ("solver_iteration_limit", "i4"), ("rotation_misalignment_threshold", "f8"),
-                         ("rotation_ransac_threshold", "f8")], align=True)
+                         ("rotation_ransac_threshold", "f8"), ("prior_eigen_form", "i4"), ("pad", "i4")], align=True)
 imu_dtype = np.dtype([("t", "f8"), ("w", "f8", 3), ("a", "f8", 3)], align=True)
 pose_dtype = np.dtype([("q", "f8", 4), ("p", "f8", 3), ("t", "f8"), ("valid", "i4"), ("pad", "i4")], align=True)
 stats_dtype = np.dtype([("frames_processed", "i8"), ("kernels_launched", "i8"), ("h2d_bytes", "i8"), ("d2h_bytes", "i8"),

@@ -48,7 +48,7 @@ struct SolveBatch {
     double *scratch;
     SolveOut *out;
 };
-size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k);
+size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k, int n_rpe);
 void solve(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st);
 // A0 = S^T S for a prior (helper used when a prior arrives without it)
 void gram(const double *S, double *A0, int n, int n_priors, size_t stride, cudaStream_t st);
@@ -68,7 +68,7 @@ struct MargBatch {
     double *scratch;
     int *rank_out;                          // number of rows kept per problem
 };
-size_t marg_scratch_doubles(int n_frames, int n_lm);
+size_t marg_scratch_doubles(int n_frames, int n_lm, int n_rpe);
 void marginalize(const MargBatch &b, int n_problems, const RigParams *rig, cudaStream_t st);
 
 // ---- T ----------------------------------------------------------------------------------------

@@ -11,9 +11,9 @@
 namespace xvbe {
 using namespace xv;
 
-size_t marg_scratch_doubles(int n_frames, int n_lm) {
+size_t marg_scratch_doubles(int n_frames, int n_lm, int n_rpe) {
     size_t n = (size_t)15 * n_frames;
-    return solve_scratch_doubles(n_frames, n_lm, 2, n_frames) + n * n + 16 * n + 1024;
+    return solve_scratch_doubles(n_frames, n_lm, 2, n_frames, n_rpe) + 2 * n * n + 16 * n + 1024;
 }
 
 __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParams *__restrict__ rig_g) {
@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
         P.m_dx = sc; sc += n + 32; P.m_r = sc; sc += n + 32; P.m_v = sc; sc += n + 32; sc += n + 32;
         P.m_T = sc; sc += n * n;
         Gm = sc; sc += (size_t)(15 * N) * (15 * N);
-        Yg = sc;
+        Yg = sc; sc += (size_t)16 * 15 * N;
+        prepare_prior(P, m, sc); sc += n * n;
+        prepare_tangents(P, sc);
+        P.du_l = nullptr; P.dw_l = nullptr;
     }
     for (int i = tid; i < N * 16; i += ST) { const double v = P.states_g[i]; s.us[i] = v; s.xs[i] = v; }
     for (int f = tid; f < kMaxActive; f += ST) { s.pose_free[f] = f < N; s.motion_free[f] = f < N; }
@@ -119,19 +122,21 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
         s.bred[i] = s.g[i] - a;                    // bc
     }
     __syncthreads();
-    // ---- rank-revealing Cholesky with diagonal pivoting: Hc ~= G^T G, G rows in Gm (r x n1) ----
-    for (int j = tid; j < n1; j += ST) { s.D[j] = s.H[hidx(j, j)]; s.col_free[j] = 1; }   // col_free == "not yet pivoted"
+    // ---- rank-revealing Cholesky with diagonal pivoting, right-looking and in place on the packed
+    //      shared-memory Hc: step k scales the pivot column into row k of G (written to Gm, r x n1) and
+    //      subtracts its outer product from the not-yet-pivoted part ----
+    for (int j = tid; j < n1; j += ST) s.col_free[j] = 1;      // col_free == "not yet pivoted"
     __syncthreads();
     int rnk = 0;
     for (int k = 0; k < n1; ++k) {
         // argmax of the remaining diagonal
         double bv = -1.0; int bi = -1;
         for (int j = tid; j < n1; j += ST)
-            if (s.col_free[j] && s.D[j] > bv) { bv = s.D[j]; bi = j; }
+            if (s.col_free[j]) { const double dj = s.H[hidx(j, j)]; if (dj > bv) { bv = dj; bi = j; } }
         for (int o = 16; o > 0; o >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) { bv = ov; bi = oi; }
+            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
         }
         __syncthreads();
         if (lane == 0) { s.red[warp] = bv; reinterpret_cast<int *>(s.jrinv)[warp] = bi; }
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
             double m = -1.0; int mi = -1;
             for (int w = 0; w < NW; ++w) {
                 const double v = s.red[w]; const int vi = reinterpret_cast<int *>(s.jrinv)[w];
-                if (vi >= 0 && (v > m || (v == m && vi < mi))) { m = v; mi = vi; }
+                if (vi >= 0 && (mi < 0 || v > m || (v == m && vi < mi))) { m = v; mi = vi; }
             }
             s_p = mi; s_dmax = m;
         }
@@ -149,20 +154,39 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
         const double dmax = s_dmax;
         if (p < 0 || !(dmax > 1.0e-8)) break;
         const double inv = 1.0 / sqrt(dmax);
+        // g = column p of the current matrix / sqrt(pivot); kept in s.y for the update
         for (int j = tid; j < n1; j += ST) {
             double v = 0.0;
-            if (s.col_free[j]) {
-                v = s.H[j >= p ? hidx(j, p) : hidx(p, j)];
-                for (int m = 0; m < k; ++m) v -= Gm[(size_t)m * n1 + p] * Gm[(size_t)m * n1 + j];
-                v *= inv;
-            }
+            if (s.col_free[j]) v = s.H[j >= p ? hidx(j, p) : hidx(p, j)] * inv;
+            s.y[j] = v;
             Gm[(size_t)k * n1 + j] = v;
-            if (s.col_free[j]) s.D[j] -= v * v;
         }
         __syncthreads();
-        if (tid == 0) { s.col_free[p] = 0; s.D[p] = 0.0; }
+        if (tid == 0) { s.col_free[p] = 0; s.g[k] = (double)p; }     // s.g is free now: remember the pivot order
+        __syncthreads();
+        for (int i = warp; i < n1; i += NW) {
+            if (!s.col_free[i]) continue;
+            const double gi = s.y[i];
+            if (gi == 0.0) continue;
+            const int row = i * (i + 1) / 2;
+            for (int j = lane; j <= i; j += 32)
+                if (s.col_free[j]) s.H[row + j] -= gi * s.y[j];
+        }
         __syncthreads();
         rnk++;
+    }
+    __syncthreads();
+    // infovec for the plain Cholesky factor: G^T infovec = bc on the range (forward substitution in pivot order)
+    double *info_chol = s.cs;
+    if (md.eigen_form == 0 && warp == 0) {
+        for (int k = 0; k < rnk; ++k) {
+            const int pk = (int)s.g[k];
+            double a = 0.0;
+            for (int m2 = lane; m2 < k; m2 += 32) a += Gm[(size_t)m2 * n1 + pk] * info_chol[m2];
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) info_chol[k] = (s.bred[pk] - a) / Gm[(size_t)k * n1 + pk];
+            __syncwarp();
+        }
     }
     __syncthreads();
     // ---- one-sided Jacobi on the rows of G: rows become sqrt(lambda_i) v_i^T ----
@@ -173,7 +197,8 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
         __syncthreads();
     }
     const int m = rnk + (rnk & 1);
-    for (int sweep = 0; sweep < 40 && rnk > 1; ++sweep) {
+    const bool eigen_form = md.eigen_form != 0;      // refine the Cholesky factor rows to sqrt(lambda_i) v_i^T (one-sided Jacobi)
+    for (int sweep = 0; eigen_form && sweep < 40 && rnk > 1; ++sweep) {
         double worst = 0.0;
         for (int t = 0; t < m - 1; ++t) {
             for (int pr = warp; pr < m / 2; pr += NW) {
@@ -230,13 +255,14 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
         }
         b.rank_out[blockIdx.x] = kept;
         s.flag = kept;
+        o_A0[(size_t)n1 * n1] = (double)kept;       // leading non-zero rows of S, read back by prepare_prior
     }
     __syncthreads();
     for (int i = warp; i < rnk; i += NW) {
         const int dst = (int)s.y[i];
         if (dst < 0) continue;
         for (int q = lane; q < n1; q += 32) o_S[(size_t)dst * n1 + q] = Gs[(size_t)i * n1 + q];
-        if (lane == 0) o_info[dst] = s.scale[i] / s.D[i];
+        if (lane == 0) o_info[dst] = eigen_form ? s.scale[i] / s.D[i] : info_chol[i];
     }
     __syncthreads();
     const int kept = s.flag;

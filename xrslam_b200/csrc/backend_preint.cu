@@ -22,14 +22,14 @@ __global__ void __launch_bounds__(32 * PW) preint_kernel(const PreintJob *__rest
                                                           const double *__restrict__ imu,
                                                           const RigParams *__restrict__ rig,
                                                           double *__restrict__ out) {
-    __shared__ double sC[PW][81], sT[PW][81];
+    __shared__ double sC[PW][81], sT[PW][81], sA[PW][81], sN[PW][81];
     __shared__ double sM[PW][15][30];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int job = blockIdx.x * PW + warp;
     if (job >= n_jobs) return;
     const PreintJob jb = jobs[job];
     const bool want_jac = jb.flags & 1, want_cov = jb.flags & 2;
-    double *C = sC[warp], *T = sT[warp];
+    double *C = sC[warp], *T = sT[warp], *A = sA[warp], *Nn = sN[warp];
     for (int e = lane; e < 81; e += 32) C[e] = 0.0;
     M3 cov_w, cov_a, cov_bg, cov_ba;
     for (int i = 0; i < 9; ++i) { cov_w.m[i] = rig->cov_w[i]; cov_a.m[i] = rig->cov_a[i]; cov_bg.m[i] = rig->cov_bg[i]; cov_ba.m[i] = rig->cov_ba[i]; }
@@ -61,24 +61,33 @@ __global__ void __launch_bounds__(32 * PW) preint_kernel(const PreintJob *__rest
             const M3 Bq = dt * Jr;
             const M3 NQ = Bq * (inv_dt * cov_w) * transpose(Bq);
             const M3 RQ = R * (inv_dt * cov_a) * transpose(R);
+            // A (9x9) and the noise term B Q B^T (9x9) are written once to shared memory, then two plain 9x9x9 products
             for (int e = lane; e < 81; e += 32) {
-                int r = e / 9, c = e % 9;
+                const int r = e / 9, c = e % 9;
+                A[e] = blkA(r, c, Rw, P1, V1, dt);
+                const int br = r / 3, bc = c / 3, i = r % 3, j = c % 3;
+                double nz = 0.0;
+                if (br == 0 && bc == 0) nz = NQ(i, j);
+                else if (br == 2 && bc == 2) nz = dt * dt * RQ(i, j);
+                else if (br == 1 && bc == 1) nz = 0.25 * dt * dt * dt * dt * RQ(i, j);
+                else if ((br == 1 && bc == 2) || (br == 2 && bc == 1)) nz = 0.5 * dt * dt * dt * RQ(i, j);
+                Nn[e] = nz;
+            }
+            __syncwarp();
+            for (int e = lane; e < 81; e += 32) {
+                const int r = e / 9, c = e % 9;
                 double acc = 0.0;
-                for (int m = 0; m < 9; ++m) acc += blkA(r, m, Rw, P1, V1, dt) * C[m * 9 + c];
+#pragma unroll
+                for (int m = 0; m < 9; ++m) acc += A[r * 9 + m] * C[m * 9 + c];
                 T[e] = acc;
             }
             __syncwarp();
             for (int e = lane; e < 81; e += 32) {
-                int r = e / 9, c = e % 9;
-                double acc = 0.0;
-                for (int m = 0; m < 9; ++m) acc += T[r * 9 + m] * blkA(c, m, Rw, P1, V1, dt);
-                int br = r / 3, bc = c / 3, i = r % 3, j = c % 3;
-                double n = 0.0;
-                if (br == 0 && bc == 0) n = NQ(i, j);
-                else if (br == 2 && bc == 2) n = dt * dt * RQ(i, j);
-                else if (br == 1 && bc == 1) n = 0.25 * dt * dt * dt * dt * RQ(i, j);
-                else if ((br == 1 && bc == 2) || (br == 2 && bc == 1)) n = 0.5 * dt * dt * dt * RQ(i, j);
-                C[e] = acc + n;
+                const int r = e / 9, c = e % 9;
+                double acc = Nn[e];
+#pragma unroll
+                for (int m = 0; m < 9; ++m) acc += T[r * 9 + m] * A[c * 9 + m];
+                C[e] = acc;
             }
             __syncwarp();
             Cbg = Cbg + dt * cov_bg;

@@ -4,27 +4,24 @@
 namespace xvbe {
 using namespace xv;
 
-size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k) {
+size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k, int n_rpe) {
     size_t M = (size_t)((n_lm_free + 31) / 32) * 32 + 32;
     size_t n = (size_t)15 * marg_k;
-    return 8 * M + (size_t)n_active * 6 * M + HPACK + (size_t)n_pre * kPreScratch + 4 * (n + 32) + n * n + 64;
+    return 8 * M + (size_t)n_active * 6 * M + HPACK + (size_t)n_pre * kPreScratch + 4 * (n + 32) + 2 * n * n + 64 + (size_t)6 * n_rpe + 2 * M;
 }
 
 
 // q <- normalize(q * exp(d)) for free pose blocks, additive elsewhere (quaternion_parameterization.h:11-17)
 __device__ void make_candidate(const Prob &P, Smem &s, double c1, double c2) {
     const int tid = threadIdx.x;
-    // delta_j = (-c1 * gs_j / D_j^2 - c2 * y_j) * scale_j
+    // delta_j = c1 * du_j + c2 * dw_j with du = -gs / D^2 * scale, dw = -y * scale (prepared per linearisation)
     for (int f = tid; f < P.d.n_frames; f += ST) {
         double *c = s.cs + f * 16;
         const double *x = s.xs + f * 16;
         for (int k = 0; k < 16; ++k) c[k] = x[k];
         if (f < P.d.n_active) {
             double dl[15];
-            for (int k = 0; k < 15; ++k) {
-                const int j = 15 * f + k;
-                dl[k] = s.col_free[j] ? (-c1 * s.g[j] / (s.D[j] * s.D[j]) - c2 * s.y[j]) * s.scale[j] : 0.0;
-            }
+            for (int k = 0; k < 15; ++k) { const int j = 15 * f + k; dl[k] = c1 * s.du[j] + c2 * s.dw[j]; }
             if (s.pose_free[f]) {
                 st4(c, qnormalized(qmul(ld4(x), expmap(v3(dl[0], dl[1], dl[2])))));
                 for (int k = 0; k < 3; ++k) c[4 + k] = x[4 + k] + dl[3 + k];
@@ -33,10 +30,7 @@ __device__ void make_candidate(const Prob &P, Smem &s, double c1, double c2) {
                 for (int k = 0; k < 9; ++k) c[7 + k] = x[7 + k] + dl[6 + k];
         }
     }
-    for (int l = tid; l < P.M; l += ST) {
-        const double d = (-c1 * P.g_l[l] / (P.D_l[l] * P.D_l[l]) - c2 * P.y_l[l]) * P.sc_l[l];
-        P.inv_c[l] = P.inv_x[l] + d;
-    }
+    for (int l = tid; l < P.M; l += ST) P.inv_c[l] = P.inv_x[l] + (c1 * P.du_l[l] + c2 * P.dw_l[l]);
     __syncthreads();
 }
 
@@ -63,8 +57,10 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
     for (int l = tid; l < M; l += ST) P.ht_l[l] = P.h_ll[l] + mu * P.D_l[l] * P.D_l[l];
     for (int c = tid; c < n; c += ST) s.bred[c] = s.g[c];
     __syncthreads();
+    if (threadIdx.x == 0 && P.d.marg_k > 0) { s.sc[15] = (double)clock64(); }
     schur_landmarks(P, s, s.bred);
     __syncthreads();
+    if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[24], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
     // in-place right-looking Cholesky on the packed lower triangle
     if (tid == 0) s.flag = 1;
     __syncthreads();
@@ -87,6 +83,7 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
         __syncthreads();
     }
     __syncthreads();
+    if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[25], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
     if (!s.flag) return false;
     // forward / backward substitution (L z = b, L^T y = z)
     for (int c = tid; c < n; c += ST) s.y[c] = s.bred[c];
@@ -105,6 +102,7 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
         for (int i = tid; i < j; i += ST) s.y[i] -= s.H[hidx(j, i)] * yj;
         __syncthreads();
     }
+    if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[26], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
     bool ok = true;
     for (int c = tid; c < n; c += ST) ok = ok && isfinite(s.y[c]);
     // back-substitute the landmarks: y_l = (gs_l - w_l . y_p) / ht_l
@@ -149,7 +147,10 @@ __global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigPar
         P.Hcopy = sc; sc += HPACK;
         P.pre_s = sc; sc += (size_t)P.d.n_pre * kPreScratch;
         P.m_dx = sc; sc += n + 32; P.m_r = sc; sc += n + 32; P.m_v = sc; sc += n + 32; sc += n + 32;
-        P.m_T = sc;
+        P.m_T = sc; sc += n * n;
+        prepare_prior(P, m, sc); sc += n * n;
+        prepare_tangents(P, sc); sc += (size_t)6 * P.d.n_rpe;
+        P.du_l = sc; sc += Mp; P.dw_l = sc;
     }
     SolveOut &out = b.out[blockIdx.x];
     // ---- load user memory ----
@@ -170,8 +171,10 @@ __global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigPar
     for (int c = 0; c < P.NPc; ++c) nfree += s.col_free[c];
     nfree += P.M;
 
+    KProf kp; kp.start(P.d.marg_k > 0);
+    if (kp.on) atomicAdd(&g_kprof[31], 1ull);
     // ---- iteration zero ----
-    double x_cost = evaluate(P, s, s.xs, P.inv_x, rg, true);
+    double x_cost = evaluate(P, s, s.xs, P.inv_x, rg, true, true, &kp);
     if (nfree == 0) {
         if (tid == 0) { out.iterations = 1; out.termination = 6; out.initial_cost = out.final_cost = x_cost; out.cost_trace[0] = x_cost; out.n_successful = out.n_unsuccessful = 0; }
         return;
@@ -273,7 +276,10 @@ __global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigPar
             // Gauss-Newton step with the mu loop
             solver_failed = true;
             while (mu < kMaxMu) {
-                if (gauss_newton(P, s, mu)) { solver_failed = false; break; }
+                kp.mark(18);
+                const bool gn_ok = gauss_newton(P, s, mu);
+                kp.mark(19);
+                if (gn_ok) { solver_failed = false; break; }
                 mu *= kMuInc;
                 for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) s.H[e] = P.Hcopy[e];
                 __syncthreads();
@@ -285,6 +291,16 @@ __global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigPar
                 for (int l = tid; l < P.M; l += ST) { t1 += P.g_l[l] * P.y_l[l]; t2 += P.D_l[l] * P.D_l[l] * P.y_l[l] * P.y_l[l]; }
                 gsy = block_sum(t1, s);
                 D2y2 = block_sum(t2, s);
+                for (int c = tid; c < P.NPc; c += ST) {
+                    const bool fr = s.col_free[c];
+                    s.du[c] = fr ? -s.g[c] / (s.D[c] * s.D[c]) * s.scale[c] : 0.0;
+                    s.dw[c] = fr ? -s.y[c] * s.scale[c] : 0.0;
+                }
+                for (int l = tid; l < P.M; l += ST) {
+                    P.du_l[l] = -P.g_l[l] / (P.D_l[l] * P.D_l[l]) * P.sc_l[l];
+                    P.dw_l[l] = -P.y_l[l] * P.sc_l[l];
+                }
+                __syncthreads();
                 gn_norm2 = D2y2;               // ||gn||^2 with gn = -D y
                 grad_dot_gn = -gsy;            // grad . gn = sum (gs/D)(-D y)
                 (void)t3;
@@ -324,10 +340,13 @@ __global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigPar
             continue;
         }
         n_invalid = 0;
+        kp.mark(20);
         make_candidate(P, s, c1, c2);
-        double cand_cost = evaluate(P, s, s.cs, P.inv_c, rg, false);
+        kp.mark(17);
+        double cand_cost = evaluate(P, s, s.cs, P.inv_c, rg, false, true, &kp);
         if (!isfinite(cand_cost)) cand_cost = x_cost;
         const double step_norm = sqrt(ambient_sq(P, s, s.xs, s.cs, P.inv_x, P.inv_c));
+        kp.mark(21);
         if (step_norm <= kParamTol * (x_norm + kParamTol)) { termination = 4; if (tid == 0 && n_rec < kMaxIter) out.cost_trace[n_rec] = it_cost; n_rec++; break; }
         const double cost_change = x_cost - cand_cost;
         if (fabs(cost_change) <= kFuncTol * x_cost) { termination = 5; if (tid == 0 && n_rec < kMaxIter) out.cost_trace[n_rec] = it_cost; n_rec++; break; }
@@ -338,14 +357,16 @@ __global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigPar
             for (int l = tid; l < P.M; l += ST) P.inv_x[l] = P.inv_c[l];
             __syncthreads();
             x_norm = sqrt(ambient_sq(P, s, s.xs, nullptr, P.inv_x, nullptr));
-            x_cost = evaluate(P, s, s.xs, P.inv_x, rg, true);
+            x_cost = evaluate(P, s, s.xs, P.inv_x, rg, true, true, &kp);
             {
                 double m = 0.0;
                 for (int c = tid; c < P.NPc; c += ST) m = fmax(m, fabs(s.g[c]));
                 for (int l = tid; l < P.M; l += ST) m = fmax(m, fabs(P.g_l[l]));
                 gmax = block_max(m, s);
             }
+            kp.mark(22);
             apply_scaling();
+            kp.mark(23);
             it_success = true;
             it_cost = x_cost;
             if (rel < 0.25) radius *= 0.5;
@@ -392,3 +413,9 @@ void gram(const double *S, double *A0, int n, int n_priors, size_t stride, cudaS
 }
 
 }  // namespace xvbe
+
+extern "C" int xrvio_debug_kprof(unsigned long long *out32, int reset) {
+    if (cudaMemcpyFromSymbol(out32, xvbe::g_kprof, 32 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(xvbe::g_kprof, z, sizeof(z)); }
+    return 0;
+}

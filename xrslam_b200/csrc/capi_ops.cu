@@ -94,13 +94,14 @@ int xrvio_op_gftt(const uint8_t *img, int n, int w, int h, int max_corners, doub
     if (!img || !corners || !count || n <= 0 || w < 8 || h < 8) return fail_arg("xrvio_op_gftt: bad argument");
     if (max_corners > XRVIO_MAX_CORNERS) { xrvio_set_error("xrvio_op_gftt: max_corners > XRVIO_MAX_CORNERS"); return XRVIO_ERR_LIMIT; }
     const size_t bytes = (size_t)n * w * h;
-    DevBuf d_img, d_cor, d_cnt, d_cand, d_cc, d_max;
+    DevBuf d_img, d_cor, d_cnt, d_cand, d_cc, d_max, d_resp;
+    CK(d_resp.alloc(bytes * sizeof(float)));
     CK(d_img.alloc(bytes)); CK(d_cor.alloc((size_t)n * xvfe::kMaxCorners * 3 * sizeof(float))); CK(d_cnt.alloc(n * sizeof(int)));
     CK(d_cand.alloc((size_t)n * xvfe::kMaxCand * 8)); CK(d_cc.alloc(n * sizeof(int))); CK(d_max.alloc(n * sizeof(unsigned)));
     CK(cudaMemcpy(d_img.p, img, bytes, cudaMemcpyHostToDevice));
     CK(cudaMemset(d_cor.p, 0, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float)));
     xvfe::gftt_harris(d_img.as<uint8_t>(), nullptr, (size_t)w * h, n, w, h, max_corners, (float)quality, (float)min_distance,
-                      d_cor.as<float>(), d_cnt.as<int>(), d_cand.as<unsigned long long>(), d_cc.as<int>(), d_max.as<unsigned>(), 0);
+                      d_cor.as<float>(), d_cnt.as<int>(), d_cand.as<unsigned long long>(), d_cc.as<int>(), d_max.as<unsigned>(), d_resp.as<float>(), 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(corners, d_cor.p, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(count, d_cnt.p, n * sizeof(int), cudaMemcpyDeviceToHost));
@@ -188,7 +189,7 @@ int xrvio_op_solve(const xrvio_rig *rig, xrvio_solve_desc *desc, int n_problems,
             d.rot_off + d.n_rot > n_rot || d.pre_off + d.n_pre > n_pre || d.n_lm_free > d.n_lm || d.marg_frames_off + d.marg_k > n_marg_frames)
             return fail_arg("xrvio_op_solve: descriptor out of range");
         d.scratch_off = scratch;
-        scratch += (long long)xvbe::solve_scratch_doubles(d.n_active, d.n_lm_free, d.n_pre, d.marg_k);
+        scratch += (long long)xvbe::solve_scratch_doubles(d.n_active, d.n_lm_free, d.n_pre, d.marg_k, d.n_rpe);
     }
     DevBuf d_rig, d_desc, d_states, d_flags, d_inv, d_rpe, d_rot, d_pre, d_pb, d_mf, d_marg, d_scr, d_out;
     CK(d_rig.alloc(sizeof(xrvio_rig))); CK(cudaMemcpy(d_rig.p, rig, sizeof(xrvio_rig), cudaMemcpyHostToDevice));
@@ -208,7 +209,7 @@ int xrvio_op_solve(const xrvio_rig *rig, xrvio_solve_desc *desc, int n_problems,
         const xrvio_solve_desc &d = desc[p];
         if (d.marg_k <= 0) continue;
         const size_t n = (size_t)15 * d.marg_k;
-        if (d.marg_off + (long long)(16 * d.marg_k + 2 * n * n + n) > n_marg_doubles) return fail_arg("xrvio_op_solve: prior arena too small");
+        if (d.marg_off + (long long)(16 * d.marg_k + 2 * n * n + n + 1) > n_marg_doubles) return fail_arg("xrvio_op_solve: prior arena too small");
         double *S = d_marg.as<double>() + d.marg_off + 16 * d.marg_k;
         xvbe::gram(S, S + n * n + n, (int)n, 1, 0, 0);
     }
@@ -236,12 +237,12 @@ int xrvio_op_marginalize(const xrvio_rig *rig, xrvio_marg_desc *desc, int n_prob
         xrvio_marg_desc &d = desc[p];
         if (d.n_frames > XRVIO_MAX_ACTIVE || d.n_frames < 2) { xrvio_set_error("xrvio_op_marginalize: 2 <= n_frames <= XRVIO_MAX_ACTIVE"); return XRVIO_ERR_LIMIT; }
         const long long n1 = 15LL * (d.n_frames - 1);
-        if (d.out_off + 16 * (d.n_frames - 1) + 2 * n1 * n1 + n1 > n_out_doubles) return fail_arg("xrvio_op_marginalize: output arena too small");
+        if (d.out_off + 16 * (d.n_frames - 1) + 2 * n1 * n1 + n1 + 1 > n_out_doubles) return fail_arg("xrvio_op_marginalize: output arena too small");
         if (d.frame_off + d.n_frames > n_frames || d.lm_off + d.n_lm > n_lm || d.rpe_off + d.n_rpe > n_rpe || d.pre_off + d.n_pre > n_pre ||
             d.n_pre > 2 || d.marg_frames_off + d.marg_k > n_marg_frames)
             return fail_arg("xrvio_op_marginalize: descriptor out of range");
         d.scratch_off = scratch;
-        scratch += (long long)xvbe::marg_scratch_doubles(d.n_frames, d.n_lm);
+        scratch += (long long)xvbe::marg_scratch_doubles(d.n_frames, d.n_lm, d.n_rpe);
     }
     DevBuf d_rig, d_desc, d_states, d_inv, d_rpe, d_pre, d_pb, d_mf, d_marg, d_scr, d_out, d_rank;
     CK(d_rig.alloc(sizeof(xrvio_rig))); CK(cudaMemcpy(d_rig.p, rig, sizeof(xrvio_rig), cudaMemcpyHostToDevice));
@@ -259,7 +260,7 @@ int xrvio_op_marginalize(const xrvio_rig *rig, xrvio_marg_desc *desc, int n_prob
     for (int p = 0; p < n_problems; ++p) {
         const xrvio_marg_desc &d = desc[p];
         const size_t n = (size_t)15 * d.marg_k;
-        if (d.marg_off + (long long)(16 * d.marg_k + 2 * n * n + n) > n_marg_doubles) return fail_arg("xrvio_op_marginalize: prior arena too small");
+        if (d.marg_off + (long long)(16 * d.marg_k + 2 * n * n + n + 1) > n_marg_doubles) return fail_arg("xrvio_op_marginalize: prior arena too small");
         double *S = d_marg.as<double>() + d.marg_off + 16 * d.marg_k;
         xvbe::gram(S, S + n * n + n, (int)n, 1, 0, 0);
     }

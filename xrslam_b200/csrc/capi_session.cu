@@ -19,9 +19,11 @@
 #include <cstdlib>
 #include <map>
 #include <string>
+#include <thread>
 #include <unordered_set>
 
 void xrvio_set_error(const std::string &e);
+struct Lane;
 
 using namespace xvs;
 
@@ -134,8 +136,9 @@ struct Session {
 
 }  // namespace
 
-struct xrvio_ctx {
+struct Lane {
     xrvio_params prm;
+    std::string err;
     int S = 0, device = 0;
     cudaStream_t st = nullptr;
     xvfe::PyrLayout L;
@@ -146,6 +149,7 @@ struct xrvio_ctx {
     double sic[2];
     std::vector<Session> ses;
     std::unique_ptr<ThreadPool> pool;
+    struct StepBuffers { Arena<int> idx_raw, idx_next, idx_prev; } sbuf;
     xrvio_stats stats{};
     // ---- device image / front-end buffers ----
     uint8_t *d_raw = nullptr;          // S * kImgQueue * w*h
@@ -153,7 +157,7 @@ struct xrvio_ctx {
     uint8_t *d_pyr = nullptr;          // S * kPyrSlots * L.total
     uint8_t *d_pyr_prev_batch = nullptr, *d_pyr_next_batch = nullptr;   // S * L.total contiguous batches for KLT
     uint8_t *d_lut = nullptr;
-    unsigned long long *d_cand = nullptr; int *d_cand_count = nullptr; unsigned *d_maxval = nullptr;
+    unsigned long long *d_cand = nullptr; int *d_cand_count = nullptr; unsigned *d_maxval = nullptr; float *d_resp = nullptr;
     Arena<float> corners; Arena<int> corner_count;
     Arena<float> klt_prev, klt_next; Arena<int> klt_n; Arena<unsigned char> klt_status;
     Arena<double> poi_pts; Arena<int> poi_npre, poi_ntot; Arena<unsigned char> poi_veto, poi_keep;
@@ -183,20 +187,20 @@ namespace {
 inline long long tkey(double t) { return (long long)std::llround(t * 1e6); }
 
 struct PhaseTimer {
-    xrvio_ctx *c; int id; std::chrono::steady_clock::time_point t0;
-    PhaseTimer(xrvio_ctx *c_, int id_) : c(c_), id(id_), t0(std::chrono::steady_clock::now()) {}
+    Lane *c; int id; std::chrono::steady_clock::time_point t0;
+    PhaseTimer(Lane *c_, int id_) : c(c_), id(id_), t0(std::chrono::steady_clock::now()) {}
     ~PhaseTimer() { c->phase_ms[id] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
 // kernel families for xrvio_get_kernel_times
 enum { FAM_CLAHE = 0, FAM_PYRAMID, FAM_GFTT, FAM_KLT, FAM_POISSON, FAM_PREINT, FAM_SOLVE, FAM_MARG, FAM_TRI, FAM_COUNT };
-cudaEvent_t prof_event(xrvio_ctx *c) {
+cudaEvent_t prof_event(Lane *c) {
     if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct ProfScope {
-    xrvio_ctx *c; int fam; int launches; cudaEvent_t a{};
-    ProfScope(xrvio_ctx *c_, int fam_, int launches_) : c(c_), fam(fam_), launches(launches_) {
+    Lane *c; int fam; int launches; cudaEvent_t a{};
+    ProfScope(Lane *c_, int fam_, int launches_) : c(c_), fam(fam_), launches(launches_) {
         if (c->prof) { a = prof_event(c); cudaEventRecord(a, c->st); }
     }
     ~ProfScope() {
@@ -204,7 +208,7 @@ struct ProfScope {
         if (c->prof) { cudaEvent_t b = prof_event(c); cudaEventRecord(b, c->st); c->prof_pending.push_back({fam, a, b}); }
     }
 };
-void prof_collect(xrvio_ctx *c) {     // call after the stream has been synchronised
+void prof_collect(Lane *c) {     // call after the stream has been synchronised
     for (auto &e : c->prof_pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->prof_ms[e.fam] += ms;
@@ -216,7 +220,7 @@ void prof_collect(xrvio_ctx *c) {     // call after the stream has been synchron
 // ---------------------------------------------------------------------------------------------
 // Detail::predict_pose + propagate_state (detail.cpp:15-28,144-177)
 // ---------------------------------------------------------------------------------------------
-void predict_pose(xrvio_ctx *c, Session &s, double t, xrvio_pose &out) {
+void predict_pose(Lane *c, Session &s, double t, xrvio_pose &out) {
     out.valid = 0; out.t = t;
     for (int k = 0; k < 4; ++k) out.q[k] = 0;
     for (int k = 0; k < 3; ++k) out.p[k] = 0;
@@ -268,7 +272,7 @@ int add_preint_job(Session &s, const std::vector<Imu> &data, double t_end, const
     return (int)s.stg.pj.size() - 1;
 }
 // merge the staged preintegration jobs of the active sessions into the batch arenas
-int merge_preint_jobs(xrvio_ctx *c, std::vector<Session *> &act) {
+int merge_preint_jobs(Lane *c, std::vector<Session *> &act) {
     c->pre_jobs.clear(); c->imu.clear();
     size_t nj = 0, ni = 0;
     for (Session *s : act) { nj += s->stg.pj.size(); ni += s->stg.imu.size(); }
@@ -283,7 +287,7 @@ int merge_preint_jobs(xrvio_ctx *c, std::vector<Session *> &act) {
     return XRVIO_OK;
 }
 
-int run_preint_jobs(xrvio_ctx *c) {
+int run_preint_jobs(Lane *c) {
     const int n = (int)c->pre_jobs.n;
     if (n == 0) return XRVIO_OK;
     CKC(c->pre_out.reserve((size_t)n * XRVIO_PRE_BLOCK));
@@ -297,7 +301,7 @@ int run_preint_jobs(xrvio_ctx *c) {
     c->stats.d2h_bytes += (size_t)n * XRVIO_PRE_BLOCK * sizeof(double);
     return XRVIO_OK;
 }
-void fetch_pre(xrvio_ctx *c, int job, std::vector<double> &dst) {
+void fetch_pre(Lane *c, int job, std::vector<double> &dst) {
     dst.assign(c->pre_out.h + (size_t)job * XRVIO_PRE_BLOCK, c->pre_out.h + (size_t)(job + 1) * XRVIO_PRE_BLOCK);
 }
 
@@ -305,7 +309,7 @@ void fetch_pre(xrvio_ctx *c, int job, std::vector<double> &dst) {
 // Problem builder (what Solver::add_frame_states / add_factor wire into Ceres, solver.cpp:84-174)
 // ---------------------------------------------------------------------------------------------
 struct Builder {
-    xrvio_ctx *c;
+    Lane *c;
     Session *s;
     std::vector<Frame *> active, consts;
     std::vector<Track *> free_lm, const_lm;
@@ -331,7 +335,7 @@ struct Builder {
 };
 
 // Packs one problem into the session's staging buffers (thread-safe across sessions).  Returns 0 or < 0.
-int pack_problem(xrvio_ctx *c, Session &s, Builder &b, int max_iterations) {
+int pack_problem(Lane *c, Session &s, Builder &b, int max_iterations) {
     Staged &g = s.stg;
     g.clear_prob();
     // a frame is active (gets columns) iff it was added with add_frame_states and has a free block
@@ -399,7 +403,7 @@ int pack_problem(xrvio_ctx *c, Session &s, Builder &b, int max_iterations) {
 }
 
 // merge the staged problems of the active sessions into the batch arenas; sets s.probN (global index or -1)
-int merge_problems(xrvio_ctx *c, std::vector<Session *> &act, int which) {
+int merge_problems(Lane *c, std::vector<Session *> &act, int which) {
     size_t nst = 0, nl = 0, nr = 0, nro = 0, np = 0, npb = 0, nmf = 0, nprob = 0;
     for (Session *s : act) {
         const Staged &g = s->stg;
@@ -432,19 +436,19 @@ int merge_problems(xrvio_ctx *c, std::vector<Session *> &act, int which) {
     return XRVIO_OK;
 }
 
-void clear_solve_arenas(xrvio_ctx *c) {
+void clear_solve_arenas(Lane *c) {
     c->sdesc.clear(); c->states.clear(); c->fflags.clear(); c->invd.clear(); c->rpe.clear(); c->rot.clear();
     c->pref.clear(); c->pblocks.clear(); c->mframes.clear();
 }
 
-int run_solves(xrvio_ctx *c) {
+int run_solves(Lane *c) {
     const int n = (int)c->sdesc.n;
     if (n == 0) return XRVIO_OK;
     size_t scratch = 0;
     for (int p = 0; p < n; ++p) {
         xvbe::SolveDesc &d = c->sdesc.h[p];
         d.scratch_off = (long long)scratch;
-        scratch += xvbe::solve_scratch_doubles(d.n_active, d.n_lm_free, d.n_pre, d.marg_k);
+        scratch += xvbe::solve_scratch_doubles(d.n_active, d.n_lm_free, d.n_pre, d.marg_k, d.n_rpe);
     }
     CKC(c->scratch.reserve(scratch * sizeof(double)));
     CKC(c->sout.reserve(n));
@@ -473,7 +477,7 @@ int run_solves(xrvio_ctx *c) {
     return XRVIO_OK;
 }
 
-void writeback(xrvio_ctx *c, Session &s, int prob) {
+void writeback(Lane *c, Session &s, int prob) {
     const xvbe::SolveDesc &d = c->sdesc.h[prob];
     for (int i = 0; i < d.n_active; ++i) std::memcpy(s.prob_frames[i]->st.d, c->states.h + (size_t)(d.frame_off + i) * 16, 16 * sizeof(double));
     for (int k = 0; k < d.n_lm_free; ++k) s.prob_tracks[k]->inv_depth = c->invd.h[d.lm_off + k];
@@ -482,9 +486,9 @@ void writeback(xrvio_ctx *c, Session &s, int prob) {
 }  // namespace
 
 // =================================================================================================
-extern "C" {
+// per-lane implementations of the session API
 
-int xrvio_default_params(xrvio_params *p, int width, int height) {
+int xrvio_default_params_impl(xrvio_params *p, int width, int height) {
     if (!p || width <= 0 || height <= 0) { xrvio_set_error("xrvio_default_params: bad argument"); return XRVIO_ERR_ARG; }
     std::memset(p, 0, sizeof(*p));
     p->width = width; p->height = height;
@@ -505,13 +509,13 @@ int xrvio_default_params(xrvio_params *p, int width, int height) {
     return XRVIO_OK;
 }
 
-int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **out) {
+static int lane_create(const xrvio_params *p, int n_sessions, int device, int host_threads, Lane **out) {
     if (!p || !out || n_sessions <= 0) { xrvio_set_error("xrvio_create: bad argument"); return XRVIO_ERR_ARG; }
     if (p->sliding_window_size + 2 > XRVIO_MAX_ACTIVE || p->max_keypoint_detection > XRVIO_MAX_CORNERS) { xrvio_set_error("xrvio_create: window / detection limit exceeded"); return XRVIO_ERR_LIMIT; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { xrvio_set_error("xrvio_create: no CUDA device (there is no CPU fallback)"); return XRVIO_ERR_CUDA; }
     CKC(cudaSetDevice(device));
-    xrvio_ctx *c = new xrvio_ctx();
+    Lane *c = new Lane();
     c->prm = *p; c->S = n_sessions; c->device = device;
     CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     c->L = xvfe::make_pyr_layout(p->width, p->height);
@@ -536,6 +540,7 @@ int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **
     CKC(cudaMalloc((void **)&c->d_cand, (size_t)S * xvfe::kMaxCand * 8));
     CKC(cudaMalloc((void **)&c->d_cand_count, S * sizeof(int)));
     CKC(cudaMalloc((void **)&c->d_maxval, S * sizeof(unsigned)));
+    CKC(cudaMalloc((void **)&c->d_resp, (size_t)S * P * sizeof(float)));
     CKC(c->corners.reserve((size_t)S * xvfe::kMaxCorners * 3)); CKC(c->corner_count.reserve(S));
     CKC(c->klt_prev.reserve((size_t)S * xvfe::kMaxPts * 2)); CKC(c->klt_next.reserve((size_t)S * xvfe::kMaxPts * 2));
     CKC(c->klt_n.reserve(S)); CKC(c->klt_status.reserve((size_t)S * xvfe::kMaxPts));
@@ -545,30 +550,36 @@ int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **
     c->prior_stride = 16 * (p->sliding_window_size + 1) + 2 * n * n + n + 64;
     CKC(cudaMalloc((void **)&c->d_prior, (size_t)S * 2 * c->prior_stride * sizeof(double)));
     CKC(cudaMemset(c->d_prior, 0, (size_t)S * 2 * c->prior_stride * sizeof(double)));
+    // reserve the batch arenas up front: growing them later means cudaFree / cudaHostAlloc, which stall every lane
+    CKC(c->pre_jobs.reserve((size_t)S * 16)); CKC(c->imu.reserve((size_t)S * 16 * 64 * 7)); CKC(c->pre_out.reserve((size_t)S * 16 * XRVIO_PRE_BLOCK));
+    CKC(c->sdesc.reserve(S)); CKC(c->states.reserve((size_t)S * XRVIO_MAX_FRAMES * 16)); CKC(c->fflags.reserve((size_t)S * XRVIO_MAX_FRAMES));
+    CKC(c->invd.reserve((size_t)S * 1024)); CKC(c->rpe.reserve((size_t)S * 4096)); CKC(c->rot.reserve((size_t)S * 256));
+    CKC(c->pref.reserve((size_t)S * 16)); CKC(c->pblocks.reserve((size_t)S * 16 * XRVIO_PRE_BLOCK)); CKC(c->mframes.reserve((size_t)S * 16));
+    CKC(c->sout.reserve(S)); CKC(c->mdesc.reserve(S)); CKC(c->mrank.reserve(S));
+    CKC(c->tjobs.reserve((size_t)S * 512)); CKC(c->tviews.reserve((size_t)S * 256 * 8 * 16)); CKC(c->tout.reserve((size_t)S * 512 * 4));
+    CKC(c->scratch.reserve((size_t)S * (xvbe::solve_scratch_doubles(XRVIO_MAX_ACTIVE, 768, 12, XRVIO_MAX_ACTIVE, 4096) + (size_t)2 * 180 * 180 + 8192) * sizeof(double)));
+    CKC(c->sbuf.idx_raw.reserve(S)); CKC(c->sbuf.idx_next.reserve(S)); CKC(c->sbuf.idx_prev.reserve(S));
     c->ses.resize(S);
     {
-        unsigned hc = std::thread::hardware_concurrency();
-        int nt = (int)std::min<unsigned>(hc ? hc : 4u, 32u);
-        if (const char *e = std::getenv("XRVIO_HOST_THREADS")) nt = std::max(1, std::atoi(e));
-        c->pool = std::make_unique<ThreadPool>(std::min(nt, S));
+        c->pool = std::make_unique<ThreadPool>(std::max(1, std::min(host_threads, S)));
     }
     for (int i = 0; i < S; ++i) { c->ses[i].idx = i; c->ses[i].ft_map.track_id_counter = &c->ses[i].track_id_counter; }
     *out = c;
     return XRVIO_OK;
 }
 
-int xrvio_destroy(xrvio_ctx *c) {
+static int lane_destroy(Lane *c) {
     if (!c) return XRVIO_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     cudaFree(c->rig_d); cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_pyr); cudaFree(c->d_pyr_prev_batch); cudaFree(c->d_pyr_next_batch);
-    cudaFree(c->d_lut); cudaFree(c->d_cand); cudaFree(c->d_cand_count); cudaFree(c->d_maxval); cudaFree(c->d_prior);
+    cudaFree(c->d_lut); cudaFree(c->d_cand); cudaFree(c->d_cand_count); cudaFree(c->d_maxval); cudaFree(c->d_resp); cudaFree(c->d_prior);
     cudaStreamDestroy(c->st);
     delete c;
     return XRVIO_OK;
 }
 
-int xrvio_push_bootstrap_state(xrvio_ctx *c, int session, double t, const double q[4], const double p[3], const double v[3]) {
+static int lane_push_bootstrap_state(Lane *c, int session, double t, const double q[4], const double p[3], const double v[3]) {
     if (!c || session < 0 || session >= c->S) { xrvio_set_error("bad session"); return XRVIO_ERR_ARG; }
     State16 s;
     for (int k = 0; k < 4; ++k) s.d[k] = q[k];
@@ -579,7 +590,7 @@ int xrvio_push_bootstrap_state(xrvio_ctx *c, int session, double t, const double
 
 // Detail::track_imu (detail.cpp:130-142): IMU samples up to the image time belong to the frame;
 // the first later sample releases the frame to the feature tracker.
-int xrvio_push_imu(xrvio_ctx *c, const int *session, const xrvio_imu *samples, int n) {
+static int lane_push_imu(Lane *c, const int *session, const xrvio_imu *samples, int n) {
     if (!c || !session || !samples || n < 0) { xrvio_set_error("xrvio_push_imu: bad argument"); return XRVIO_ERR_ARG; }
     for (int i = 0; i < n; ++i) {
         if (session[i] < 0 || session[i] >= c->S) { xrvio_set_error("bad session"); return XRVIO_ERR_ARG; }
@@ -596,7 +607,7 @@ int xrvio_push_imu(xrvio_ctx *c, const int *session, const xrvio_imu *samples, i
 }
 
 // Detail::track_camera (detail.cpp:103-128)
-int xrvio_push_images(xrvio_ctx *c, const int *session, const uint8_t *const *data, const int *stride, const double *t, int n, int on_device) {
+static int lane_push_images(Lane *c, const int *session, const uint8_t *const *data, const int *stride, const double *t, int n, int on_device) {
     if (!c || !session || !data || !t || n < 0) { xrvio_set_error("xrvio_push_images: bad argument"); return XRVIO_ERR_ARG; }
     CKC(cudaSetDevice(c->device));
     PhaseTimer pt_(c, 30);
@@ -620,13 +631,13 @@ int xrvio_push_images(xrvio_ctx *c, const int *session, const uint8_t *const *da
     return XRVIO_OK;
 }
 
-int xrvio_get_pose(xrvio_ctx *c, int session, xrvio_pose *pose) {
+static int lane_get_pose(Lane *c, int session, xrvio_pose *pose) {
     if (!c || !pose || session < 0 || session >= c->S) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
     *pose = c->ses[session].out_pose;
     pose->valid = pose->valid && c->ses[session].sw_map != nullptr;
     return XRVIO_OK;
 }
-int xrvio_get_latest_state(xrvio_ctx *c, int session, double *t, double state16[16]) {
+static int lane_get_latest_state(Lane *c, int session, double *t, double state16[16]) {
     if (!c || session < 0 || session >= c->S) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
     Session &s = c->ses[session];
     if (!s.has_swt_latest) return XRVIO_ERR_STATE;
@@ -634,11 +645,11 @@ int xrvio_get_latest_state(xrvio_ctx *c, int session, double *t, double state16[
     if (state16) std::memcpy(state16, s.swt_state.d, sizeof(s.swt_state.d));
     return XRVIO_OK;
 }
-int xrvio_get_state(xrvio_ctx *c, int session) {
+static int lane_get_state(Lane *c, int session) {
     if (!c || session < 0 || session >= c->S) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
     return c->ses[session].sw_map ? XRVIO_STATE_TRACKING : XRVIO_STATE_INITIALIZING;
 }
-int xrvio_get_landmarks(xrvio_ctx *c, int session, double *xyz, int capacity) {
+static int lane_get_landmarks(Lane *c, int session, double *xyz, int capacity) {
     if (!c || session < 0 || session >= c->S) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
     Session &s = c->ses[session];
     if (!s.sw_map) return 0;
@@ -650,30 +661,178 @@ int xrvio_get_landmarks(xrvio_ctx *c, int session, double *xyz, int capacity) {
         }
     return n;
 }
-int xrvio_set_profiling(xrvio_ctx *c, int enable) {
+static int lane_set_profiling(Lane *c, int enable) {
     if (!c) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
     c->prof = enable != 0;
     return XRVIO_OK;
 }
-int xrvio_get_kernel_times(xrvio_ctx *c, double *ms, long long *launches, int capacity) {
+static int lane_get_kernel_times(Lane *c, double *ms, long long *launches, int capacity) {
     if (!c || !ms || !launches) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
     cudaStreamSynchronize(c->st);
     prof_collect(c);
     for (int k = 0; k < capacity && k < 16; ++k) { ms[k] = c->prof_ms[k]; launches[k] = c->prof_launches[k]; }
     return FAM_COUNT;
 }
-int xrvio_get_phase_times(xrvio_ctx *c, double *ms, int capacity) {
+static int lane_get_phase_times(Lane *c, double *ms, int capacity) {
     if (!c || !ms) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
     for (int k = 0; k < capacity && k < 32; ++k) ms[k] = c->phase_ms[k];
     return 32;
 }
-int xrvio_get_stats(xrvio_ctx *c, xrvio_stats *st) {
+static int lane_get_stats(Lane *c, xrvio_stats *st) {
     if (!c || !st) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
     *st = c->stats;
     return XRVIO_OK;
 }
 
-}  // extern "C"
-
 // the step itself lives in session_step.inl to keep this file readable
 #include "session_step.inl"
+
+// =================================================================================================
+// Public session API: a context is split into independent LANES (disjoint session ranges, each with
+// its own CUDA stream, arenas and host worker threads).  xrvio_step advances all lanes concurrently,
+// so one lane's host bookkeeping overlaps the other lanes' kernels and small kernels of different
+// lanes share the GPU.  Sessions never interact, so the lane split does not change any result.
+// =================================================================================================
+struct xrvio_ctx {
+    std::vector<Lane *> lanes;
+    std::vector<std::pair<int, int>> where;     // session -> (lane, local index)
+    int S = 0, device = 0;
+    std::vector<std::vector<int>> tmp_idx;
+};
+
+namespace {
+template <class F> int each_lane(xrvio_ctx *ctx, F fn) {
+    const int L = (int)ctx->lanes.size();
+    std::vector<int> rc(L, 0);
+    std::vector<std::string> errs(L);
+    if (L == 1) { rc[0] = fn(ctx->lanes[0]); return rc[0]; }
+    std::vector<std::thread> th;
+    for (int l = 0; l < L; ++l)
+        th.emplace_back([&, l] {
+            cudaSetDevice(ctx->device);
+            rc[l] = fn(ctx->lanes[l]);
+            if (rc[l]) errs[l] = xrvio_last_error();
+        });
+    for (auto &t : th) t.join();
+    for (int l = 0; l < L; ++l) if (rc[l]) { xrvio_set_error(errs[l]); return rc[l]; }
+    return XRVIO_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int xrvio_default_params(xrvio_params *p, int width, int height) { return xrvio_default_params_impl(p, width, height); }
+
+int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **out) {
+    if (!p || !out || n_sessions <= 0) { xrvio_set_error("xrvio_create: bad argument"); return XRVIO_ERR_ARG; }
+    int L = n_sessions >= 32 ? 4 : (n_sessions >= 8 ? 2 : 1);
+    if (const char *e = std::getenv("XRVIO_LANES")) L = std::max(1, std::min(std::atoi(e), n_sessions));
+    unsigned hc = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned>(hc ? hc : 4u, 64u);
+    if (const char *e = std::getenv("XRVIO_HOST_THREADS")) nt = std::max(1, std::atoi(e));
+    const int per_lane_threads = std::max(1, nt / L);
+    xrvio_ctx *ctx = new xrvio_ctx();
+    ctx->S = n_sessions; ctx->device = device;
+    int base = 0;
+    for (int l = 0; l < L; ++l) {
+        const int cnt = n_sessions / L + (l < n_sessions % L ? 1 : 0);
+        Lane *lane = nullptr;
+        int rc = lane_create(p, cnt, device, per_lane_threads, &lane);
+        if (rc) { for (Lane *x : ctx->lanes) lane_destroy(x); delete ctx; return rc; }
+        ctx->lanes.push_back(lane);
+        for (int i = 0; i < cnt; ++i) ctx->where.emplace_back(l, i);
+        base += cnt;
+    }
+    ctx->tmp_idx.resize(L);
+    *out = ctx;
+    return XRVIO_OK;
+}
+
+int xrvio_destroy(xrvio_ctx *ctx) {
+    if (!ctx) return XRVIO_OK;
+    for (Lane *l : ctx->lanes) lane_destroy(l);
+    delete ctx;
+    return XRVIO_OK;
+}
+
+#define LANE_OF(sess, l, i)                                                                         \
+    if (!ctx || (sess) < 0 || (sess) >= ctx->S) { xrvio_set_error("bad session index"); return XRVIO_ERR_ARG; } \
+    Lane *l = ctx->lanes[ctx->where[(sess)].first];                                                  \
+    const int i = ctx->where[(sess)].second;
+
+int xrvio_push_bootstrap_state(xrvio_ctx *ctx, int session, double t, const double q[4], const double p[3], const double v[3]) {
+    LANE_OF(session, l, i);
+    return lane_push_bootstrap_state(l, i, t, q, p, v);
+}
+
+int xrvio_push_imu(xrvio_ctx *ctx, const int *session, const xrvio_imu *samples, int n) {
+    if (!ctx || !session || !samples || n < 0) { xrvio_set_error("xrvio_push_imu: bad argument"); return XRVIO_ERR_ARG; }
+    for (int k = 0; k < n; ++k) {
+        LANE_OF(session[k], l, i);
+        int rc = lane_push_imu(l, &i, samples + k, 1);
+        if (rc) return rc;
+    }
+    return XRVIO_OK;
+}
+
+int xrvio_push_images(xrvio_ctx *ctx, const int *session, const uint8_t *const *data, const int *stride, const double *t, int n, int on_device) {
+    if (!ctx || !session || !data || !t || n < 0) { xrvio_set_error("xrvio_push_images: bad argument"); return XRVIO_ERR_ARG; }
+    for (int k = 0; k < n; ++k) {
+        LANE_OF(session[k], l, i);
+        int rc = lane_push_images(l, &i, data + k, stride ? stride + k : nullptr, t + k, 1, on_device);
+        if (rc) return rc;
+    }
+    return XRVIO_OK;
+}
+
+int xrvio_step(xrvio_ctx *ctx) {
+    if (!ctx) { xrvio_set_error("xrvio_step: null context"); return XRVIO_ERR_ARG; }
+    return each_lane(ctx, [](Lane *l) { return lane_step(l); });
+}
+
+int xrvio_get_pose(xrvio_ctx *ctx, int session, xrvio_pose *pose) { LANE_OF(session, l, i); return lane_get_pose(l, i, pose); }
+int xrvio_get_latest_state(xrvio_ctx *ctx, int session, double *t, double state16[16]) { LANE_OF(session, l, i); return lane_get_latest_state(l, i, t, state16); }
+int xrvio_get_state(xrvio_ctx *ctx, int session) { LANE_OF(session, l, i); return lane_get_state(l, i); }
+int xrvio_get_landmarks(xrvio_ctx *ctx, int session, double *xyz, int capacity) { LANE_OF(session, l, i); return lane_get_landmarks(l, i, xyz, capacity); }
+
+int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *st) {
+    if (!ctx || !st) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    std::memset(st, 0, sizeof(*st));
+    for (Lane *l : ctx->lanes) {
+        xrvio_stats a;
+        lane_get_stats(l, &a);
+        st->frames_processed += a.frames_processed; st->kernels_launched += a.kernels_launched; st->h2d_bytes += a.h2d_bytes; st->d2h_bytes += a.d2h_bytes;
+        st->window_solves += a.window_solves; st->localize_solves += a.localize_solves; st->subwindow_solves += a.subwindow_solves;
+        st->marginalizations += a.marginalizations;
+        if (a.last_window_cost_initial != 0) { st->last_window_cost_initial = a.last_window_cost_initial; st->last_window_cost_final = a.last_window_cost_final; }
+    }
+    return XRVIO_OK;
+}
+int xrvio_set_profiling(xrvio_ctx *ctx, int enable) {
+    if (!ctx) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    for (Lane *l : ctx->lanes) lane_set_profiling(l, enable);
+    return XRVIO_OK;
+}
+int xrvio_get_kernel_times(xrvio_ctx *ctx, double *ms, long long *launches, int capacity) {
+    if (!ctx || !ms || !launches) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    for (int k = 0; k < capacity; ++k) { ms[k] = 0; launches[k] = 0; }
+    int nf = 0;
+    for (Lane *l : ctx->lanes) {
+        double m[16]; long long ln[16];
+        nf = lane_get_kernel_times(l, m, ln, 16);
+        for (int k = 0; k < capacity && k < 16; ++k) { ms[k] += m[k]; launches[k] += ln[k]; }
+    }
+    return nf;
+}
+int xrvio_get_phase_times(xrvio_ctx *ctx, double *ms, int capacity) {
+    if (!ctx || !ms) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    for (int k = 0; k < capacity; ++k) ms[k] = 0;
+    for (Lane *l : ctx->lanes) {
+        double m[32];
+        lane_get_phase_times(l, m, 32);
+        for (int k = 0; k < capacity && k < 32; ++k) ms[k] += m[k];
+    }
+    return 32;
+}
+
+}  // extern "C"

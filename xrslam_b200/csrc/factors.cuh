@@ -16,12 +16,16 @@ struct RpeEval {
 };
 
 // reprojection_factor.h:25-90
+// tb: the two tangent vectors b1, b2 of the target bearing (lie_algebra.cpp:47-56), precomputed per observation
 __device__ __forceinline__ void rpe_eval(const Q4 &qt, const V3 &pt, const Q4 &qr, const V3 &pr, double inv_depth,
-                                         const V3 &zt, const V3 &zr, const RigParams &rg, bool want_jac,
+                                         const V3 &zt, const V3 &zr, const double *tb, const RigParams &rg, bool want_jac,
                                          bool want_ref_jac, RpeEval &e) {
     const Q4 cq = ld4(rg.cam_q);
     const V3 cp = ld3(rg.cam_p);
-    const M3 T = local_tangent(zt);
+    M3 T;
+    T(0, 0) = tb[0]; T(1, 0) = tb[1]; T(2, 0) = tb[2];
+    T(0, 1) = tb[3]; T(1, 1) = tb[4]; T(2, 1) = tb[5];
+    T(0, 2) = zt.x; T(1, 2) = zt.y; T(2, 2) = zt.z;
     const V3 y_ref = (1.0 / inv_depth) * zr;           // z_ref / inv_depth
     const V3 y_ref_c = qrot(cq, y_ref) + cp;
     const V3 x = qrot(qr, y_ref_c) + pr;

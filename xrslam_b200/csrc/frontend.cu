@@ -15,6 +15,12 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     }
     return p;
 }
+// single reflection, valid for -len < p < 2*len - 1 (all KLT window offsets); clamped for safety
+__device__ __forceinline__ int reflect1(int p, int len) {
+    p = p < 0 ? -p : p;
+    p = p >= len ? 2 * len - 2 - p : p;
+    return min(max(p, 0), len - 1);
+}
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }   // round half to even
 __device__ __forceinline__ uint8_t sat_u8(int v) { return (uint8_t)min(max(v, 0), 255); }
 
@@ -261,40 +267,28 @@ __device__ __forceinline__ void harris_tile(const uint8_t *__restrict__ I, int w
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) harris_max_kernel(const uint8_t *__restrict__ img, const int *__restrict__ idx,
-                                                          size_t img_stride, int w, int h,
-                                                          unsigned int *__restrict__ maxval) {
-    __shared__ float resp[HT_H][HT_W];
-    __shared__ float wmax[8];
-    const uint8_t *I = img + (size_t)(idx ? idx[blockIdx.z] : blockIdx.z) * img_stride;
-    harris_tile<0>(I, w, h, blockIdx.x * HT_W, blockIdx.y * HT_H, resp);
-    float m = 0.f;
-    for (int i = threadIdx.x; i < HT_W * HT_H; i += blockDim.x) m = fmaxf(m, resp[i / HT_W][i % HT_W]);
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < 8; ++k) m = fmaxf(m, wmax[k]);
-        if (m > 0.f) atomicMax(&maxval[blockIdx.z], __float_as_uint(m));   // positive floats order as uints
-    }
-}
-
+// Single pass over the image: Harris response on a tile with a 1-px halo, 3x3 non-maximum suppression
+// and the per-image maximum.  Every positive local maximum becomes a candidate; the quality threshold
+// (q * max, which needs the global maximum) is applied by corner_select_kernel.
 __global__ void __launch_bounds__(256) harris_nms_kernel(const uint8_t *__restrict__ img, const int *__restrict__ idx,
                                                           size_t img_stride, int w, int h,
-                                                          const unsigned int *__restrict__ maxval, float quality,
+                                                          unsigned int *__restrict__ maxval,
                                                           unsigned long long *__restrict__ cand,
                                                           int *__restrict__ cand_count) {
     __shared__ float resp[HT_H + 2][HT_W + 2];
+    __shared__ float wmax[8];
     const uint8_t *I = img + (size_t)(idx ? idx[blockIdx.z] : blockIdx.z) * img_stride;
     const int bx = blockIdx.x * HT_W, by = blockIdx.y * HT_H;
     harris_tile<1>(I, w, h, bx, by, resp);
-    const float thr = (float)((double)__uint_as_float(maxval[blockIdx.z]) * (double)quality);
+    float m = 0.f;
     for (int i = threadIdx.x; i < HT_W * HT_H; i += blockDim.x) {
         int ly = i / HT_W, lx = i - ly * HT_W;
         int gx = bx + lx, gy = by + ly;
-        if (gx < 1 || gx >= w - 1 || gy < 1 || gy >= h - 1) continue;
+        if (gx >= w || gy >= h) continue;
         float v = resp[ly + 1][lx + 1];
-        if (!(v > thr) || v == 0.f) continue;      // THRESH_TOZERO, then `val != 0`
+        m = fmaxf(m, v);
+        if (gx < 1 || gx >= w - 1 || gy < 1 || gy >= h - 1) continue;
+        if (!(v > 0.f)) continue;
         bool is_max = true;
 #pragma unroll
         for (int j = 0; j < 3; ++j)
@@ -307,21 +301,23 @@ __global__ void __launch_bounds__(256) harris_nms_kernel(const uint8_t *__restri
                     ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(gy * w + gx);
         }
     }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) m = fmaxf(m, wmax[k]);
+        if (m > 0.f) atomicMax(&maxval[blockIdx.z], __float_as_uint(m));   // positive floats order as uints
+    }
 }
 
-// sort candidates (descending by response, then by descending address == descending y*w+x), greedy
-// min-distance selection on a cell grid (goodFeaturesToTrack), one block per image.
-__global__ void __launch_bounds__(1024) corner_select_kernel(unsigned long long *__restrict__ cand,
-                                                              const int *__restrict__ cand_count, int w, int h,
-                                                              int max_corners, float min_distance,
-                                                              float *__restrict__ corners, int *__restrict__ count) {
-    const int img = blockIdx.x;
-    unsigned long long *C = cand + (size_t)img * kMaxCand;
-    const int n = min(cand_count[img], kMaxCand);
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    for (int i = n + threadIdx.x; i < np2; i += blockDim.x) C[i] = 0ull;
-    __syncthreads();
+// Candidate selection, one block per image: (1) a histogram over the top bits of the response picks
+// a cut so that only the strongest ~kSortTarget candidates are compacted and bitonic-sorted
+// (descending by response, then by descending address == descending y*w+x, as greaterThanPtr);
+// (2) greedy min-distance selection on a cell grid (goodFeaturesToTrack).  If the greedy pass runs out
+// of sorted candidates before max_corners are accepted, the whole list is sorted and the pass repeated.
+constexpr int kSortTarget = 2048;
+constexpr int kHistBins = 2048;
+__device__ void bitonic_desc(unsigned long long *C, int np2) {
     for (int k = 2; k <= np2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = threadIdx.x; i < np2; i += blockDim.x) {
@@ -335,67 +331,172 @@ __global__ void __launch_bounds__(1024) corner_select_kernel(unsigned long long 
             __syncthreads();
         }
     }
-    // greedy selection by warp 0
+}
+__global__ void __launch_bounds__(1024) corner_select_kernel(unsigned long long *__restrict__ cand,
+                                                              const int *__restrict__ cand_count,
+                                                              const unsigned int *__restrict__ maxval, float quality,
+                                                              int w, int h, int max_corners, float min_distance,
+                                                              float *__restrict__ corners, int *__restrict__ count) {
+    const int img = blockIdx.x;
+    unsigned long long *C = cand + (size_t)img * kMaxCand;
+    // threshold(eig, maxVal * qualityLevel, THRESH_TOZERO): drop candidates that are not above the cut
+    __shared__ int s_n;
+    {
+        const int n_all = min(cand_count[img], kMaxCand);
+        const float thr = (float)((double)__uint_as_float(maxval[img]) * (double)quality);
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        // stable-order-free compaction in place: survivors are appended to the front region through a counter; a
+        // survivor at position i is only ever written to a slot <= i because slots are handed out in index order per pass
+        for (int base = 0; base < n_all; base += blockDim.x) {
+            const int i = base + threadIdx.x;
+            unsigned long long key = 0ull;
+            bool keep = false;
+            if (i < n_all) { key = C[i]; keep = __uint_as_float((unsigned int)(key >> 32)) > thr; }
+            __syncthreads();
+            if (keep) C[atomicAdd(&s_n, 1)] = key;
+            __syncthreads();
+        }
+    }
+    const int n = s_n;
+    extern __shared__ unsigned char smem_raw[];
     constexpr int CELL_CAP = 8;
     const int cell = __float2int_rn(min_distance);
     const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
-    extern __shared__ unsigned char smem_raw[];
     short *cell_cnt = reinterpret_cast<short *>(smem_raw);                 // gw*gh
     short2 *cell_pts = reinterpret_cast<short2 *>(cell_cnt + ((gw * gh + 1) & ~1));   // gw*gh*CELL_CAP
-    for (int i = threadIdx.x; i < gw * gh; i += blockDim.x) cell_cnt[i] = 0;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        const float md2 = min_distance * min_distance;
-        int ncorners = 0;
-        for (int i = 0; i < n && ncorners < max_corners; ++i) {
-            unsigned long long key = C[i];
-            int idx = (int)(key & 0xffffffffu);
-            int y = idx / w, x = idx - y * w;
-            int xc = x / cell, yc = y / cell;
-            bool bad = false;
-            if (lane < 9) {
-                int xx = xc - 1 + lane % 3, yy = yc - 1 + lane / 3;
-                if (xx >= 0 && xx < gw && yy >= 0 && yy < gh) {
-                    int c = yy * gw + xx;
-                    int m = cell_cnt[c];
-                    for (int q = 0; q < m; ++q) {
-                        short2 p = cell_pts[c * CELL_CAP + q];
-                        float dx = (float)(x - p.x), dy = (float)(y - p.y);
-                        if (dx * dx + dy * dy < md2) bad = true;
+    __shared__ int hist[kHistBins];
+    __shared__ int s_cut, s_m, s_done, s_ncorners;
+    // ---- (1) choose the cut: bin = top 11 bits below the sign of the float response (exponent + 3 mantissa bits) ----
+    int m_sorted = n;
+    if (n > 2 * kSortTarget) {
+        for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[(unsigned)(C[i] >> 32) >> 20], 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0, b = kHistBins - 1;
+            for (; b > 0; --b) { acc += hist[b]; if (acc >= kSortTarget) break; }
+            s_cut = b; s_m = 0;
+        }
+        __syncthreads();
+        // partition: strong candidates to the front (order inside the partitions is irrelevant before the sort)
+        const int cut = s_cut;
+        // two-pointer style compaction through a shared counter: swap-based in-place partition
+        // pass 1: count strong
+        int strong = 0;
+        for (int b = cut + threadIdx.x; b < kHistBins; b += blockDim.x) strong += hist[b];
+        for (int o = 16; o > 0; o >>= 1) strong += __shfl_xor_sync(0xffffffffu, strong, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_m, strong);
+        __syncthreads();
+        const int m = s_m;
+        // elements in [0,m) that are weak must swap with elements in [m,n) that are strong
+        __shared__ int s_wi, s_si;
+        if (threadIdx.x == 0) { s_wi = 0; s_si = 0; }
+        __syncthreads();
+        // collect indices of misplaced elements into the tail of the candidate buffer of this image (scratch beyond n)
+        // kMaxCand slots exist; use the region [kMaxCand - 2*m_mis, kMaxCand) only if free -> simpler: do it in two sweeps with atomics
+        unsigned long long *W = C;   // alias
+        // sweep A: weak elements in the front block record their positions
+        int *pos_w = reinterpret_cast<int *>(cell_pts);            // reuse the (not yet used) grid storage: gw*gh*CELL_CAP*4 bytes
+        const int pos_cap = gw * gh * CELL_CAP / 2;                  // ints available per list
+        int *pos_s = pos_w + pos_cap;
+        bool overflow = false;
+        for (int i = threadIdx.x; i < m; i += blockDim.x)
+            if ((int)((unsigned)(W[i] >> 32) >> 20) < cut) { int k = atomicAdd(&s_wi, 1); if (k < pos_cap) pos_w[k] = i; else overflow = true; }
+        for (int i = m + threadIdx.x; i < n; i += blockDim.x)
+            if ((int)((unsigned)(W[i] >> 32) >> 20) >= cut) { int k = atomicAdd(&s_si, 1); if (k < pos_cap) pos_s[k] = i; else overflow = true; }
+        const int any_over = __syncthreads_or(overflow ? 1 : 0);
+        if (!any_over) {
+            const int ns = min(s_wi, s_si);
+            for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+                const unsigned long long t = W[pos_w[k]]; W[pos_w[k]] = W[pos_s[k]]; W[pos_s[k]] = t;
+            }
+            m_sorted = m;
+        }
+        __syncthreads();
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int cnt = attempt == 0 ? m_sorted : n;
+        int np2 = 1;
+        while (np2 < cnt) np2 <<= 1;
+        // pad [cnt, np2) with zeros: when only the strong part is sorted, save and restore the overwritten tail
+        if (attempt == 0 && np2 > cnt && cnt < n) {
+            // the padding would destroy weak candidates in [cnt, np2): sort the larger power of two instead (they are
+            // all weaker than the cut, so the strong prefix still comes out in exact order)
+            np2 = min(np2, 1 << 30);
+            const int lim = min(np2, n);
+            for (int i = lim + threadIdx.x; i < np2; i += blockDim.x) C[i] = 0ull;
+        } else {
+            for (int i = cnt + threadIdx.x; i < np2; i += blockDim.x) C[i] = 0ull;
+        }
+        __syncthreads();
+        bitonic_desc(C, np2);
+        const int usable = attempt == 0 ? m_sorted : n;      // candidates guaranteed to be in global order
+        for (int i = threadIdx.x; i < gw * gh; i += blockDim.x) cell_cnt[i] = 0;
+        if (threadIdx.x == 0) { s_done = 0; s_ncorners = 0; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const float md2 = min_distance * min_distance;
+            int ncorners = 0;
+            int i = 0;
+            for (; i < usable && ncorners < max_corners; i += 32) {
+                const unsigned long long mykey = (i + lane < usable) ? C[i + lane] : 0ull;     // prefetch 32 candidates
+                const int lim = min(32, usable - i);
+                for (int q = 0; q < lim && ncorners < max_corners; ++q) {
+                    const unsigned long long key = __shfl_sync(0xffffffffu, mykey, q);
+                    const int idx = (int)(key & 0xffffffffu);
+                    const int y = idx / w, x = idx - y * w;
+                    const int xc = x / cell, yc = y / cell;
+                    bool bad = false;
+                    if (lane < 9) {
+                        const int xx = xc - 1 + lane % 3, yy = yc - 1 + lane / 3;
+                        if (xx >= 0 && xx < gw && yy >= 0 && yy < gh) {
+                            const int c = yy * gw + xx;
+                            const int mm = cell_cnt[c];
+                            for (int r = 0; r < mm; ++r) {
+                                const short2 p = cell_pts[c * CELL_CAP + r];
+                                const float dx = (float)(x - p.x), dy = (float)(y - p.y);
+                                if (dx * dx + dy * dy < md2) bad = true;
+                            }
+                        }
+                    }
+                    bad = __any_sync(0xffffffffu, bad);
+                    if (!bad) {
+                        if (lane == 0) {
+                            const int c = yc * gw + xc;
+                            const int mm = cell_cnt[c];
+                            if (mm < CELL_CAP) { cell_pts[c * CELL_CAP + mm] = make_short2((short)x, (short)y); cell_cnt[c] = mm + 1; }
+                            float *o = corners + ((size_t)img * kMaxCorners + ncorners) * 3;
+                            o[0] = (float)x; o[1] = (float)y; o[2] = __uint_as_float((unsigned int)(key >> 32));
+                        }
+                        ncorners++;
+                        __syncwarp();
                     }
                 }
             }
-            bad = __any_sync(0xffffffffu, bad);
-            if (!bad) {
-                if (lane == 0) {
-                    int c = yc * gw + xc;
-                    int m = cell_cnt[c];
-                    if (m < CELL_CAP) { cell_pts[c * CELL_CAP + m] = make_short2((short)x, (short)y); cell_cnt[c] = m + 1; }
-                    float *o = corners + ((size_t)img * kMaxCorners + ncorners) * 3;
-                    o[0] = (float)x; o[1] = (float)y; o[2] = __uint_as_float((unsigned int)(key >> 32));
-                }
-                ncorners++;
-                __syncwarp();
-            }
+            if (lane == 0) { s_ncorners = ncorners; s_done = (ncorners >= max_corners || usable >= n) ? 1 : 0; }
         }
-        if (lane == 0) count[img] = ncorners;
+        __syncthreads();
+        if (s_done) break;
     }
+    if (threadIdx.x == 0) count[img] = s_ncorners;
 }
 
 void gftt_harris(const uint8_t *img, const int *idx, size_t img_stride, int n, int w, int h, int max_corners, float quality,
                  float min_distance, float *corners, int *count, unsigned long long *cand, int *cand_count,
-                 unsigned int *maxval, cudaStream_t st) {
+                 unsigned int *maxval, float *resp_map, cudaStream_t st) {
     cudaMemsetAsync(maxval, 0, sizeof(unsigned int) * n, st);
     cudaMemsetAsync(cand_count, 0, sizeof(int) * n, st);
     dim3 grid((w + HT_W - 1) / HT_W, (h + HT_H - 1) / HT_H, n);
-    harris_max_kernel<<<grid, 256, 0, st>>>(img, idx, img_stride, w, h, maxval);
-    harris_nms_kernel<<<grid, 256, 0, st>>>(img, idx, img_stride, w, h, maxval, quality, cand, cand_count);
+    (void)resp_map;
+    harris_nms_kernel<<<grid, 256, 0, st>>>(img, idx, img_stride, w, h, maxval, cand, cand_count);
     int cell = (int)lrintf(min_distance);
     int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
     size_t smem = (size_t)((gw * gh + 1) & ~1) * sizeof(short) + (size_t)gw * gh * 8 * sizeof(short2);
     if (max_corners > kMaxCorners) max_corners = kMaxCorners;
-    corner_select_kernel<<<n, 1024, smem, st>>>(cand, cand_count, w, h, max_corners, min_distance, corners, count);
+    corner_select_kernel<<<n, 1024, smem, st>>>(cand, cand_count, maxval, quality, w, h, max_corners, min_distance, corners, count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -408,13 +509,16 @@ constexpr int WINP = WIN + 1;     // 22: window + 1 for bilinear taps
 constexpr int RAWP = WIN + 3;     // 24: + 1 px ring for the Scharr stencil
 constexpr int KLT_WARPS = 4;
 
+constexpr int JREG = 32;          // side of the staged search region (window 22 + 10 px of slack)
 struct KltSmem {
-    uint8_t raw[RAWP][RAWP + 4];      // level image around the template window (reflect-101 border)
+    union {
+        uint8_t raw[RAWP][RAWP + 4];  // level image around the template window (reflect-101 border)
+        uint8_t J[JREG][JREG];        // search region in the other image (staged once per level, re-staged on exit)
+    };
     short dx[WINP][WINP];             // Scharr derivatives at the 22x22 positions (0 outside the image)
     short dy[WINP][WINP];
     short I[WIN * WIN];               // template patch  (<< 5)
     short Ix[WIN * WIN], Iy[WIN * WIN];
-    uint8_t J[WINP][WINP + 2];        // search window in the other image
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -423,9 +527,17 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // One LK run for one point through all levels.  Returns status; out = tracked point (level 0).
+// Lane l owns window pixels i = l + 32 k (k < 14); their (y, x) are computed once (no div/mod in the loops).
 __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *__restrict__ pyrJ, const PyrLayout &L,
                                float px, float py, float gx, float gy, float &ox, float &oy, KltSmem &sm) {
     const int lane = threadIdx.x & 31;
+    constexpr int NPX = (WIN * WIN + 31) / 32;      // 14
+    int pxy[NPX];                                   // y << 8 | x, or -1 beyond the 441 pixels
+#pragma unroll
+    for (int k = 0; k < NPX; ++k) {
+        const int i = lane + 32 * k;
+        pxy[k] = i < WIN * WIN ? (((i / WIN) << 8) | (i % WIN)) : -1;
+    }
     bool status = true;
     float outx = 0.f, outy = 0.f;
     for (int level = kPyrLevels - 1; level >= 0; --level) {
@@ -449,11 +561,23 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
         int iw01 = cv_round(a * (1.f - b) * 16384.f);
         int iw10 = cv_round((1.f - a) * b * 16384.f);
         int iw11 = 16384 - iw00 - iw01 - iw10;
-        // stage the raw template neighbourhood
+        // stage the raw template neighbourhood (24 x 24): loads first, stores after, so the loads overlap
         __syncwarp();
-        for (int i = lane; i < RAWP * RAWP; i += 32) {
-            int ly = i / RAWP, lx = i - ly * RAWP;
-            sm.raw[ly][lx] = I[(size_t)reflect101(ipy - 1 + ly, rows) * cols + reflect101(ipx - 1 + lx, cols)];
+        {
+            constexpr int NR = (RAWP * RAWP + 31) / 32;     // 18
+            uint8_t v[NR];
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+                const int i = lane + 32 * k;
+                const int ly = i / RAWP, lx = i - ly * RAWP;
+                v[k] = i < RAWP * RAWP ? I[(size_t)reflect1(ipy - 1 + ly, rows) * cols + reflect1(ipx - 1 + lx, cols)] : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+                const int i = lane + 32 * k;
+                const int ly = i / RAWP, lx = i - ly * RAWP;
+                if (i < RAWP * RAWP) sm.raw[ly][lx] = v[k];
+            }
         }
         __syncwarp();
         for (int i = lane; i < WINP * WINP; i += 32) {
@@ -474,9 +598,12 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
         }
         __syncwarp();
         float A11 = 0.f, A12 = 0.f, A22 = 0.f;
-        for (int i = lane; i < WIN * WIN; i += 32) {
-            int y = i / WIN, x = i - y * WIN;
-            int cy = y + 1, cx = x + 1;
+#pragma unroll
+        for (int k = 0; k < NPX; ++k) {
+            if (pxy[k] < 0) continue;
+            const int y = pxy[k] >> 8, x = pxy[k] & 255;
+            const int i = lane + 32 * k;
+            const int cy = y + 1, cx = x + 1;
             int ival = ((int)sm.raw[cy][cx] * iw00 + (int)sm.raw[cy][cx + 1] * iw01 + (int)sm.raw[cy + 1][cx] * iw10 +
                         (int)sm.raw[cy + 1][cx + 1] * iw11 + (1 << 8)) >> 9;
             int ixval = ((int)sm.dx[y][x] * iw00 + (int)sm.dx[y][x + 1] * iw01 + (int)sm.dx[y + 1][x] * iw10 +
@@ -495,8 +622,18 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
             continue;
         }
         D = 1.f / D;
+        // the template (and its gradients) stay in registers for the iterations
+        short tI[NPX], tIx[NPX], tIy[NPX];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NPX; ++k) {
+            const int i = lane + 32 * k;
+            tI[k] = pxy[k] >= 0 ? sm.I[i] : (short)0; tIx[k] = pxy[k] >= 0 ? sm.Ix[i] : (short)0; tIy[k] = pxy[k] >= 0 ? sm.Iy[i] : (short)0;
+        }
         nx -= 10.f; ny -= 10.f;
         float pdx = 0.f, pdy = 0.f;
+        int rox = 0, roy = 0;
+        bool staged = false;
         for (int j = 0; j < 30; ++j) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (inx < -WIN || inx >= cols || iny < -WIN || iny >= rows) {
@@ -508,19 +645,28 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
             iw01 = cv_round(a * (1.f - b) * 16384.f);
             iw10 = cv_round((1.f - a) * b * 16384.f);
             iw11 = 16384 - iw00 - iw01 - iw10;
-            __syncwarp();
-            for (int i = lane; i < WINP * WINP; i += 32) {
-                int ly = i / WINP, lx = i - ly * WINP;
-                sm.J[ly][lx] = J[(size_t)reflect101(iny + ly, rows) * cols + reflect101(inx + lx, cols)];
+            if (!staged || inx < rox || inx > rox + JREG - WINP || iny < roy || iny > roy + JREG - WINP) {
+                rox = inx - (JREG - WINP) / 2; roy = iny - (JREG - WINP) / 2;
+                __syncwarp();
+                // lane = column, 32 rows: 32 independent loads per lane
+                uint8_t v[JREG];
+                const int cxg = reflect1(rox + lane, cols);
+#pragma unroll
+                for (int r = 0; r < JREG; ++r) v[r] = J[(size_t)reflect1(roy + r, rows) * cols + cxg];
+#pragma unroll
+                for (int r = 0; r < JREG; ++r) sm.J[r][lane] = v[r];
+                __syncwarp();
+                staged = true;
             }
-            __syncwarp();
+            const uint8_t *Jb = &sm.J[iny - roy][inx - rox];
             float b1 = 0.f, b2 = 0.f;
-            for (int i = lane; i < WIN * WIN; i += 32) {
-                int y = i / WIN, x = i - y * WIN;
-                int diff = (((int)sm.J[y][x] * iw00 + (int)sm.J[y][x + 1] * iw01 + (int)sm.J[y + 1][x] * iw10 +
-                             (int)sm.J[y + 1][x + 1] * iw11 + (1 << 8)) >> 9) - (int)sm.I[i];
-                b1 += (float)(diff * (int)sm.Ix[i]);
-                b2 += (float)(diff * (int)sm.Iy[i]);
+#pragma unroll
+            for (int k = 0; k < NPX; ++k) {
+                if (pxy[k] < 0) continue;
+                const uint8_t *q = Jb + (pxy[k] >> 8) * JREG + (pxy[k] & 255);
+                const int diff = (((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[JREG] * iw10 + (int)q[JREG + 1] * iw11 + (1 << 8)) >> 9) - (int)tI[k];
+                b1 += (float)(diff * (int)tIx[k]);
+                b2 += (float)(diff * (int)tIy[k]);
             }
             b1 = warp_sum(b1) * FLT_SCALE; b2 = warp_sum(b2) * FLT_SCALE;
             float dxv = (A12 * b2 - A22 * b1) * D;
@@ -589,16 +735,21 @@ void klt_track(const uint8_t *prev_pyr, const uint8_t *next_pyr, const int *prev
 // K5 Poisson-disk filter (poisson_disk_filter.h): one warp per list; the 25-cell neighbourhood scan
 // (first cell skipped, one extra cell visited) is spread over the lanes.
 // ------------------------------------------------------------------------------------------------
-constexpr int PG_W = 192, PG_H = 128;    // grid cells available (cell = radius / sqrt 2)
+constexpr int PG_W = 96, PG_H = 64;      // grid cells available (cell = radius / sqrt 2): images up to ~1350 x 900 at r = 20
 __global__ void __launch_bounds__(32) poisson_kernel(const double *__restrict__ pts, const int *__restrict__ n_preset,
                                                       const int *__restrict__ n_total,
                                                       const uint8_t *__restrict__ veto, uint8_t *__restrict__ keep,
                                                       double radius) {
     extern __shared__ short grid[];      // PG_W * PG_H, -1 = empty
+    __shared__ double P[kMaxPts * 2];    // the list, staged once (the scan is strictly sequential)
     const int list = blockIdx.x, lane = threadIdx.x;
     for (int i = lane; i < PG_W * PG_H; i += 32) grid[i] = -1;
+    {
+        const double *Pg = pts + (size_t)list * kMaxPts * 2;
+        const int nt = n_total[list];
+        for (int i = lane; i < 2 * nt; i += 32) P[i] = Pg[i];
+    }
     __syncwarp();
-    const double *P = pts + (size_t)list * kMaxPts * 2;
     const double r2 = radius * radius;
     const double gs = radius / sqrt(2.0);
     const int npre = n_preset[list], ntot = n_total[list];

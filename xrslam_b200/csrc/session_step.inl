@@ -2,25 +2,18 @@
 
 namespace {
 
-struct StepBuffers {       // small index arrays living in the context (allocated lazily)
-    Arena<int> idx_raw, idx_next, idx_prev;
-};
-StepBuffers &sb(xrvio_ctx *c) {
-    static std::map<xrvio_ctx *, std::unique_ptr<StepBuffers>> m;     // contexts are few; freed at process exit
-    auto &p = m[c];
-    if (!p) p = std::make_unique<StepBuffers>();
-    return *p;
-}
+typedef Lane::StepBuffers StepBuffers;
+StepBuffers &sb(Lane *c) { return c->sbuf; }
 
 // run body(i) for every active session on the host thread pool; first error wins
-template <class F> int for_sessions(xrvio_ctx *c, std::vector<Session *> &act, F body) {
+template <class F> int for_sessions(Lane *c, std::vector<Session *> &act, F body) {
     for (Session *s : act) s->rc = 0;
     c->pool->parallel_for((int)act.size(), [&](int i) { if (act[i]->rc == 0) { int rc = body(i, *act[i]); if (rc) act[i]->rc = rc; } });
     for (Session *s : act) if (s->rc) { xrvio_set_error(s->err.empty() ? "session error" : s->err); return s->rc; }
     return XRVIO_OK;
 }
 
-int run_poisson(xrvio_ctx *c, int n, bool with_veto) {
+int run_poisson(Lane *c, int n, bool with_veto) {
     const size_t pb = (size_t)n * xvfe::kMaxPts;
     CKC(cudaMemcpyAsync(c->poi_pts.d, c->poi_pts.h, pb * 2 * sizeof(double), cudaMemcpyHostToDevice, c->st));
     CKC(cudaMemcpyAsync(c->poi_npre.d, c->poi_npre.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
@@ -40,7 +33,7 @@ int run_poisson(xrvio_ctx *c, int n, bool with_veto) {
 // ---------------------------------------------------------------------------------------------
 // FeatureTracker::work for one released frame of every session in `act`
 // ---------------------------------------------------------------------------------------------
-int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
+int front_end_round(Lane *c, std::vector<Session *> &act) {
     const int n = (int)act.size();
     const int w = c->prm.width, h = c->prm.height;
     const size_t P = (size_t)w * h;
@@ -92,10 +85,10 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
       xvfe::clahe(c->d_raw, B.idx_raw.d, P, c->d_pyr, B.idx_next.d, c->L.total, c->d_lut, n, w, h, c->prm.clahe_clip_limit,
                   c->prm.clahe_width, c->prm.clahe_height, c->st); }
     { ProfScope ps(c, FAM_PYRAMID, 3); xvfe::pyramid(c->d_pyr, B.idx_next.d, n, c->L, c->st); }
-    { ProfScope ps(c, FAM_GFTT, 3);
+    { ProfScope ps(c, FAM_GFTT, 2);
       xvfe::gftt_harris(c->d_pyr, B.idx_next.d, c->L.total, n, w, h, c->prm.max_keypoint_detection, 1.0e-3f, 20.0f, c->corners.d,
-                        c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->st); }
-    c->stats.kernels_launched += 2 + 3 + 3;
+                        c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->d_resp, c->st); }
+    c->stats.kernels_launched += 2 + 3 + 2;
     CKC(cudaMemcpyAsync(c->corners.h, c->corners.d, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     CKC(cudaMemcpyAsync(c->corner_count.h, c->corner_count.d, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     c->stats.d2h_bytes += (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float) + n * sizeof(int);
@@ -275,7 +268,7 @@ int front_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
 // ---------------------------------------------------------------------------------------------
 // Back end helpers
 // ---------------------------------------------------------------------------------------------
-int run_triangulation(xrvio_ctx *c) {
+int run_triangulation(Lane *c) {
     const int n = (int)c->tjobs.n;
     if (n == 0) return XRVIO_OK;
     CKC(c->tout.reserve((size_t)n * 4));
@@ -289,7 +282,7 @@ int run_triangulation(xrvio_ctx *c) {
     c->stats.d2h_bytes += (size_t)n * 4 * sizeof(double);
     return XRVIO_OK;
 }
-void add_tri_job(xrvio_ctx *c, Session &s, Track *tr) {          // Track::triangulate input (track.cpp:46-62), staged
+void add_tri_job(Lane *c, Session &s, Track *tr) {          // Track::triangulate input (track.cpp:46-62), staged
     xvbe::TriJob j{(int)(s.stg.tv.size() / 16), (int)tr->refs.size()};
     for (auto &r : tr->refs) {
         Q4 q; V3 p;
@@ -300,7 +293,7 @@ void add_tri_job(xrvio_ctx *c, Session &s, Track *tr) {          // Track::trian
     }
     s.stg.tj.push_back(j);
 }
-int merge_tri_jobs(xrvio_ctx *c, std::vector<Session *> &act) {
+int merge_tri_jobs(Lane *c, std::vector<Session *> &act) {
     c->tjobs.clear(); c->tviews.clear();
     size_t nj = 0, nv = 0;
     for (Session *s : act) { nj += s->stg.tj.size(); nv += s->stg.tv.size(); }
@@ -316,7 +309,7 @@ int merge_tri_jobs(xrvio_ctx *c, std::vector<Session *> &act) {
 }
 
 // Initializer::mirror_keyframe_map (initializer.cpp:22-76) + ground-truth states
-bool bootstrap_mirror(xrvio_ctx *c, Session &s, long long init_frame_id) {
+bool bootstrap_mirror(Lane *c, Session &s, long long init_frame_id) {
     Map &ft = s.ft_map;
     const long last = ft.frame_index_by_id(init_frame_id);
     const long gap = c->prm.init_keyframe_gap, dist = gap * (c->prm.init_keyframe_num - 1);
@@ -353,7 +346,7 @@ bool bootstrap_mirror(xrvio_ctx *c, Session &s, long long init_frame_id) {
 }
 
 // SlidingWindowTracker::mirror_frame up to the preintegration (sliding_window_tracker.cpp:31-75)
-bool mirror_frame(xrvio_ctx *c, Session &s, long long frame_id) {
+bool mirror_frame(Lane *c, Session &s, long long frame_id) {
     Map *m = s.sw_map.get();
     Map &ft = s.ft_map;
     Frame *keyframe = m->frames.back().get();
@@ -385,7 +378,7 @@ bool mirror_frame(xrvio_ctx *c, Session &s, long long frame_id) {
 }
 
 // SlidingWindowTracker::manage_keyframe (sliding_window_tracker.cpp:145-223)
-bool manage_keyframe(xrvio_ctx *c, Session &s) {
+bool manage_keyframe(Lane *c, Session &s) {
     Map *m = s.sw_map.get();
     Frame *ki = m->frames[m->frame_num() - 2].get();
     Frame *nj = m->frames[m->frame_num() - 1].get();
@@ -426,7 +419,7 @@ bool manage_keyframe(xrvio_ctx *c, Session &s) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
+int back_end_round(Lane *c, std::vector<Session *> &act) {
     PhaseTimer *pt = new PhaseTimer(c, 10);
     // ---- phase E: mirror + preintegration with Jacobians and covariance ----
     { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
@@ -595,7 +588,8 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
         Map *m = s.sw_map.get();
         const int K = (int)m->frame_num() - 1;
         const size_t n = (size_t)15 * K;
-        std::vector<double> a(16 * K + 2 * n * n + n, 0.0);
+        std::vector<double> a(16 * K + 2 * n * n + n + 1, 0.0);
+        a.back() = 6.0;                              // rows 0..5 are the only non-zero rows of the initial S
         for (int k = 0; k < K; ++k) std::memcpy(&a[16 * k], m->frames[k]->st.d, 16 * sizeof(double));
         double *S = &a[16 * K], *A0 = S + n * n + n;
         for (int k = 0; k < 6; ++k) { S[k * n + k] = 1.0e15; A0[k * n + k] = 1.0e30; }
@@ -751,6 +745,7 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
             for (Frame *f : m->marg.frames) g.mframes.push_back(f->tmp);
             d.marg_off = (long long)(((size_t)s.idx * 2 + m->marg.slot) * c->prior_stride);
             d.out_off = (long long)(((size_t)s.idx * 2 + (1 - m->marg.slot)) * c->prior_stride);
+            d.eigen_form = c->prm.prior_eigen_form;
             for (int i = 0; i < N; ++i) m->frames[i]->tmp = -1;
             g.md = d; g.has_marg = true;
             return 0; }); if (rc) return rc; }
@@ -778,7 +773,7 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
             for (xvbe::PreRef r : g.pref) { r.block += blk_base; c->pref.push(r); }
             app(c->pblocks, g.pblocks); app(c->mframes, g.mframes);
             d.scratch_off = (long long)scratch;
-            scratch += xvbe::marg_scratch_doubles(d.n_frames, d.n_lm);
+            scratch += xvbe::marg_scratch_doubles(d.n_frames, d.n_lm, d.n_rpe);
             c->mdesc.push(d);
             g.has_marg = false;
         }
@@ -830,7 +825,7 @@ int back_end_round(xrvio_ctx *c, std::vector<Session *> &act) {
 
 }  // namespace
 
-extern "C" int xrvio_step(xrvio_ctx *c) {
+static int lane_step(Lane *c) {
     if (!c) { xrvio_set_error("xrvio_step: null context"); return XRVIO_ERR_ARG; }
     CKC(cudaSetDevice(c->device));
     while (true) {

@@ -13,7 +13,7 @@
 namespace xvbe {
 using namespace xv;
 
-constexpr int ST = 256;                    // threads per CTA
+constexpr int ST = 512;                    // threads per CTA
 constexpr int NW = ST / 32;
 constexpr int HPACK = kNP * (kNP + 1) / 2;
 constexpr int kPreScratch = 1024;          // doubles of scratch per preintegration factor
@@ -24,12 +24,21 @@ constexpr double kFuncTol = 1e-6, kGradTol = 1e-10, kParamTol = 1e-8;
 constexpr double kMinDiag = 1e-6, kMaxDiag = 1e32, kMinMu = 1e-8, kMaxMu = 1.0, kMuInc = 10.0;
 constexpr int kMaxInvalid = 5;
 
+// in-kernel section timing (clock64 of thread 0 of window problems), read back through xrvio_debug_kprof
+__device__ unsigned long long g_kprof[32];
+struct KProf {
+    long long last; bool on;
+    __device__ void start(bool enable) { on = enable && threadIdx.x == 0; if (on) last = clock64(); }
+    __device__ void mark(int i) { if (on) { long long t = clock64(); atomicAdd(&g_kprof[i], (unsigned long long)(t - last)); last = t; } }
+};
+
 struct Smem {
     double H[HPACK];                       // packed lower-triangular, row i at i(i+1)/2
     double xs[kMaxFrames * 16];            // current iterate
     double cs[kMaxFrames * 16];            // candidate
     double us[kMaxFrames * 16];            // user memory (last state written back)
     double g[kNP], scale[kNP], D[kNP], y[kNP], bred[kNP];
+    double du[kNP], dw[kNP];               // unscaled steepest-descent / Gauss-Newton directions of the current linearisation
     double red[NW];
     double jrinv[kMaxActive * 9];
     unsigned char col_free[kNP];
@@ -81,11 +90,41 @@ struct Prob {
     const double *pre_blocks;
     const int *marg_frames;
     const double *marg_lin, *marg_S, *marg_info, *marg_A0;
-    int marg_n;
+    double *rpe_tb;                // per observation: tangent basis b1, b2 of the target bearing (6 doubles)
+    double *marg_St;               // transposed copy of the non-zero rows of S (scratch), St[c * rank + r]
+    int marg_n, marg_rank;
     // scratch (global)
-    double *inv_x, *inv_c, *h_ll, *g_l, *sc_l, *D_l, *y_l, *ht_l, *W, *Hcopy, *pre_s, *m_dx, *m_r, *m_v, *m_T;
+    double *inv_x, *inv_c, *h_ll, *g_l, *sc_l, *D_l, *y_l, *ht_l, *W, *Hcopy, *pre_s, *m_dx, *m_r, *m_v, *m_T, *du_l, *dw_l;
     int M, NPc;                    // free landmarks, pose/motion columns = 15 * n_active
 };
+
+// One-time per-problem precomputation: tangent bases of all reprojection observations.
+static __device__ void prepare_tangents(Prob &P, double *tb) {
+    P.rpe_tb = tb;
+    for (int o = threadIdx.x; o < P.d.n_rpe; o += ST) {
+        const RpeObs &ob = P.rpe[P.d.rpe_off + o];
+        const M3 T = local_tangent(ld3(ob.zt));
+        double *t = tb + (size_t)o * 6;
+        t[0] = T(0, 0); t[1] = T(1, 0); t[2] = T(2, 0); t[3] = T(0, 1); t[4] = T(1, 1); t[5] = T(2, 1);
+    }
+    __syncthreads();
+}
+
+// One-time preparation of the prior for a solve: number of leading non-zero rows (stored by the
+// marginalisation kernel behind A0; 0 = unknown) and a transposed copy of those rows.
+static __device__ void prepare_prior(Prob &P, const double *arena, double *St) {
+    const int n = P.marg_n;
+    P.marg_St = St;
+    if (P.d.marg_k <= 0) { P.marg_rank = 0; return; }
+    int rk = (int)arena[(size_t)16 * P.d.marg_k + 2 * (size_t)n * n + n];
+    if (rk <= 0 || rk > n) rk = n;
+    P.marg_rank = rk;
+    for (int e = threadIdx.x; e < rk * n; e += ST) {
+        const int r = e / n, c = e % n;
+        St[(size_t)c * rk + r] = P.marg_S[(size_t)r * n + c];
+    }
+    __syncthreads();
+}
 
 // ------------------------------------------------------------------------------------------------
 // Residual (+ Jacobian) evaluation at S (= xs or cs) / inv (= inv_x or inv_c).  Returns the cost.
@@ -93,7 +132,8 @@ struct Prob {
 // rebuilt.  Constant blocks and "user memory" reads come from us / invd_user.
 // ------------------------------------------------------------------------------------------------
 static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const double *inv, const RigParams &rg,
-                           bool want_jac, bool robust = true) {
+                           bool want_jac, bool robust = true, KProf *kp = nullptr) {
+    const int kb = want_jac ? 0 : 8;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M;
     if (want_jac) {
@@ -104,6 +144,7 @@ static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const
         for (int i = tid; i < nw; i += ST) P.W[i] = 0.0;
     }
     __syncthreads();
+    if (kp) kp->mark(kb + 0);
     double cost = 0.0;
     // ---------------- reprojection residuals (Cauchy loss) ----------------
     for (int base = warp * 32; base < P.d.n_rpe; base += NW * 32) {
@@ -122,7 +163,7 @@ static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const
             tf = ts < P.d.n_active && s.pose_free[ts];
             rf = !prior && rs < P.d.n_active && s.pose_free[rs];
             lf = !prior && lm < M;
-            rpe_eval(ld4(st), ld3(st + 4), ld4(sr), ld3(sr + 4), idp, ld3(ob.zt), ld3(ob.zr), rg, want_jac,
+            rpe_eval(ld4(st), ld3(st + 4), ld4(sr), ld3(sr + 4), idp, ld3(ob.zt), ld3(ob.zr), P.rpe_tb + (size_t)o * 6, rg, want_jac,
                      want_jac && !prior, e);
             const double sq = e.r[0] * e.r[0] + e.r[1] * e.r[1];
             if (robust) {
@@ -194,6 +235,7 @@ static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const
             }
         }
     }
+    if (kp) kp->mark(kb + 1);
     // ---------------- rotation priors (Cauchy loss), rare ----------------
     for (int o = tid; o < P.d.n_rot; o += ST) {
         const RotObs ob = P.rot[P.d.rot_off + o];
@@ -211,27 +253,38 @@ static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const
             }
         }
     }
-    // ---------------- preintegration factors (no loss), one warp per factor ----------------
-    for (int f = warp; f < P.d.n_pre; f += NW) {
+    if (kp) kp->mark(kb + 2);
+    // ---------------- preintegration factors (no loss) ----------------
+    // residuals (and raw Jacobians) of all factors are evaluated SIMT by the first n_pre threads; the
+    // whitening and J^T J products of the Jacobian pass are then done cooperatively, one warp per factor
+    if (tid < P.d.n_pre) {
+        const int f = tid;
         const PreRef pf = P.pre[P.d.pre_off + f];
         const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
         double *sc = P.pre_s + (size_t)f * kPreScratch;     // [0,15) r  [16,241) Ji  [241,466) Jj  [466,691) Jwi [691,916) Jwj [916,931) rw
         const double *si = pf.prior ? (s.us + pf.i * 16) : (S + pf.i * 16);
         const double *sj = S + pf.j * 16;
-        if (lane == 0) pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, want_jac, sc, sc + 16, sc + 241);
-        __syncwarp();
+        pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, want_jac, sc, sc + 16, sc + 241);
+    }
+    __syncthreads();
+    if (tid < 15 * P.d.n_pre) {          // whitened residual, one thread per row
+        const int f = tid / 15, r = tid % 15;
+        const PreRef pf = P.pre[P.d.pre_off + f];
+        const double *Sic = P.pre_blocks + (size_t)pf.block * kPreBlock + PB_SIC;
+        double *sc = P.pre_s + (size_t)f * kPreScratch;
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) a += Sic[r * 15 + k] * sc[k];
+        sc[916 + r] = a;
+        cost += 0.5 * a * a;
+    }
+    if (kp) kp->mark(kb + 3);
+    if (want_jac) __syncthreads();
+    for (int f = warp; want_jac && f < P.d.n_pre; f += NW) {
+        const PreRef pf = P.pre[P.d.pre_off + f];
+        const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
+        double *sc = P.pre_s + (size_t)f * kPreScratch;
         const double *Sic = pb + PB_SIC;
-        if (lane < 15) {
-            double a = 0.0;
-            for (int k = 0; k < 15; ++k) a += Sic[lane * 15 + k] * sc[k];
-            sc[916 + lane] = a;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            double a = 0.0;
-            for (int k = 0; k < 15; ++k) a += sc[916 + k] * sc[916 + k];
-            cost += 0.5 * a;
-        }
         if (!want_jac) continue;
         for (int e = lane; e < 450; e += 32) {              // whiten: Jw = sqrt_inv_cov * J
             const int which = e / 225, idx = e % 225, r = idx / 15, c = idx % 15;
@@ -284,6 +337,7 @@ static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const
         }
     }
     __syncthreads();
+    if (kp) kp->mark(kb + 4);
     // ---------------- marginalisation prior (no loss) ----------------
     if (P.d.marg_k > 0) {
         const int K = P.d.marg_k, n = P.marg_n;
@@ -295,17 +349,37 @@ static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const
                 for (int k = 0; k < 9; ++k) s.jrinv[tid * 9 + k] = Jri.m[k];
         }
         __syncthreads();
-        for (int r = warp; r < n; r += NW) {               // r = S dx + infovec, one warp per row
-            double a = 0.0;
-            for (int c = lane; c < n; c += 32) a += P.marg_S[(size_t)r * n + c] * P.m_dx[c];
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) { a += P.marg_info[r]; P.m_r[r] = a; cost += 0.5 * a * a; }
+        {   // r = S dx + infovec over the non-zero rows: one thread per row on the transposed copy (coalesced)
+            const int rk = P.marg_rank;
+            // 4 lanes per row (column slices c = q, q+4, ...), two independent accumulators per lane
+            for (int r0 = 0; r0 < rk; r0 += ST / 4) {
+                const int r = r0 + (tid >> 2), q = tid & 3;
+                double a0 = 0.0, a1 = 0.0;
+                if (r < rk) {
+                    int cidx = q;
+                    for (; cidx + 4 < n; cidx += 8) {
+                        a0 += P.marg_St[(size_t)cidx * rk + r] * P.m_dx[cidx];
+                        a1 += P.marg_St[(size_t)(cidx + 4) * rk + r] * P.m_dx[cidx + 4];
+                    }
+                    for (; cidx < n; cidx += 4) a0 += P.marg_St[(size_t)cidx * rk + r] * P.m_dx[cidx];
+                }
+                double a = a0 + a1;
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                if (r < rk && q == 0) {
+                    a += P.marg_info[r];
+                    P.m_r[r] = a;
+                    cost += 0.5 * a * a;
+                }
+            }
+            // rows beyond the rank are exactly zero in S; their residual is infovec[r] (zero for our priors)
+            for (int r = rk + tid; r < n; r += ST) { const double a = P.marg_info[r]; P.m_r[r] = a; cost += 0.5 * a * a; }
         }
         if (want_jac) {
             __syncthreads();
             for (int c = tid; c < n; c += ST) {            // v = S^T r
                 double a = 0.0;
-                for (int r = 0; r < n; ++r) a += P.marg_S[(size_t)r * n + c] * P.m_r[r];
+                for (int r = 0; r < P.marg_rank; ++r) a += P.marg_S[(size_t)r * n + c] * P.m_r[r];
                 P.m_v[c] = a;
             }
             // T = A0 * B  (B = blockdiag(Jr^-1 on q blocks, I))
@@ -351,7 +425,9 @@ static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const
             }
         }
     }
+    if (kp) kp->mark(kb + 5);
     cost = block_sum(cost, s);
+    if (kp) kp->mark(kb + 6);
     if (want_jac) {
         // constant columns: unit diagonal, zero gradient (their off-diagonals were never accumulated)
         for (int c = tid; c < P.NPc; c += ST)
