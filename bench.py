@@ -75,9 +75,25 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(self.reasons)}
 
 
+def stream_seeds(rank, n_streams=None):
+    """Session -> synthetic stream seed; ranks own disjoint seed ranges (seeds = 1000*rank + i)."""
+    return [1000 * rank + i for i in range(n_streams or N_STREAMS)]
+
+
+def reduce_max_ms(ms, device=None):
+    """Whole-job time = max over ranks (the only collective of the harness)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(ms)
+    t = torch.tensor([ms], device=device if device is not None else 'cpu', dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def build_streams(rank, n_frames):
     from oracle.synth import Stream
-    streams = [Stream(1000 * rank + i, W_IMG, H_IMG) for i in range(N_STREAMS)]
+    streams = [Stream(seed, W_IMG, H_IMG) for seed in stream_seeds(rank)]
     imus = [s.imu(n_frames * s.imu_per_cam + 2) for s in streams]
     return streams, imus
 
@@ -181,14 +197,7 @@ def run_cuda_arm(args, rank, world, local_rank):
     r_dev = one_run(dev_ptrs, True, False, True)
     r_e2e = one_run(host_ptrs, False, True, False)
 
-    def agg_ms(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    ms_dev, ms_e2e = agg_ms(r_dev['ms']), agg_ms(r_e2e['ms'])
+    ms_dev, ms_e2e = reduce_max_ms(r_dev['ms'], dev), reduce_max_ms(r_e2e['ms'], dev)
     if rank != 0:
         return
     s0, s1 = r_dev['stats0'], r_dev['stats1']

@@ -61,3 +61,58 @@ def test_batched_sessions_are_independent(xrvio):
     b2 = np.array([p for (_, _, p) in solo[0]])
     assert np.abs(b - b2).max() < 1e-6
     ctx.close(); ctx2.close()
+
+
+def test_xrslam_c_abi_shim_player_protocol(xrvio, golden_dir):
+    """Drives libxrvio.so through the reference's outer C ABI the way xrslam-pc/player does (main.cpp:116-165):
+    gyroscope and accelerometer samples in time order, then the image, RunOneFrame, GetResult(STATE / BODY_POSE).
+    The trajectory must equal the one obtained through the batched session API."""
+    import ctypes as C
+    dll = C.CDLL(xrvio.LIB_PATH)
+
+    class Img(C.Structure):
+        _fields_ = [('data', C.c_void_p), ('timeStamp', C.c_double), ('stride', C.c_int), ('camera_id', C.c_int), ('channel', C.c_int), ('ext', C.c_void_p)]
+
+    class Vec(C.Structure):
+        _fields_ = [('data', C.c_double * 3), ('timestamp', C.c_double)]
+
+    class Pose(C.Structure):
+        _fields_ = [('quaternion', C.c_double * 4), ('translation', C.c_double * 3), ('timestamp', C.c_double)]
+    cfg = C.c_void_p()
+    assert dll.XRSLAMCreate(os.path.join(golden_dir, 'synth_slam.yaml').encode(), os.path.join(golden_dir, 'synth_sensor.yaml').encode(), b'', b'test', C.byref(cfg)) == 1
+    s = Stream(3)
+    n_frames = 50
+    imu = s.imu(n_frames * s.imu_per_cam + 2)
+    dll.XRSLAMExtPushBootstrapState.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    for k in range(40):
+        q, p, v = s.gt_state(s.frame_time(k))
+        dll.XRSLAMExtPushBootstrapState(s.frame_time(k), (C.c_double * 4)(*q), (C.c_double * 3)(*p), (C.c_double * 3)(*v))
+    k_imu = 0
+    poses = []
+    for k in range(n_frames):
+        t_img = s.frame_time(k)
+        while k_imu < len(imu) and imu[k_imu, 0] <= t_img + 1e-9:
+            g = Vec((C.c_double * 3)(*imu[k_imu, 1:4]), imu[k_imu, 0])
+            a = Vec((C.c_double * 3)(*imu[k_imu, 4:7]), imu[k_imu, 0])
+            dll.XRSLAMPushSensorData(3, C.byref(g))      # XRSLAM_SENSOR_GYROSCOPE
+            dll.XRSLAMPushSensorData(2, C.byref(a))      # XRSLAM_SENSOR_ACCELERATION
+            k_imu += 1
+        im = np.ascontiguousarray(s.frame(k))
+        img = Img(im.ctypes.data, t_img, im.shape[1], 0, 1, None)
+        dll.XRSLAMPushSensorData(0, C.byref(img))
+        dll.XRSLAMRunOneFrame()
+        st = C.c_int(-1)
+        dll.XRSLAMGetResult(2, C.byref(st))
+        if st.value == 1:
+            po = Pose()
+            dll.XRSLAMGetResult(0, C.byref(po))
+            if po.timestamp > 0:
+                poses.append([po.timestamp] + list(po.translation))
+    dll.XRSLAMDestroy()
+    assert len(poses) >= 10
+    ctx, outs = drive.run_streams_cuda([s], n_frames)
+    ref = np.array([[t] + list(p) for (t, q, p) in outs[0]])
+    got = np.array(poses)
+    assert got.shape == ref.shape and np.allclose(got[:, 0], ref[:, 0])
+    assert np.abs(got[:, 1:] - ref[:, 1:]).max() < 1e-6
+    ctx.close()

@@ -17,6 +17,7 @@ SOURCES = {
     "backend_marg.cu": [],
     "capi_ops.cu": [],
     "capi_session.cu": [],
+    "xrslam_shim.cu": [],
 }
 
 

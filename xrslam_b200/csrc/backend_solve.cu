@@ -61,45 +61,52 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
     schur_landmarks(P, s, s.bred);
     __syncthreads();
     if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[24], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
-    // in-place right-looking Cholesky on the packed lower triangle
+    // in-place right-looking Cholesky on the packed lower triangle.  The scaled pivot column is mirrored
+    // into a contiguous vector (s.du, free at this point) so the trailing update reads it conflict-free;
+    // 1/L_jj is kept in s.dw for the substitutions.
     if (tid == 0) s.flag = 1;
     __syncthreads();
+    double *col = s.du, *idiag = s.dw;
     for (int j = 0; j < n; ++j) {
         const double d = s.H[hidx(j, j)];
         if (!(d > 0.0) || !isfinite(d)) {
             if (tid == 0) s.flag = 0;
             break;                                   // uniform: every thread reads the same d
         }
-        const double inv = 1.0 / sqrt(d);
+        const double inv = rsqrt(d);
         __syncthreads();
-        for (int i = j + tid; i < n; i += ST) s.H[hidx(i, j)] = (i == j) ? sqrt(d) : s.H[hidx(i, j)] * inv;
-        __syncthreads();
-        for (int i = j + 1 + warp; i < n; i += NW) {
-            const double lij = s.H[hidx(i, j)];
-            if (lij == 0.0) continue;
-            const int row = i * (i + 1) / 2;
-            for (int k = j + 1 + lane; k <= i; k += 32) s.H[row + k] -= lij * s.H[hidx(k, j)];
+        for (int i = j + tid; i < n; i += ST) {
+            const double v = (i == j) ? d * inv : s.H[hidx(i, j)] * inv;
+            s.H[hidx(i, j)] = v;
+            col[i] = v;
+            if (i == j) idiag[j] = inv;
         }
         __syncthreads();
+        for (int i = j + 1 + warp; i < n; i += NW) {
+            const double lij = col[i];
+            if (lij == 0.0) continue;
+            double *row = s.H + i * (i + 1) / 2;
+            for (int k = j + 1 + lane; k <= i; k += 32) row[k] -= lij * col[k];
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[25], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
     if (!s.flag) return false;
-    // forward / backward substitution (L z = b, L^T y = z)
+    // forward / backward substitution (L z = b, L^T y = z), one barrier per column
+    // forward: work vector s.y (starts as b_red), result z in s.bred; backward: work vector s.bred, result in s.y.
+    // Each column reads one finished entry and writes a different array, so one barrier per column suffices.
     for (int c = tid; c < n; c += ST) s.y[c] = s.bred[c];
     __syncthreads();
     for (int j = 0; j < n; ++j) {
-        if (tid == 0) s.y[j] /= s.H[hidx(j, j)];
-        __syncthreads();
-        const double yj = s.y[j];
-        for (int i = j + 1 + tid; i < n; i += ST) s.y[i] -= s.H[hidx(i, j)] * yj;
+        const double zj = s.y[j] * idiag[j];
+        for (int i = j + 1 + tid; i < n; i += ST) s.y[i] -= s.H[hidx(i, j)] * zj;
+        if (tid == 0) s.bred[j] = zj;
         __syncthreads();
     }
     for (int j = n - 1; j >= 0; --j) {
-        if (tid == 0) s.y[j] /= s.H[hidx(j, j)];
-        __syncthreads();
-        const double yj = s.y[j];
-        for (int i = tid; i < j; i += ST) s.y[i] -= s.H[hidx(j, i)] * yj;
+        const double yj = s.bred[j] * idiag[j];
+        for (int i = tid; i < j; i += ST) s.bred[i] -= s.H[hidx(j, i)] * yj;
+        if (tid == 0) s.y[j] = yj;
         __syncthreads();
     }
     if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[26], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
