@@ -67,26 +67,84 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
     if (tid == 0) s.flag = 1;
     __syncthreads();
     double *col = s.du, *idiag = s.dw;
-    for (int j = 0; j < n; ++j) {
-        const double d = s.H[hidx(j, j)];
-        if (!(d > 0.0) || !isfinite(d)) {
-            if (tid == 0) s.flag = 0;
-            break;                                   // uniform: every thread reads the same d
+    // Register-resident Cholesky: the lower triangle is cut into 6x6 tiles, one tile per thread (n <= 180 ->
+    // <= 465 tiles), held in registers for the whole factorisation.  Per column: the owners of that column scale it
+    // and publish it in shared memory (barrier), every thread applies the rank-1 update to its tile from 12
+    // shared-memory reads (barrier).  Shared memory only carries the pivot column, not the matrix.
+    {
+        constexpr int TB = 6;
+        const int nt = (n + TB - 1) / TB;
+        int ti = -1, tk = -1;
+        if (tid < nt * (nt + 1) / 2) {
+            ti = (int)((sqrt(8.0 * tid + 1.0) - 1.0) * 0.5);
+            while (ti * (ti + 1) / 2 > tid) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
+            tk = tid - ti * (ti + 1) / 2;
         }
-        const double inv = rsqrt(d);
+        double a[TB][TB];
+#pragma unroll
+        for (int li = 0; li < TB; ++li)
+#pragma unroll
+            for (int lk = 0; lk < TB; ++lk) {
+                const int gi = ti * TB + li, gk = tk * TB + lk;
+                a[li][lk] = (ti >= 0 && gi < n && gk <= gi) ? s.H[hidx(gi, gk)] : 0.0;
+            }
+        if (tid == 0) s.sc[14] = a[0][0];
         __syncthreads();
-        for (int i = j + tid; i < n; i += ST) {
-            const double v = (i == j) ? d * inv : s.H[hidx(i, j)] * inv;
-            s.H[hidx(i, j)] = v;
-            col[i] = v;
-            if (i == j) idiag[j] = inv;
+        for (int j = 0; j < n; ++j) {
+            const double d = s.sc[14];
+            if (!(d > 0.0) || !isfinite(d)) {
+                if (tid == 0) s.flag = 0;
+                break;                               // uniform: every thread reads the same d
+            }
+            const double inv = rsqrt(d);
+            const int jt = j / TB, lj = j - jt * TB;
+            if (tk == jt) {
+#pragma unroll
+                for (int lk = 0; lk < TB; ++lk) {
+                    if (lk != lj) continue;
+#pragma unroll
+                    for (int li = 0; li < TB; ++li) {
+                        const int gi = ti * TB + li;
+                        if (gi >= j && gi < n) {
+                            const double v = (gi == j) ? d * inv : a[li][lk] * inv;
+                            a[li][lk] = v;
+                            col[gi] = v;
+                            if (gi == j) idiag[j] = inv;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (tk >= jt) {                          // tiles entirely left of column j are final
+                double ci[TB], ck[TB];
+#pragma unroll
+                for (int l = 0; l < TB; ++l) {
+                    const int gi = ti * TB + l, gk = tk * TB + l;
+                    ci[l] = (gi > j && gi < n) ? col[gi] : 0.0;
+                    ck[l] = (gk > j && gk < n) ? col[gk] : 0.0;
+                }
+#pragma unroll
+                for (int li = 0; li < TB; ++li)
+#pragma unroll
+                    for (int lk = 0; lk < TB; ++lk) a[li][lk] -= ci[li] * ck[lk];
+                const int jn = j + 1, jnt = jn / TB, ljn = jn - jnt * TB;
+                if (ti == jnt && tk == jnt) {
+#pragma unroll
+                    for (int l = 0; l < TB; ++l) if (l == ljn) s.sc[14] = a[l][l];
+                }
+            }
+            __syncthreads();
         }
         __syncthreads();
-        for (int i = j + 1 + warp; i < n; i += NW) {
-            const double lij = col[i];
-            if (lij == 0.0) continue;
-            double *row = s.H + i * (i + 1) / 2;
-            for (int k = j + 1 + lane; k <= i; k += 32) row[k] -= lij * col[k];
+        if (s.flag) {
+#pragma unroll
+            for (int li = 0; li < TB; ++li)
+#pragma unroll
+                for (int lk = 0; lk < TB; ++lk) {
+                    const int gi = ti * TB + li, gk = tk * TB + lk;
+                    if (ti >= 0 && gi < n && gk <= gi) s.H[hidx(gi, gk)] = a[li][lk];
+                }
         }
     }
     __syncthreads();
