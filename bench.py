@@ -130,6 +130,8 @@ def run_cuda_arm(args, rank, world, local_rank):
     from oracle import drive
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # several ranks share the host: give each its share of cores for the library's bookkeeping threads
+    os.environ.setdefault('XRVIO_HOST_THREADS', str(max(8, min(64, (os.cpu_count() or 8) // max(world, 1)))))
     K, Wm = args.steps, max(args.warmup, 3)
     n_frames = PRIME_FRAMES + Wm + K + 1
     streams, imus = build_streams(rank, n_frames)
@@ -230,8 +232,11 @@ def run_cuda_arm(args, rank, world, local_rank):
     else:
         algo_bytes = 0.0
     achieved = algo_bytes / (fam_ms * 1e-3) / 1e9 if fam_ms > 0 else 0.0
+    # DRAM traffic of one 64-problem window-BA launch of the solve kernel from the committed ncu --set full capture
+    # (profiles/r1_ncu_full_raw.csv: dram__bytes_read.sum 32.53 MB + dram__bytes_write.sum 10.32 MB); other families: not captured
+    traffic = 42.85e6 if dom == 'solve' else None
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'launches': n_launch, 'avg_launch_ms': fam_ms / n_launch,
+                'frac': achieved / peak, 'traffic': traffic, 'launches': n_launch, 'avg_launch_ms': fam_ms / n_launch,
                 'share_of_kernel_time': fam_ms / max(sum(v[0] for v in kt.values()), 1e-9),
                 'family_ms': {k: round(v[0], 3) for k, v in kt.items()}}
     out = {

@@ -7,7 +7,8 @@ Outputs:
   frontend_kat.npz      oracle front-end results on that pair (counts the reference asserts: 164 / 161)
   backend_problems.npz  one recorded problem of every solve kind + a marginalisation, before / after the oracle
   preint.npz            preintegration jobs and oracle results
-  stream3_traj.npz      oracle trajectory of synthetic stream seed 3 (first 60 frames)
+  stream3_traj.npz      oracle trajectory of synthetic stream seed 3 (first 66 frames)
+  stream7_traj140.npz   oracle trajectory of synthetic stream seed 7, 140 frames (steady-state marginalisation)
 """
 import os
 import shutil
@@ -117,7 +118,16 @@ def preint():
     print('preintegration goldens saved')
 
 
+def long_trajectory():
+    s = Stream(7)
+    sess = run_stream(s, 140)
+    traj = np.array([[t] + list(q) + list(p) for (t, q, p) in sess.outputs])
+    np.savez_compressed(os.path.join(HERE, 'stream7_traj140.npz'), traj=traj)
+    print('long trajectory rows', len(traj))
+
+
 if __name__ == '__main__':
+    long_trajectory()
     frontend_kat()
     preint()
     backend_problems()

@@ -45,6 +45,21 @@ def test_single_stream_matches_golden_trajectory(xrvio, golden_dir):
     ctx.close()
 
 
+def test_long_stream_ate_vs_oracle(xrvio, golden_dir):
+    """140 frames (100+ tracked, ~25 window BAs with marginalisation in steady state): ATE <= 1e-3 m vs the oracle."""
+    ref = np.load(os.path.join(golden_dir, 'stream7_traj140.npz'))['traj']
+    s = Stream(7)
+    ctx, outs = drive.run_streams_cuda([s], 140)
+    got = np.array([[t] + list(q) + list(p) for (t, q, p) in outs[0]])
+    assert got.shape == ref.shape and np.allclose(got[:, 0], ref[:, 0])
+    ate = _ate(ref[:, 5:8], got[:, 5:8])
+    raw = np.linalg.norm(got[:, 5:8] - ref[:, 5:8], axis=1)
+    assert ate <= 1e-3, (ate, raw.max())
+    st = ctx.stats()
+    assert st['marginalizations'] >= 15
+    ctx.close()
+
+
 def test_batched_sessions_are_independent(xrvio):
     """Sessions advanced in one batch give exactly the result of the same stream run alone."""
     streams = [Stream(3), Stream(4), Stream(3)]

@@ -194,7 +194,9 @@ def test_c_abi_exports_every_declared_symbol():
     from xrslam_b200 import capi
     hdr = open(os.path.join(os.path.dirname(capi._HERE), 'include', 'xrvio.h')).read()
     names = set(re.findall(r'\b(xrvio_[a-z_0-9]+)\s*\(', hdr))
-    assert len(names) >= 25
+    hdr2 = open(os.path.join(os.path.dirname(capi._HERE), 'include', 'xrslam_compat.h')).read()
+    names |= set(re.findall(r'\b(XRSLAM[A-Za-z]+)\s*\(', hdr2))
+    assert len(names) >= 31 and 'XRSLAMCreate' in names
     dll = ctypes.CDLL(capi.LIB_PATH)
     for n in sorted(names):
         assert hasattr(dll, n), 'libxrvio.so does not export ' + n
