@@ -349,6 +349,8 @@ def main():
         run_reference_arm(args, rank, world)
         return
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'        # keep stdout to the single JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)

@@ -94,14 +94,13 @@ int xrvio_op_gftt(const uint8_t *img, int n, int w, int h, int max_corners, doub
     if (!img || !corners || !count || n <= 0 || w < 8 || h < 8) return fail_arg("xrvio_op_gftt: bad argument");
     if (max_corners > XRVIO_MAX_CORNERS) { xrvio_set_error("xrvio_op_gftt: max_corners > XRVIO_MAX_CORNERS"); return XRVIO_ERR_LIMIT; }
     const size_t bytes = (size_t)n * w * h;
-    DevBuf d_img, d_cor, d_cnt, d_cand, d_cc, d_max, d_resp;
-    CK(d_resp.alloc(bytes * sizeof(float)));
+    DevBuf d_img, d_cor, d_cnt, d_cand, d_cc, d_max;
     CK(d_img.alloc(bytes)); CK(d_cor.alloc((size_t)n * xvfe::kMaxCorners * 3 * sizeof(float))); CK(d_cnt.alloc(n * sizeof(int)));
     CK(d_cand.alloc((size_t)n * xvfe::kMaxCand * 8)); CK(d_cc.alloc(n * sizeof(int))); CK(d_max.alloc(n * sizeof(unsigned)));
     CK(cudaMemcpy(d_img.p, img, bytes, cudaMemcpyHostToDevice));
     CK(cudaMemset(d_cor.p, 0, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float)));
     xvfe::gftt_harris(d_img.as<uint8_t>(), nullptr, (size_t)w * h, n, w, h, max_corners, (float)quality, (float)min_distance,
-                      d_cor.as<float>(), d_cnt.as<int>(), d_cand.as<unsigned long long>(), d_cc.as<int>(), d_max.as<unsigned>(), d_resp.as<float>(), 0);
+                      d_cor.as<float>(), d_cnt.as<int>(), d_cand.as<unsigned long long>(), d_cc.as<int>(), d_max.as<unsigned>(), 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(corners, d_cor.p, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(count, d_cnt.p, n * sizeof(int), cudaMemcpyDeviceToHost));

@@ -153,11 +153,9 @@ struct Lane {
     xrvio_stats stats{};
     // ---- device image / front-end buffers ----
     uint8_t *d_raw = nullptr;          // S * kImgQueue * w*h
-    uint8_t *d_stage = nullptr;        // S * w*h  contiguous batch for CLAHE input
     uint8_t *d_pyr = nullptr;          // S * kPyrSlots * L.total
-    uint8_t *d_pyr_prev_batch = nullptr, *d_pyr_next_batch = nullptr;   // S * L.total contiguous batches for KLT
     uint8_t *d_lut = nullptr;
-    unsigned long long *d_cand = nullptr; int *d_cand_count = nullptr; unsigned *d_maxval = nullptr; float *d_resp = nullptr;
+    unsigned long long *d_cand = nullptr; int *d_cand_count = nullptr; unsigned *d_maxval = nullptr;
     Arena<float> corners; Arena<int> corner_count;
     Arena<float> klt_prev, klt_next; Arena<int> klt_n; Arena<unsigned char> klt_status;
     Arena<double> poi_pts; Arena<int> poi_npre, poi_ntot; Arena<unsigned char> poi_veto, poi_keep;
@@ -190,6 +188,15 @@ struct PhaseTimer {
     Lane *c; int id; std::chrono::steady_clock::time_point t0;
     PhaseTimer(Lane *c_, int id_) : c(c_), id(id_), t0(std::chrono::steady_clock::now()) {}
     ~PhaseTimer() { c->phase_ms[id] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+// consecutive phases of a step: pt.next(id) closes the running phase and opens the next one
+struct PhaseClock {
+    Lane *c; int id; std::chrono::steady_clock::time_point t0;
+    PhaseClock(Lane *c_, int id_) : c(c_), id(id_), t0(std::chrono::steady_clock::now()) {}
+    void next(int nid) { stop(); id = nid; t0 = std::chrono::steady_clock::now(); }
+    void stop() { if (id >= 0) c->phase_ms[id] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); id = -1; }
+    ~PhaseClock() { stop(); }
 };
 
 // kernel families for xrvio_get_kernel_times
@@ -532,15 +539,11 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
     const size_t P = (size_t)p->width * p->height;
     const int S = n_sessions;
     CKC(cudaMalloc((void **)&c->d_raw, (size_t)S * kImgQueue * P));
-    CKC(cudaMalloc((void **)&c->d_stage, (size_t)S * P));
     CKC(cudaMalloc((void **)&c->d_pyr, (size_t)S * kPyrSlots * c->L.total));
-    CKC(cudaMalloc((void **)&c->d_pyr_prev_batch, (size_t)S * c->L.total));
-    CKC(cudaMalloc((void **)&c->d_pyr_next_batch, (size_t)S * c->L.total));
     CKC(cudaMalloc((void **)&c->d_lut, (size_t)S * p->clahe_width * p->clahe_height * 256));
     CKC(cudaMalloc((void **)&c->d_cand, (size_t)S * xvfe::kMaxCand * 8));
     CKC(cudaMalloc((void **)&c->d_cand_count, S * sizeof(int)));
     CKC(cudaMalloc((void **)&c->d_maxval, S * sizeof(unsigned)));
-    CKC(cudaMalloc((void **)&c->d_resp, (size_t)S * P * sizeof(float)));
     CKC(c->corners.reserve((size_t)S * xvfe::kMaxCorners * 3)); CKC(c->corner_count.reserve(S));
     CKC(c->klt_prev.reserve((size_t)S * xvfe::kMaxPts * 2)); CKC(c->klt_next.reserve((size_t)S * xvfe::kMaxPts * 2));
     CKC(c->klt_n.reserve(S)); CKC(c->klt_status.reserve((size_t)S * xvfe::kMaxPts));
@@ -572,8 +575,8 @@ static int lane_destroy(Lane *c) {
     if (!c) return XRVIO_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
-    cudaFree(c->rig_d); cudaFree(c->d_raw); cudaFree(c->d_stage); cudaFree(c->d_pyr); cudaFree(c->d_pyr_prev_batch); cudaFree(c->d_pyr_next_batch);
-    cudaFree(c->d_lut); cudaFree(c->d_cand); cudaFree(c->d_cand_count); cudaFree(c->d_maxval); cudaFree(c->d_resp); cudaFree(c->d_prior);
+    cudaFree(c->rig_d); cudaFree(c->d_raw); cudaFree(c->d_pyr); 
+    cudaFree(c->d_lut); cudaFree(c->d_cand); cudaFree(c->d_cand_count); cudaFree(c->d_maxval); cudaFree(c->d_prior);
     cudaStreamDestroy(c->st);
     delete c;
     return XRVIO_OK;

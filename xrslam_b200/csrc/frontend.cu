@@ -486,11 +486,10 @@ __global__ void __launch_bounds__(1024) corner_select_kernel(unsigned long long 
 
 void gftt_harris(const uint8_t *img, const int *idx, size_t img_stride, int n, int w, int h, int max_corners, float quality,
                  float min_distance, float *corners, int *count, unsigned long long *cand, int *cand_count,
-                 unsigned int *maxval, float *resp_map, cudaStream_t st) {
+                 unsigned int *maxval, cudaStream_t st) {
     cudaMemsetAsync(maxval, 0, sizeof(unsigned int) * n, st);
     cudaMemsetAsync(cand_count, 0, sizeof(int) * n, st);
     dim3 grid((w + HT_W - 1) / HT_W, (h + HT_H - 1) / HT_H, n);
-    (void)resp_map;
     harris_nms_kernel<<<grid, 256, 0, st>>>(img, idx, img_stride, w, h, maxval, cand, cand_count);
     int cell = (int)lrintf(min_distance);
     int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;

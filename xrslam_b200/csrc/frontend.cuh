@@ -40,10 +40,10 @@ void pyramid(uint8_t *pyr, const int *idx /* pyramid index per batch item, may b
 void scharr(const uint8_t *img, int16_t *deriv, int n, int w, int h, cudaStream_t st);
 // ---- K3: GFTT with Harris response.  img: n images (stride `img_stride` bytes between images).
 // corners: n * kMaxCorners * 3 floats (x, y, response); count: n ints.
-// scratch: cand (n * kMaxCand * 8 bytes), cand_count (n ints), maxval (n uint32), resp_map (n * w*h floats)
+// scratch: cand (n * kMaxCand * 8 bytes), cand_count (n ints), maxval (n uint32)
 void gftt_harris(const uint8_t *img, const int *idx, size_t img_stride, int n, int w, int h, int max_corners, float quality,
                  float min_distance, float *corners, int *count, unsigned long long *cand, int *cand_count,
-                 unsigned int *maxval, float *resp_map, cudaStream_t st);
+                 unsigned int *maxval, cudaStream_t st);
 // ---- K4: pyramidal LK forward + gates + backward + 0.5 px check (opencv_image.cpp:75-154).
 // prev_pyr / next_pyr: n pyramids.  pts: n * kMaxPts * 2 floats.  npts: n ints.
 // next_pts in: initial guess (gyro prediction); out: tracked position.  status out: n * kMaxPts bytes.

@@ -39,7 +39,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
     const size_t P = (size_t)w * h;
     StepBuffers &B = sb(c);
     CKC(B.idx_raw.reserve(n)); CKC(B.idx_next.reserve(n)); CKC(B.idx_prev.reserve(n));
-    PhaseTimer *pt = new PhaseTimer(c, 0);
+    PhaseClock pt(c, 0);
     // ---- phase A: CLAHE + pyramid + GFTT on the new image; preintegration (no Jacobian / covariance) ----
     { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
         s.stg.clear_jobs();
@@ -78,7 +78,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         }
         return 0; }); if (rc) return rc; }
     { int rc = merge_preint_jobs(c, act); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 1);
+    pt.next(1);
     CKC(cudaMemcpyAsync(B.idx_raw.d, B.idx_raw.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
     CKC(cudaMemcpyAsync(B.idx_next.d, B.idx_next.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
     { ProfScope ps(c, FAM_CLAHE, 2);
@@ -87,7 +87,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
     { ProfScope ps(c, FAM_PYRAMID, 3); xvfe::pyramid(c->d_pyr, B.idx_next.d, n, c->L, c->st); }
     { ProfScope ps(c, FAM_GFTT, 2);
       xvfe::gftt_harris(c->d_pyr, B.idx_next.d, c->L.total, n, w, h, c->prm.max_keypoint_detection, 1.0e-3f, 20.0f, c->corners.d,
-                        c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->d_resp, c->st); }
+                        c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->st); }
     c->stats.kernels_launched += 2 + 3 + 2;
     CKC(cudaMemcpyAsync(c->corners.h, c->corners.d, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     CKC(cudaMemcpyAsync(c->corner_count.h, c->corner_count.d, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -95,7 +95,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
     { int rc = run_preint_jobs(c); if (rc) return rc; }     // also synchronises the stream
     if (c->pre_jobs.n == 0) CKC(cudaStreamSynchronize(c->st));
     CKC(cudaGetLastError());
-    delete pt; pt = new PhaseTimer(c, 2);
+    pt.next(2);
     // ---- phase B: pyramidal LK (previous pyramid -> new pyramid), gyro-predicted initial guess ----
     std::atomic<int> n_klt_a{0};
     { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
@@ -130,7 +130,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         n_klt_a += np;
     return 0; }); if (rc) return rc; }
     const int n_klt = n_klt_a.load();
-    delete pt; pt = new PhaseTimer(c, 3);
+    pt.next(3);
     if (n_klt > 0) {
         const size_t pb = (size_t)n * xvfe::kMaxPts * 2 * sizeof(float);
         CKC(cudaMemcpyAsync(c->klt_prev.d, c->klt_prev.h, pb, cudaMemcpyHostToDevice, c->st));
@@ -146,7 +146,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         c->stats.h2d_bytes += 2 * pb + 2 * n * sizeof(int);
         c->stats.d2h_bytes += pb + (size_t)n * xvfe::kMaxPts;
     }
-    delete pt; pt = new PhaseTimer(c, 4);
+    pt.next(4);
     // ---- phase C: Frame::track_keypoints after the LK call (frame.cpp:99-173) ----
     std::atomic<int> any_track_a{0};
     { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
@@ -197,9 +197,9 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         if (!s.order.empty()) any_track_a = 1;
     return 0; }); if (rc) return rc; }
     const bool any_track = any_track_a.load() != 0;
-    delete pt; pt = new PhaseTimer(c, 5);
+    pt.next(5);
     if (any_track) { int rc = run_poisson(c, n, true); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 6);
+    pt.next(6);
     { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
         if (!s.fe_has_last) return 0;
         Frame *f = s.cur.get();
@@ -222,7 +222,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
             s.has_latest = true; s.latest_t = f->t; s.latest = f->st;
         }
         return 0; }); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 7);
+    pt.next(7);
     // ---- phase D: Frame::detect_keypoints (frame.cpp:55-72, opencv_image.cpp:46-72) ----
     { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
         Frame *f = s.cur.get();
@@ -239,9 +239,9 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         }
         s.n_corners = nc;
         return 0; }); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 8);
+    pt.next(8);
     { int rc = run_poisson(c, n, false); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 9);
+    pt.next(9);
     { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
         Frame *f = s.cur.get();
         const int npre = c->poi_npre.h[i];
@@ -261,7 +261,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         }
     return 0; }); if (rc) return rc; }
     c->stats.frames_processed += n;
-    delete pt;
+    pt.stop();
     return XRVIO_OK;
 }
 
@@ -420,7 +420,7 @@ bool manage_keyframe(Lane *c, Session &s) {
 namespace {
 
 int back_end_round(Lane *c, std::vector<Session *> &act) {
-    PhaseTimer *pt = new PhaseTimer(c, 10);
+    PhaseClock pt(c, 10);
     // ---- phase E: mirror + preintegration with Jacobians and covariance ----
     { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
         s.stg.clear_jobs();
@@ -441,9 +441,9 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         }
         return 0; }); if (rc) return rc; }
     { int rc = merge_preint_jobs(c, act); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 11);
+    pt.next(11);
     { int rc = run_preint_jobs(c); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 12);
+    pt.next(12);
     // ---- phase F: bootstrap triangulation; localize / initial BA problems ----
     bool any_boot = false;
     for (Session *sp : act) any_boot = any_boot || sp->be_mode == 1;
@@ -501,9 +501,9 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         }
         return 0; }); if (rc) return rc; }
     { int rc = merge_problems(c, act, 1); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 13);
+    pt.next(13);
     { int rc = run_solves(c); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 14);
+    pt.next(14);
     std::atomic<long long> n_win{0}, n_loc{0}, n_sub{0};
     { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
         s.stg.clear_jobs();
@@ -525,9 +525,9 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         }
         return 0; }); if (rc) return rc; }
     { int rc = merge_tri_jobs(c, act); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 15);
+    pt.next(15);
     { int rc = run_triangulation(c); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 16);
+    pt.next(16);
     // ---- phase H: preintegration for refine_window / refine_subwindow ----
     { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
         s.stg.clear_jobs();
@@ -577,9 +577,9 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         }
         return 0; }); if (rc) return rc; }
     { int rc = merge_preint_jobs(c, act); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 17);
+    pt.next(17);
     { int rc = run_preint_jobs(c); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 18);
+    pt.next(18);
     // ---- refine_window / refine_subwindow problems ----
     // initial priors (estimation/marginalization_factor.h:18-33): zero information except 1e15 on frame-0 q and p
     for (Session *sp : act) {
@@ -654,9 +654,9 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         frame->fix_pose = frame->fix_motion = false;
         return rc2; }); if (rc) return rc; }
     { int rc = merge_problems(c, act, 2); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 19);
+    pt.next(19);
     { int rc = run_solves(c); if (rc) return rc; }
-    delete pt; pt = new PhaseTimer(c, 20);
+    pt.next(20);
     { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
         if (s.prob2 < 0) return 0;
         writeback(c, s, s.prob2);
@@ -694,7 +694,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
             c->stats.last_window_cost_final = c->sout.h[sp->prob2].final_cost;
         }
     c->stats.window_solves += n_win; c->stats.localize_solves += n_loc; c->stats.subwindow_solves += n_sub;
-    delete pt; pt = new PhaseTimer(c, 21);
+    pt.next(21);
     // ---- slide_window: marginalise frame 0 while the window is too long (:360-368, map.cpp:51-63) ----
     while (true) {
         { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
@@ -809,7 +809,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         });
         c->stats.marginalizations += nm;
     }
-    delete pt; pt = new PhaseTimer(c, 22);
+    pt.next(22);
     // ---- FrontendWorker latest state (frontend_worker.cpp:48-51,72-75) ----
     for (Session *sp : act) {
         Session &s = *sp;
@@ -819,7 +819,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         if (!f->subframes.empty()) f = f->subframes.back().get();
         s.has_swt_latest = true; s.swt_t = f->t; s.swt_frame_id = s.ft_map.frames.back()->id; s.swt_state = f->st;
     }
-    delete pt;
+    pt.stop();
     return XRVIO_OK;
 }
 
