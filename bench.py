@@ -50,34 +50,60 @@ def read_peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region.  Uses NVML in-process (cheap); falls back to nvidia-smi."""
+
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.idx = gpu_index
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._halt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in (('hw_slowdown', n.nvmlClocksThrottleReasonHwSlowdown), ('hw_thermal_slowdown', n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ('sw_thermal_slowdown', n.nvmlClocksThrottleReasonSwThermalSlowdown), ('sw_power_cap', n.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        out = subprocess.run(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for nm, v in zip(names, out[2:]):
+            if 'Active' in v and 'Not' not in v:
+                self.reasons.add(nm)
+
+    def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(',')
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if 'Active' in v and 'Not' not in v:
-                        self.reasons.add(n)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.1 if self._nvml is not None else 0.5)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=3)
         return {'sm_mhz': float(np.median(self.samples)) if self.samples else None, 'sm_max_mhz': self.max_mhz,
-                'reasons': sorted(self.reasons)}
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
 
 
 def stream_seeds(rank, n_streams=None):
@@ -201,8 +227,8 @@ def run_cuda_arm(args, rank, world, local_rank):
         ctx.close()
         return res
 
-    r_dev = one_run(dev_ptrs, True, False, True)
     r_e2e = one_run(host_ptrs, False, True, False)
+    r_dev = one_run(dev_ptrs, True, False, True)
 
     ms_dev, ms_e2e = reduce_max_ms(r_dev['ms'], dev), reduce_max_ms(r_e2e['ms'], dev)
     if rank != 0:
