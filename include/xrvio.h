@@ -219,6 +219,9 @@ int xrvio_set_profiling(xrvio_ctx *ctx, int enable);
 int xrvio_get_kernel_times(xrvio_ctx *ctx, double *ms, long long *launches, int capacity);
 /* Host wall time accumulated per internal step phase (diagnostics; up to 32 slots). */
 int xrvio_get_phase_times(xrvio_ctx *ctx, double *ms, int capacity);
+/* Diagnostics: clock64 cycles accumulated per section of the solve kernel over all window problems (32 slots, slot 31 =
+ * number of problems); see tools/phase_probe.py for the slot names. */
+int xrvio_debug_kprof(unsigned long long *out32, int reset);
 
 #ifdef __cplusplus
 }
