@@ -48,8 +48,11 @@ capi.lib.xrvio_debug_kprof(arr, 0)
 a = list(arr)
 npb = max(a[31], 1)
 lab = {0: 'J zero', 1: 'J rpe', 2: 'J rot', 3: 'J pre simt', 4: 'J pre coop', 5: 'J marg', 6: 'J reduce', 8: 'C zero/sync', 9: 'C rpe', 10: 'C rot', 11: 'C pre simt', 12: 'C pre coop', 13: 'C marg',
-       14: 'C reduce', 17: 'loop pre-cand', 18: 'D/alpha', 19: 'gauss_newton', 20: 'dogleg', 21: 'cand+ambient', 22: 'post-accept eval etc', 23: 'apply_scaling', 24: 'GN schur', 25: 'GN cholesky', 26: 'GN substitution'}
+       14: 'C reduce', 17: 'loop pre-cand', 18: 'D/alpha', 19: 'gauss_newton', 20: 'dogleg', 21: 'cand+ambient', 22: 'post-accept eval etc', 23: 'apply_scaling', 24: 'GN schur', 25: 'GN cholesky', 26: 'GN substitution', 27: 'GN calls', 28: 'GN cholesky failures'}
 print('window problems', npb)
 for i in range(31):
     if a[i]:
-        print('%2d %-22s %10.1f kcycles/problem' % (i, lab.get(i, ''), a[i] / npb / 1e3))
+        if i in (27, 28):
+            print('%2d %-22s %10.3f per problem' % (i, lab.get(i, ''), a[i] / npb))
+        else:
+            print('%2d %-22s %10.1f kcycles/problem' % (i, lab.get(i, ''), a[i] / npb / 1e3))

@@ -57,7 +57,7 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
     for (int l = tid; l < M; l += ST) P.ht_l[l] = P.h_ll[l] + mu * P.D_l[l] * P.D_l[l];
     for (int c = tid; c < n; c += ST) s.bred[c] = s.g[c];
     __syncthreads();
-    if (threadIdx.x == 0 && P.d.marg_k > 0) { s.sc[15] = (double)clock64(); }
+    if (threadIdx.x == 0 && P.d.marg_k > 0) { s.sc[15] = (double)clock64(); atomicAdd(&g_kprof[27], 1ull); }
     schur_landmarks(P, s, s.bred);
     __syncthreads();
     if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[24], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
@@ -149,7 +149,7 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
     }
     __syncthreads();
     if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[25], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
-    if (!s.flag) return false;
+    if (!s.flag) { if (threadIdx.x == 0 && P.d.marg_k > 0) atomicAdd(&g_kprof[28], 1ull); return false; }
     // forward / backward substitution (L z = b, L^T y = z), one barrier per column
     // forward: work vector s.y (starts as b_red), result z in s.bred; backward: work vector s.bred, result in s.y.
     // Each column reads one finished entry and writes a different array, so one barrier per column suffices.
