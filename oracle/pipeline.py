@@ -56,6 +56,11 @@ class Config:
         self.predict_keypoints = True
         self.clahe_clip_limit, self.clahe_width, self.clahe_height = 6.0, 8, 8
         self.init_keyframe_num, self.init_keyframe_gap = 8, 5
+        # configs/euroc_slam.yaml:21-28, config.cpp:66 (random)
+        self.init_min_matches, self.init_min_parallax = 50, 10.0
+        self.init_min_triangulation, self.init_min_landmarks = 20, 30
+        self.init_refine_imu = True
+        self.random = 648
         self.solver_iteration_limit = 30
         self.rotation_misalignment_threshold = 0.02
         self.rotation_ransac_threshold = 10.0
@@ -858,8 +863,8 @@ class Session:
             t, fid, q, p, v, bg, ba = self.swt.get_latest_state()
             self.swt_latest = (t, frame_id, q, p, v, bg, ba)
 
-    # initializer.cpp:22-76 (mirror_keyframe_map) + ground-truth bootstrap + :88-130 (final VI-BA)
-    def bootstrap(self, init_frame_id):
+    # initializer.cpp:22-76
+    def mirror_keyframe_map(self, init_frame_id):
         cfg = self.cfg
         ft = self.ft_map
         last = ft.frame_index_by_id(init_frame_id)
@@ -884,19 +889,19 @@ class Session:
             nj.preintegration.data = []
             for f in range(idxs[j - 1], idxs[j]):
                 nj.preintegration.data.extend([(t, w.copy(), a.copy()) for (t, w, a) in ft.frames[f + 1].preintegration.data])
-        # ---- ground-truth replacement of init_sfm / init_imu ----
-        for f in m.frames:
-            q, p, v = self.gt_fn(f.t)
-            f.q, f.p, f.v = q.copy(), p.copy(), v.copy()
-            f.bg, f.ba = np.zeros(3), np.zeros(3)
-        for tr in list(m.tracks):
-            if tr.keypoint_num() >= 2:
-                x = tr.triangulate()
-                if x is not None:
-                    tr.set_landmark_point(x)
-                    tr.triangulated = True
-                    tr.valid = True
-        # ---- final visual-inertial BA (initializer.cpp:88-130) ----
+        return m
+
+    def _new_tracker_shell(self, m):
+        swt = SlidingWindowTracker.__new__(SlidingWindowTracker)
+        swt.map, swt.cfg = m, self.cfg
+        swt.solve_fn = self.solve_fn or ceres_tr.solve
+        swt.marg_fn = self.marg_fn or marg_mod.marginalize
+        swt.recorder = self.recorder
+        return swt
+
+    # initializer.cpp:86-135: final visual-inertial BA, then the map becomes the sliding window
+    def final_ba(self, swt):
+        cfg, m = self.cfg, swt.map
         m.frames[0].fix_pose = True
         b = ProblemBuilder(cfg)
         for f in m.frames:
@@ -913,17 +918,46 @@ class Session:
             fi, fj = m.frames[j - 1], m.frames[j]
             if fj.preintegration.integrate(fj.t, fi.bg, fi.ba, True, True):
                 b.add_pre(fi, fj, fj.preintegration, False)
-        swt = SlidingWindowTracker.__new__(SlidingWindowTracker)
-        swt.map, swt.cfg = m, cfg
-        swt.solve_fn = self.solve_fn or ceres_tr.solve
-        swt.marg_fn = self.marg_fn or marg_mod.marginalize
-        swt.recorder = self.recorder
         swt._solve(b, 'init_ba')
         for f in m.frames:
             f.keyframe = True
-        # NOTE: FT_FIX_POSE stays set on frame 0 in the reference (initializer.cpp:97 never clears it).
+        # NOTE: FT_FIX_POSE stays set on frame 0 in the reference (initializer.cpp:86 never clears it).
         SlidingWindowTracker.__init__(swt, m, cfg, swt.solve_fn, swt.marg_fn, swt.recorder)
         return swt
+
+    # mirror_keyframe_map + ground-truth replacement of init_sfm / init_imu + final VI-BA
+    def bootstrap(self, init_frame_id):
+        if self.gt_fn is None:
+            return self.initialize(init_frame_id)
+        m = self.mirror_keyframe_map(init_frame_id)
+        if m is None:
+            return None
+        for f in m.frames:
+            q, p, v = self.gt_fn(f.t)
+            f.q, f.p, f.v = q.copy(), p.copy(), v.copy()
+            f.bg, f.ba = np.zeros(3), np.zeros(3)
+        for tr in list(m.tracks):
+            if tr.keypoint_num() >= 2:
+                x = tr.triangulate()
+                if x is not None:
+                    tr.set_landmark_point(x)
+                    tr.triangulated = True
+                    tr.valid = True
+        return self.final_ba(self._new_tracker_shell(m))
+
+    # initializer.cpp:78-155 with the reference's own SfM + IMU alignment (oracle/initializer.py)
+    def initialize(self, init_frame_id):
+        from .initializer import Initializer
+        m = self.mirror_keyframe_map(init_frame_id)
+        if m is None:
+            return None
+        swt = self._new_tracker_shell(m)
+        ini = Initializer(self.cfg, m, swt._solve, ProblemBuilder)
+        ok = ini.run()
+        self.init_trace = ini.trace
+        if not ok:
+            return None
+        return self.final_ba(swt)
 
 
 def run_stream(stream, n_frames, cfg=None, **kw):
