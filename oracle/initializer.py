@@ -83,6 +83,60 @@ def set_imu_pose(frame, q_i, p_i):
     frame.p = p_i - qrot(frame.q, cfg.p_bi)
 
 
+def two_view_seed(pts_i, pts_j, fx, min_triangulation, seed):
+    """initializer.cpp:197-285: homography and essential RANSAC, the eight (R, T) candidates, two-view
+    triangulation of each and the reference's selection rule.  Pure function of the matches."""
+    n = len(pts_i)
+    out = dict(fail=None, candidate=-1, counts=[0] * 8)
+    Rs, Ts = [], []
+    H, _ = geo.find_homography_matrix(pts_i, pts_j, 0.7 / fx, 0.999, 1000, seed)
+    ok, RH1, RH2, TH1, TH2, _, _ = geo.decompose_homography(H)
+    if not ok:
+        out['fail'] = 'pure rotation'
+        return out
+    TH1 = TH1 / np.linalg.norm(TH1)
+    TH2 = TH2 / np.linalg.norm(TH2)
+    Rs += [RH1, RH1, RH2, RH2]
+    Ts += [TH1, -TH1, TH2, -TH2]
+    E, _ = geo.find_essential_matrix(pts_i, pts_j, 0.7 / fx, 0.999, 1000, seed)
+    RE1, RE2, TE = geo.decompose_essential(E)
+    TE = TE / np.linalg.norm(TE)
+    Rs += [RE1, RE1, RE2, RE2]
+    Ts += [TE, -TE, TE, -TE]
+    P1 = np.concatenate([np.eye(3), np.zeros((3, 1))], axis=1)
+    cand_pts, cand_status, counts, scores = [], [], [], []
+    best = 0
+    for c in range(len(Rs)):
+        P2 = np.concatenate([Rs[c], Ts[c][:, None]], axis=1)
+        pts = np.zeros((n, 3))
+        status = np.zeros(n, np.uint8)
+        count, score = 0, 0.0
+        for j in range(n):
+            x1 = np.append(pts_i[j], 1.0)
+            x2 = np.append(pts_j[j], 1.0)
+            q = geo.triangulate_point_2v(P1, P2, x1, x2)
+            q1, q2 = P1 @ q, P2 @ q
+            if q1[2] * q[3] > 0 and q2[2] * q[3] > 0:
+                if q1[2] / q[3] < 100 and q2[2] / q[3] < 100:
+                    pts[j] = q[:3] / q[3]
+                    status[j] = 1
+                    count += 1
+                    score += 0.5 * (np.sum((q1[:2] / q1[2] - pts_i[j]) ** 2) + np.sum((q2[:2] / q2[2] - pts_j[j]) ** 2))
+        cand_pts.append(pts)
+        cand_status.append(status)
+        counts.append(count)
+        scores.append(score)
+        if counts[c] > min_triangulation and scores[c] < scores[best]:      # the selection rule of :262-268
+            best = c
+        elif counts[c] > counts[best]:
+            best = c
+    out.update(candidate=best, counts=counts, scores=scores, R=Rs[best], T=Ts[best], points=cand_pts[best],
+               status=cand_status[best], Rs=Rs, Ts=Ts)
+    if counts[best] < min_triangulation:
+        out['fail'] = 'triangulation'
+    return out
+
+
 class Initializer:
     def __init__(self, cfg, map_, solve, builder_cls, recorder=None):
         """map_: the mirrored keyframe map; solve(builder, kind) -> summary (writes the states back)."""
@@ -95,7 +149,7 @@ class Initializer:
         cfg, m = self.cfg, self.map
         fi, fj = m.frames[0], m.frames[-1]
         K = cfg.K
-        pts_i, pts_j, matches = [], [], []
+        pts_i, pts_j, matches, par_list = [], [], [], []
         total_parallax = 0.0
         for ki in range(fi.keypoint_num()):
             tr = fi.tracks[ki]
@@ -110,7 +164,8 @@ class Initializer:
             matches.append((ki, kj))
             ui = np.array([bi[0] / bi[2] * K[0] + K[2], bi[1] / bi[2] * K[1] + K[3]])
             uj = np.array([bj[0] / bj[2] * K[0] + K[2], bj[1] / bj[2] * K[1] + K[3]])
-            total_parallax += np.linalg.norm(ui - uj)
+            par_list.append(np.linalg.norm(ui - uj))
+            total_parallax += par_list[-1]
         n = len(matches)
         self.trace['matches'] = n
         if n < cfg.init_min_matches:
@@ -121,57 +176,18 @@ class Initializer:
             return False
         pts_i = np.array(pts_i)
         pts_j = np.array(pts_j)
-
-        Rs, Ts = [], []
-        H, _ = geo.find_homography_matrix(pts_i, pts_j, 0.7 / K[0], 0.999, 1000, cfg.random)
-        ok, RH1, RH2, TH1, TH2, _, _ = geo.decompose_homography(H)
-        if not ok:
-            self.trace['fail'] = 'pure rotation'
+        seed = two_view_seed(pts_i, pts_j, K[0], cfg.init_min_triangulation, cfg.random)
+        self.trace['sfm_in'] = (pts_i, pts_j, np.array(par_list))
+        self.trace['sfm_out'] = seed
+        if seed['fail']:
+            self.trace['fail'] = seed['fail']
             return False
-        TH1 = TH1 / np.linalg.norm(TH1)
-        TH2 = TH2 / np.linalg.norm(TH2)
-        Rs += [RH1, RH1, RH2, RH2]
-        Ts += [TH1, -TH1, TH2, -TH2]
-        E, _ = geo.find_essential_matrix(pts_i, pts_j, 0.7 / K[0], 0.999, 1000, cfg.random)
-        RE1, RE2, TE = geo.decompose_essential(E)
-        TE = TE / np.linalg.norm(TE)
-        Rs += [RE1, RE1, RE2, RE2]
-        Ts += [TE, -TE, TE, -TE]
-
-        # [1.1] two-view triangulation of every candidate; the selection rule is the reference's (:262-268)
-        P1 = np.concatenate([np.eye(3), np.zeros((3, 1))], axis=1)
-        cand_pts, cand_status, counts, scores = [], [], [], []
-        best = 0
-        for c in range(len(Rs)):
-            P2 = np.concatenate([Rs[c], Ts[c][:, None]], axis=1)
-            pts = np.zeros((n, 3))
-            status = np.zeros(n, np.uint8)
-            count, score = 0, 0.0
-            for j in range(n):
-                x1 = np.append(pts_i[j], 1.0)
-                x2 = np.append(pts_j[j], 1.0)
-                q = geo.triangulate_point_2v(P1, P2, x1, x2)
-                q1, q2 = P1 @ q, P2 @ q
-                if q1[2] * q[3] > 0 and q2[2] * q[3] > 0:
-                    if q1[2] / q[3] < 100 and q2[2] / q[3] < 100:
-                        pts[j] = q[:3] / q[3]
-                        status[j] = 1
-                        count += 1
-                        score += 0.5 * (np.sum((q1[:2] / q1[2] - pts_i[j]) ** 2) + np.sum((q2[:2] / q2[2] - pts_j[j]) ** 2))
-            cand_pts.append(pts)
-            cand_status.append(status)
-            counts.append(count)
-            scores.append(score)
-            if counts[c] > cfg.init_min_triangulation and scores[c] < scores[best]:
-                best = c
-            elif counts[c] > counts[best]:
-                best = c
+        best = seed['candidate']
         self.trace['candidate'] = best
-        self.trace['counts'] = counts
-        init_R, init_T = Rs[best], Ts[best]
-        if counts[best] < cfg.init_min_triangulation:
-            self.trace['fail'] = 'triangulation'
-            return False
+        self.trace['counts'] = seed['counts']
+        init_R, init_T = seed['R'], seed['T']
+        cand_pts = {best: seed['points']}
+        cand_status = {best: seed['status']}
 
         # [2.1] first / last keyframe poses (camera frame of keyframe 0 is the origin)
         set_camera_pose(fi, np.array([0.0, 0, 0, 1]), np.zeros(3))
@@ -237,6 +253,9 @@ class Initializer:
         for j in range(1, m.frame_num()):
             fj = m.frames[j]
             fj.preintegration.integrate(fj.t, self.bg, self.ba, True, False)
+        # (t, q, p, v, dq_dbg) of every edge, kept for the host-logic tests
+        self.trace.setdefault('deltas', []).append([(f.preintegration.t, f.preintegration.q.copy(), f.preintegration.p.copy(),
+                                                      f.preintegration.v.copy(), f.preintegration.dq_dbg.copy()) for f in m.frames[1:]])
 
     def solve_gyro_bias(self):
         self.preintegrate()
@@ -251,6 +270,7 @@ class Initializer:
             A += pre.dq_dbg.T @ pre.dq_dbg
             b += pre.dq_dbg.T @ logmap(qmul(qconj(qmul(qi, pre.q)), qj))
         self.bg = np.linalg.lstsq(A, b, rcond=None)[0]
+        self.trace['bg'] = self.bg.copy()
 
     def solve_gravity_scale_velocity(self):
         self.preintegrate()
@@ -278,6 +298,7 @@ class Initializer:
         self.gravity = g / np.linalg.norm(g) * GRAVITY_NOMINAL
         self.scale = float(x[3])
         self.velocities = [x[4 + 3 * i:7 + 3 * i].copy() for i in range(N)]
+        self.trace['gsv'] = (self.gravity.copy(), self.scale, np.array(self.velocities))
 
     def refine_scale_velocity_via_gravity(self):
         damp = 0.1
@@ -308,6 +329,7 @@ class Initializer:
         self.gravity = g / np.linalg.norm(g) * GRAVITY_NOMINAL
         self.scale = float(x[2])
         self.velocities = [x[3 + 3 * i:6 + 3 * i].copy() for i in range(N)]
+        self.trace['refined'] = (self.gravity.copy(), self.scale, np.array(self.velocities))
 
     def apply_init(self, apply_ba=False, apply_velocity=True):
         m, cfg = self.map, self.cfg
@@ -337,6 +359,7 @@ class Initializer:
         self.gravity = np.zeros(3)
         self.scale = 1.0
         self.velocities = [np.zeros(3) for _ in range(N)]
+        self.trace['align_frames'] = [(f.q.copy(), f.p.copy()) for f in self.map.frames]
         self.solve_gyro_bias()
         self.solve_gravity_scale_velocity()
         self.trace['scale0'] = self.scale
