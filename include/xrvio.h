@@ -182,6 +182,12 @@ typedef struct xrvio_params {
     int solver_iteration_limit;
     double rotation_misalignment_threshold, rotation_ransac_threshold;
     int prior_eigen_form;         /* 1: marginalisation prior kept in eigen form (see xrvio_marg_desc.eigen_form); default 0 */
+    int initializer;              /* 1 (default): a session that was given no bootstrap state runs the reference's own
+                                     initializer (core/initializer.cpp:78-571: two-view SfM seed, PnP, visual BA, IMU
+                                     alignment) before its first visual-inertial BA; 0: it waits for bootstrap states */
+    int init_min_matches, init_min_triangulation, init_min_landmarks, init_refine_imu;   /* configs/euroc_slam.yaml:21-28 */
+    double init_min_parallax;
+    int random_seed;              /* Config::random() (config.cpp:66), seed of the RANSAC samplers of the initializer */
     int pad;
 } xrvio_params;
 
@@ -194,6 +200,14 @@ typedef struct xrvio_stats {
     long long window_solves, localize_solves, subwindow_solves, marginalizations;
     double last_window_cost_initial, last_window_cost_final;
 } xrvio_stats;
+
+/* Outcome of the initializer attempts of a session (core/initializer.cpp:78-571).  last_fail: 0 initialised (or not yet
+ * tried), 1 too few matches, 2 too little parallax, 3 pure rotation, 4 two-view triangulation, 5 visual BA unusable,
+ * 6 scale outside [0.001, 1], 7 too few landmarks, 8 keyframe without IMU data, 9 fewer frames than the keyframe span */
+typedef struct xrvio_init_info {
+    int attempts, last_fail, matches, candidate, landmarks, pad;
+    double parallax, scale;
+} xrvio_init_info;
 
 #define XRVIO_STATE_INITIALIZING 0   /* SysState::SYS_INITIALIZING */
 #define XRVIO_STATE_TRACKING 1       /* SysState::SYS_TRACKING */
@@ -211,6 +225,7 @@ int xrvio_get_pose(xrvio_ctx *ctx, int session, xrvio_pose *pose);          /* o
 int xrvio_get_latest_state(xrvio_ctx *ctx, int session, double *t, double state16[16]);   /* last optimised frame */
 int xrvio_get_state(xrvio_ctx *ctx, int session);                           /* XRVIO_STATE_* or < 0 */
 int xrvio_get_landmarks(xrvio_ctx *ctx, int session, double *xyz, int capacity);   /* returns count */
+int xrvio_get_init_info(xrvio_ctx *ctx, int session, xrvio_init_info *out);
 int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *stats);
 /* Per-kernel-family device time measured with CUDA events on the launch stream (off by default).
  * Families: 0 clahe 1 pyramid 2 gftt 3 klt 4 poisson 5 preintegration 6 solve 7 marginalize 8 triangulate.

@@ -19,7 +19,7 @@ def imu_batch(sessions, rows):
     return np.asarray(sessions, np.int32), a
 
 
-def run_streams_cuda(streams, n_frames, frames=None, ctx=None, collect=True):
+def run_streams_cuda(streams, n_frames, frames=None, ctx=None, collect=True, bootstrap=True):
     """Runs len(streams) sessions for n_frames frames.  frames[s][k]: optional pre-rendered u8 images.
     Returns (ctx, outputs) with outputs[s] = list of (t, q, p) poses as the player would write them."""
     S = len(streams)
@@ -28,6 +28,8 @@ def run_streams_cuda(streams, n_frames, frames=None, ctx=None, collect=True):
     k_imu = [0] * S
     outputs = [[] for _ in range(S)]
     for s, st in enumerate(streams):
+        if not bootstrap:
+            break                           # the sessions run the reference initializer instead
         for k in range(min(n_frames, 40)):
             t = st.frame_time(k)
             q, p, v = st.gt_state(t)

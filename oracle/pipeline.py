@@ -960,11 +960,11 @@ class Session:
         return self.final_ba(swt)
 
 
-def run_stream(stream, n_frames, cfg=None, **kw):
+def run_stream(stream, n_frames, cfg=None, bootstrap=True, **kw):
     """Drive a synthetic Stream through a Session the way xrslam-pc/player would
     (IMU samples in time order, image, ...).  Returns the Session."""
     cfg = cfg or Config(stream.w, stream.h, stream.K)
-    sess = Session(cfg, gt_fn=stream.gt_state, **kw)
+    sess = Session(cfg, gt_fn=stream.gt_state if bootstrap else None, **kw)
     imu = stream.imu(n_frames * stream.imu_per_cam + 2)
     k_imu = 0
     for k in range(n_frames):

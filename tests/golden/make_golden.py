@@ -8,6 +8,7 @@ Outputs:
   backend_problems.npz  one recorded problem of every solve kind + a marginalisation, before / after the oracle
   preint.npz            preintegration jobs and oracle results
   stream3_traj.npz      oracle trajectory of synthetic stream seed 3 (first 66 frames)
+  stream7_init_traj.npz oracle trajectory of stream seed 7 initialised by the reference initializer (no bootstrap states)
   stream7_traj140.npz   oracle trajectory of synthetic stream seed 7, 140 frames (steady-state marginalisation)
 """
 import os
@@ -126,8 +127,24 @@ def long_trajectory():
     print('long trajectory rows', len(traj))
 
 
+def initializer_trajectory():
+    """Stream 7 WITHOUT ground-truth bootstrap: the oracle runs the reference initializer (oracle/initializer.py)."""
+    s = Stream(7)
+    sess = run_stream(s, 70, bootstrap=False)
+    traj = np.array([[t] + list(q) + list(p) for (t, q, p) in sess.outputs])
+    tr = sess.init_trace
+    np.savez_compressed(os.path.join(HERE, 'stream7_init_traj.npz'), traj=traj,
+                        info=np.array([tr['matches'], tr['candidate'], tr['landmarks'], tr['parallax'], tr['scale']], np.float64))
+    print('initializer trajectory rows', len(traj), tr['matches'], tr['candidate'], tr['landmarks'], tr['scale'])
+
+
 if __name__ == '__main__':
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'init':
+        initializer_trajectory()
+        sys.exit(0)
     long_trajectory()
+    initializer_trajectory()
     frontend_kat()
     preint()
     backend_problems()

@@ -1,0 +1,57 @@
+"""Row N3 of SURVEY.md 8(f): a session that is given NO bootstrap state runs the reference's initializer
+(two-view SfM seed, PnP, visual BA, IMU alignment; xrslam_b200/csrc/session_init.inl + init_host.hpp) and is
+compared with the oracle pipeline doing the same (tests/golden/stream7_init_traj.npz, made by
+tests/golden/make_golden.py init)."""
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle.synth import Stream
+from oracle import drive
+
+
+def _ate(a, b):
+    """RMSE of position differences after rigid SE3 alignment (evo_ape -a semantics)."""
+    a, b = np.asarray(a), np.asarray(b)
+    ca, cb = a.mean(0), b.mean(0)
+    H = (b - cb).T @ (a - ca)
+    U, _, Vt = np.linalg.svd(H)
+    D = np.diag([1, 1, np.sign(np.linalg.det(U @ Vt))])
+    R = (U @ D @ Vt).T
+    al = (R @ (b - cb).T).T + ca
+    return float(np.sqrt(np.mean(np.sum((al - a) ** 2, axis=1))))
+
+
+def test_initializer_matches_oracle(xrvio, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'stream7_init_traj.npz'))
+    ref, info_ref = g['traj'], g['info']
+    s = Stream(7)
+    ctx, outs = drive.run_streams_cuda([s], 70, bootstrap=False)
+    info = ctx.get_init_info(0)
+    assert info['last_fail'] == 0 and info['attempts'] == 1, info
+    assert abs(info['matches'] - info_ref[0]) <= 2 and info['candidate'] == int(info_ref[1])
+    assert abs(info['landmarks'] - info_ref[2]) <= 10
+    assert abs(info['parallax'] - info_ref[3]) < 0.05 and abs(info['scale'] / info_ref[4] - 1) < 1e-2
+    got = np.array([[t] + list(q) + list(p) for (t, q, p) in outs[0]])
+    assert got.shape == ref.shape and np.allclose(got[:, 0], ref[:, 0])        # initialised on the same frame
+    ate = _ate(ref[:, 5:8], got[:, 5:8])
+    raw = np.linalg.norm(got[:, 5:8] - ref[:, 5:8], axis=1).max()
+    assert ate <= 1e-3 and raw <= 2e-3, (ate, raw)
+    gt = np.array([s.gt_state(t)[1] for t in got[:, 0]])
+    assert _ate(gt, got[:, 5:8]) < 0.02                                         # metric scale and gravity are right
+    st = ctx.stats()
+    assert st['window_solves'] >= 5 and st['localize_solves'] >= 30
+    ctx.close()
+
+
+def test_initializer_can_be_disabled(xrvio):
+    s = Stream(7)
+    p = drive.params_for(s)
+    p['initializer'] = 0
+    from xrslam_b200 import capi
+    ctx = capi.Context(p, 1)
+    ctx, outs = drive.run_streams_cuda([s], 40, ctx=ctx, bootstrap=False)
+    assert ctx.get_state(0) == 0 and len(outs[0]) == 0 and ctx.get_init_info(0)['attempts'] == 0
+    ctx.close()

@@ -207,15 +207,15 @@ def test_struct_layouts_match_header():
     import subprocess, tempfile
     from xrslam_b200 import capi
     inc = os.path.join(os.path.dirname(capi._HERE), 'include')
-    src = '#include <stdio.h>\n#include "xrvio.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",sizeof(xrvio_rig),sizeof(xrvio_preint_job),' \
+    src = '#include <stdio.h>\n#include "xrvio.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",sizeof(xrvio_rig),sizeof(xrvio_preint_job),' \
           'sizeof(xrvio_rpe),sizeof(xrvio_rot),sizeof(xrvio_pre_ref),sizeof(xrvio_solve_desc),sizeof(xrvio_solve_out),sizeof(xrvio_marg_desc),' \
-          'sizeof(xrvio_params),sizeof(xrvio_pose),sizeof(xrvio_stats));}\n'
+          'sizeof(xrvio_params),sizeof(xrvio_pose),sizeof(xrvio_stats),sizeof(xrvio_init_info));}\n'
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, 'p.c'); open(c, 'w').write(src)
         subprocess.check_call(['gcc', '-I', inc, c, '-o', os.path.join(td, 'p')])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(td, 'p')]).split()]
     want = [capi.rig_dtype, capi.preint_job_dtype, capi.rpe_dtype, capi.rot_dtype, capi.pre_ref_dtype, capi.solve_desc_dtype,
-            capi.solve_out_dtype, capi.marg_desc_dtype, capi.params_dtype, capi.pose_dtype, capi.stats_dtype]
+            capi.solve_out_dtype, capi.marg_desc_dtype, capi.params_dtype, capi.pose_dtype, capi.stats_dtype, capi.init_info_dtype]
     assert sizes == [d.itemsize for d in want]
 
 

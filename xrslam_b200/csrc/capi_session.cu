@@ -13,6 +13,7 @@
 #include "backend.cuh"
 #include "frontend.cuh"
 #include "session_host.hpp"
+#include "init_host.hpp"
 #include "thread_pool.hpp"
 #include <atomic>
 #include <chrono>
@@ -109,6 +110,8 @@ struct Session {
     xrvio_pose out_pose{};
     double out_t = 0;
     std::map<long long, State16> bootstrap;       // keyed by round(t * 1e6)
+    xrvio_init_info init{};                       // outcome of the initializer attempts (session_init.inl)
+    bool init_now = false;                        // the initializer succeeded in this round
     int img_slot_next = 0;
     int pyr_next = 0;
     // per-round scratch
@@ -325,6 +328,7 @@ struct Builder {
     struct P { Frame *i, *j; bool prior; const std::vector<double> *blk; };
     std::vector<R> rpe; std::vector<Ro> rot; std::vector<P> pre;
     bool use_marg = false;
+    bool with_motion = true;       // false: Solver::add_frame_states(frame, false) -- pose blocks only (initializer.cpp:342)
     void add_active(Frame *f) { if (f->tmp == -1) { f->tmp = -2; active.push_back(f); } }
     void touch(Frame *f) { if (f->tmp == -1) { f->tmp = -3; consts.push_back(f); } }
     void add_rpe(Frame *f, Track *tr, bool prior) {
@@ -348,9 +352,10 @@ int pack_problem(Lane *c, Session &s, Builder &b, int max_iterations) {
     // a frame is active (gets columns) iff it was added with add_frame_states and has a free block
     std::vector<Frame *> &frames = s.prob_frames;
     frames.clear();
-    for (Frame *f : b.active) if (!(f->fix_pose && f->fix_motion)) frames.push_back(f);
+    auto all_fixed = [&](const Frame *f) { return f->fix_pose && (f->fix_motion || !b.with_motion); };
+    for (Frame *f : b.active) if (!all_fixed(f)) frames.push_back(f);
     const int n_active = (int)frames.size();
-    for (Frame *f : b.active) if (f->fix_pose && f->fix_motion) frames.push_back(f);
+    for (Frame *f : b.active) if (all_fixed(f)) frames.push_back(f);
     for (Frame *f : b.consts) frames.push_back(f);
     if (n_active > XRVIO_MAX_ACTIVE || (int)frames.size() > XRVIO_MAX_FRAMES) { s.err = "solve problem exceeds XRVIO_MAX_ACTIVE / XRVIO_MAX_FRAMES"; return XRVIO_ERR_LIMIT; }
     for (size_t i = 0; i < frames.size(); ++i) frames[i]->tmp = (int)i;
@@ -365,7 +370,7 @@ int pack_problem(Lane *c, Session &s, Builder &b, int max_iterations) {
     g.flags.resize(frames.size());
     for (size_t i = 0; i < frames.size(); ++i) {
         std::memcpy(&g.states[i * 16], frames[i]->st.d, 16 * sizeof(double));
-        g.flags[i] = (unsigned char)((frames[i]->fix_pose ? 0 : 1) | (frames[i]->fix_motion ? 0 : 2));
+        g.flags[i] = (unsigned char)((frames[i]->fix_pose ? 0 : 1) | ((frames[i]->fix_motion || !b.with_motion) ? 0 : 2));
     }
     g.invd.resize(lms.size());
     for (size_t i = 0; i < lms.size(); ++i) g.invd[i] = lms[i]->inv_depth;
@@ -513,6 +518,9 @@ int xrvio_default_params_impl(xrvio_params *p, int width, int height) {
     p->predict_keypoints = 1; p->clahe_clip_limit = 6.0; p->clahe_width = 8; p->clahe_height = 8;
     p->init_keyframe_num = 8; p->init_keyframe_gap = 5; p->solver_iteration_limit = 30;
     p->rotation_misalignment_threshold = 0.02; p->rotation_ransac_threshold = 10.0;
+    p->initializer = 1;                                                                       // configs/euroc_slam.yaml:21-28
+    p->init_min_matches = 50; p->init_min_parallax = 10.0; p->init_min_triangulation = 20; p->init_min_landmarks = 30;
+    p->init_refine_imu = 1; p->random_seed = 648;                                             // config.cpp:66
     return XRVIO_OK;
 }
 
@@ -797,6 +805,13 @@ int xrvio_get_pose(xrvio_ctx *ctx, int session, xrvio_pose *pose) { LANE_OF(sess
 int xrvio_get_latest_state(xrvio_ctx *ctx, int session, double *t, double state16[16]) { LANE_OF(session, l, i); return lane_get_latest_state(l, i, t, state16); }
 int xrvio_get_state(xrvio_ctx *ctx, int session) { LANE_OF(session, l, i); return lane_get_state(l, i); }
 int xrvio_get_landmarks(xrvio_ctx *ctx, int session, double *xyz, int capacity) { LANE_OF(session, l, i); return lane_get_landmarks(l, i, xyz, capacity); }
+
+int xrvio_get_init_info(xrvio_ctx *ctx, int session, xrvio_init_info *out) {
+    LANE_OF(session, l, i);
+    if (!out) { xrvio_set_error("xrvio_get_init_info: null output"); return XRVIO_ERR_ARG; }
+    *out = l->ses[i].init;
+    return XRVIO_OK;
+}
 
 int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *st) {
     if (!ctx || !st) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }

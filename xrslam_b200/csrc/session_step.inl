@@ -308,34 +308,19 @@ int merge_tri_jobs(Lane *c, std::vector<Session *> &act) {
     return XRVIO_OK;
 }
 
-// Initializer::mirror_keyframe_map (initializer.cpp:22-76) + ground-truth states
+#include "session_init.inl"
+
+// Initializer::mirror_keyframe_map (initializer.cpp:22-76) + externally supplied states instead of init_sfm / init_imu
 bool bootstrap_mirror(Lane *c, Session &s, long long init_frame_id) {
     Map &ft = s.ft_map;
     const long last = ft.frame_index_by_id(init_frame_id);
     const long gap = c->prm.init_keyframe_gap, dist = gap * (c->prm.init_keyframe_num - 1);
     if (last < dist) return false;
     const long first = last - dist;
-    std::vector<long> idxs;
-    for (int i = 0; i < c->prm.init_keyframe_num; ++i) idxs.push_back(first + i * gap);
-    for (long ix : idxs)
-        if (s.bootstrap.find(tkey(ft.frames[ix]->t)) == s.bootstrap.end()) return false;
-    auto m = std::make_unique<Map>();
-    m->track_id_counter = &s.track_id_counter;
-    for (long ix : idxs) m->attach_frame(ft.frames[ix]->clone());
-    for (size_t j = 1; j < m->frame_num(); ++j) {
-        Frame *oi = ft.frames[idxs[j - 1]].get(), *oj = ft.frames[idxs[j]].get();
-        Frame *ni = m->frames[j - 1].get(), *nj = m->frames[j].get();
-        for (size_t ki = 0; ki < oi->keypoint_num(); ++ki)
-            if (Track *tr = oi->tracks[ki]) {
-                int kj = tr->get_keypoint_index(oj);
-                if (kj >= 0) track_add_keypoint(frame_get_track(ni, (int)ki, nullptr), nj, kj);
-            }
-        nj->imu.clear();
-        for (long f = idxs[j - 1]; f < idxs[j]; ++f) {
-            const auto &od = ft.frames[f + 1]->imu;
-            nj->imu.insert(nj->imu.end(), od.begin(), od.end());
-        }
-    }
+    for (int i = 0; i < c->prm.init_keyframe_num; ++i)
+        if (s.bootstrap.find(tkey(ft.frames[first + i * gap]->t)) == s.bootstrap.end()) return false;
+    std::unique_ptr<Map> m = mirror_keyframe_map(c, s, init_frame_id);
+    if (!m) return false;
     for (auto &f : m->frames) {
         const State16 &g = s.bootstrap[tkey(f->t)];
         f->st = g;
@@ -421,13 +406,23 @@ namespace {
 
 int back_end_round(Lane *c, std::vector<Session *> &act) {
     PhaseClock pt(c, 10);
+    // ---- sessions that were given no bootstrap state run the reference initializer, one attempt per frame
+    //      (frontend_worker.cpp:28-51); on success the map continues below like a bootstrapped one ----
+    for (Session *sp : act) {
+        Session &s = *sp;
+        s.init_now = false;
+        if (s.sw_map || !c->prm.initializer || !s.bootstrap.empty()) continue;
+        const int rc = initialize_session(c, s, s.ft_map.frames.back()->id);
+        if (rc) return rc;
+        s.init_now = (bool)s.sw_map;
+    }
     // ---- phase E: mirror + preintegration with Jacobians and covariance ----
     { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
         s.stg.clear_jobs();
         s.be_mode = 0; s.pre_jobs.clear(); s.pre_job_frames.clear(); s.prob1 = s.prob2 = -1; s.is_keyframe = false;
         const long long frame_id = s.ft_map.frames.back()->id;
-        if (!s.sw_map) {
-            if (!bootstrap_mirror(c, s, frame_id)) return 0;
+        if (!s.sw_map || s.init_now) {
+            if (!s.init_now && !bootstrap_mirror(c, s, frame_id)) return 0;
             s.be_mode = 1;
             Map *m = s.sw_map.get();
             for (size_t j = 1; j < m->frame_num(); ++j) {

@@ -157,6 +157,11 @@ int XRSLAMCreate(const char *slam_config_path, const char *device_config_path, c
     if (numbers_after(slam, "clahe_height", 1, v)) p.clahe_height = (int)v[0];
     if (numbers_after(slam, "keyframe_num", 1, v)) p.init_keyframe_num = (int)v[0];
     if (numbers_after(slam, "keyframe_gap", 1, v)) p.init_keyframe_gap = (int)v[0];
+    if (numbers_after(slam, "min_matches", 1, v)) p.init_min_matches = (int)v[0];
+    if (numbers_after(slam, "min_parallax", 1, v)) p.init_min_parallax = v[0];
+    if (numbers_after(slam, "min_triangulation", 1, v)) p.init_min_triangulation = (int)v[0];
+    if (numbers_after(slam, "min_landmarks", 1, v)) p.init_min_landmarks = (int)v[0];
+    { size_t r = slam.find("refine_imu:"); if (r != std::string::npos) p.init_refine_imu = slam.compare(r + 11, 6, " false") == 0 ? 0 : 1; }
     if (numbers_after(slam, "iteration_limit", 1, v)) p.solver_iteration_limit = (int)v[0];
     if (numbers_after(slam, "misalignment_threshold", 1, v)) p.rotation_misalignment_threshold = v[0];
     if (numbers_after(slam, "ransac_threshold", 1, v)) p.rotation_ransac_threshold = v[0];
