@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp", ".inl"))]
     headers.append(os.path.join(HERE, "..", "include", "xrvio.h"))
     hdr_time = max(os.path.getmtime(h) for h in headers)
     objs = []
@@ -59,5 +59,21 @@ def build(force=False, verbose=False):
     return LIB
 
 
+PLAYER_DIR = os.path.join(HERE, "..", "player")
+PLAYER = os.path.join(PLAYER_DIR, "xrvio_player")
+
+
+def build_player(force=False):
+    """Headless player (player/main.cpp) linked against libxrvio.so through the XRSLAM C ABI."""
+    build()
+    srcs = [os.path.join(PLAYER_DIR, f) for f in os.listdir(PLAYER_DIR) if f.endswith((".cpp", ".hpp"))]
+    srcs.append(os.path.join(HERE, "..", "include", "xrslam_compat.h"))
+    if force or not os.path.exists(PLAYER) or max(os.path.getmtime(s) for s in srcs + [LIB]) > os.path.getmtime(PLAYER):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", PLAYER, os.path.join(PLAYER_DIR, "main.cpp"), "-L" + LIBDIR, "-lxrvio", "-lz",
+                               "-Wl,-rpath,$ORIGIN/../xrslam_b200/lib"])
+    return os.path.abspath(PLAYER)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_player(force="--force" in sys.argv))
