@@ -265,6 +265,13 @@ class Frame:
         next_bearings = [remove_k(next_kps[i], nxt.K) for i in range(n)]
         # essential-matrix RANSAC mask (frame.cpp:108-114): see oracle/ransac.py header
         mask_e = np.ones(n, np.uint8) if n >= 5 else np.zeros(n, np.uint8)
+        if getattr(cfg, 'essential_ransac', False) and n >= 5:
+            # the real thing (stereo.cpp:40-69 with threshold 1.0): used by tests to show that the mask is all ones
+            from .geometry import find_essential_matrix
+            ch = np.array([b[:2] / b[2] for b in self.bearings]).reshape(n, 2)
+            nh = np.array([b[:2] / b[2] for b in next_bearings]).reshape(n, 2)
+            _, mask_e = find_essential_matrix(ch, nh, 1.0)
+            cfg.essential_masks.append(mask_e.copy())
         status = status.copy()
         status[mask_e == 0] = 0
         b1 = np.array(self.bearings).reshape(n, 3)

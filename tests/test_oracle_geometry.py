@@ -137,3 +137,27 @@ def test_initializer_recovers_metric_state():
     z = np.array([0, 0, 1.0])
     assert np.linalg.norm(qrot(qconj(f1.q), z) - qrot(qconj(q1), z)) < 0.01
     assert abs(np.linalg.norm(f1.v) / np.linalg.norm(v1) - 1) < 0.03
+
+
+@pytest.mark.timeout(300)
+def test_per_frame_essential_mask_is_all_ones():
+    """frame.cpp:108-114 runs the 5-point RANSAC with threshold 1.0 (2 * 3.84 in squared normalised units) on every
+    frame pair; oracle/ransac.py and the CUDA session replace it by its effect.  Run the real thing on a stream."""
+    from oracle.synth import Stream
+    from oracle.pipeline import Session, Config
+    st = Stream(3)
+    cfg = Config(st.w, st.h, st.K)
+    cfg.essential_ransac = True
+    cfg.essential_masks = []
+    sess = Session(cfg, gt_fn=st.gt_state)
+    n = 16
+    imu = st.imu(n * st.imu_per_cam + 2)
+    k_imu = 0
+    for k in range(n):
+        t_img = st.frame_time(k)
+        while k_imu < len(imu) and imu[k_imu, 0] <= t_img + 1e-9:
+            sess.track_imu(imu[k_imu, 0], imu[k_imu, 1:4], imu[k_imu, 4:7])
+            k_imu += 1
+        sess.track_camera(t_img, st.frame(k))
+    assert len(cfg.essential_masks) >= n - 3
+    assert all(m.all() and len(m) >= 50 for m in cfg.essential_masks)
