@@ -129,6 +129,13 @@ int xrvio_set_device(int device);
 
 int xrvio_pyramid_layout(int w, int h, int *widths, int *heights, long long *offsets, long long *total);
 
+/* Undistortion of n w*h images (row N2).  model XRVIO_DISTORTION_RADTAN restates cv::undistort(img, K, D) as the EuRoC
+ * reader calls it (euroc_dataset_reader.cpp:62-72), XRVIO_DISTORTION_EQUIDISTANT restates xrslam::extra::ImageUndistorter
+ * + cv::remap (image_undistorter.h:13-97).  K = fx fy cx cy. */
+#define XRVIO_DISTORTION_NONE 0
+#define XRVIO_DISTORTION_RADTAN 1
+#define XRVIO_DISTORTION_EQUIDISTANT 2
+int xrvio_op_undistort(const uint8_t *src, uint8_t *dst, int n, int w, int h, int model, const double K[4], const double D[4]);
 int xrvio_op_clahe(const uint8_t *src, uint8_t *dst, int n, int w, int h, double clip_limit, int tiles_x, int tiles_y);
 int xrvio_op_pyramid(const uint8_t *level0, int n, int w, int h, uint8_t *pyr, int16_t *deriv /* may be NULL */);
 int xrvio_op_gftt(const uint8_t *img, int n, int w, int h, int max_corners, double quality, double min_distance,
@@ -188,7 +195,10 @@ typedef struct xrvio_params {
     int init_min_matches, init_min_triangulation, init_min_landmarks, init_refine_imu;   /* configs/euroc_slam.yaml:21-28 */
     double init_min_parallax;
     int random_seed;              /* Config::random() (config.cpp:66), seed of the RANSAC samplers of the initializer */
-    int pad;
+    int distortion_model;         /* 0 (default): pushed images are already undistorted, as with the reference's readers;
+                                     XRVIO_DISTORTION_RADTAN / _EQUIDISTANT: the library undistorts every pushed image on the
+                                     device with the readers' arithmetic (xrvio_op_undistort) before CLAHE */
+    double distortion[4];         /* k1 k2 p1 p2 (radtan) or k1 k2 k3 k4 (equidistant); intrinsics are fx fy cx cy above */
 } xrvio_params;
 
 typedef struct xrvio_imu { double t, w[3], a[3]; } xrvio_imu;

@@ -147,7 +147,7 @@ class DatasetReader {
         if (!read_gray_image(item.second, raw, err)) return {item.first, GrayImage()};
         if (config.distortion_flag) {
             if (undistorter.width != raw.width || undistorter.height != raw.height)
-                undistorter.build(raw.width, raw.height, config.K, config.D, model, float_params);
+                undistorter.build(raw.width, raw.height, config.K, config.D, model);
             undistorter.apply(raw, img);
         } else img = std::move(raw);
         image_width = img.width; image_height = img.height;

@@ -26,7 +26,6 @@ int main(int argc, char **argv) {
     }
     if (cmd == "undistort" && argc == 16) {
         const std::string model = argv[2];
-        const bool fl = std::atoi(argv[3]) != 0;
         const int w = std::atoi(argv[4]), h = std::atoi(argv[5]);
         double K[4], D[4];
         for (int i = 0; i < 4; ++i) { K[i] = std::atof(argv[6 + i]); D[i] = std::atof(argv[10 + i]); }
@@ -35,7 +34,7 @@ int main(int argc, char **argv) {
         GrayImage src, dst;
         src.width = w; src.height = h; src.data = buf;
         Undistorter u;
-        u.build(w, h, K, D, model, fl);
+        u.build(w, h, K, D, model);
         u.apply(src, dst);
         write_raw(argv[15], dst);
         return 0;

@@ -81,6 +81,16 @@ def pyramid_layout(w, h):
     return list(ws), list(hs), list(offs), tot.value
 
 
+def op_undistort(images, model, K, D):
+    """images: (n, h, w) u8.  model: 1 radtan (cv::undistort), 2 equidistant (ImageUndistorter + cv::remap)."""
+    images = np.ascontiguousarray(images, np.uint8)
+    n, h, w = images.shape
+    out = np.empty_like(images)
+    K = np.ascontiguousarray(K, np.float64); D = np.ascontiguousarray(D, np.float64)
+    lib.check(lib.xrvio_op_undistort(_p(images), _p(out), n, w, h, int(model), _p(K), _p(D)))
+    return out
+
+
 def op_clahe(imgs, clip=6.0, tiles=(8, 8)):
     imgs = np.ascontiguousarray(imgs, np.uint8)
     n, h, w = imgs.shape
@@ -194,7 +204,8 @@ params_dtype = np.dtype([("width", "i4"), ("height", "i4"), ("fx", "f8"), ("fy",
                          ("solver_iteration_limit", "i4"), ("rotation_misalignment_threshold", "f8"),
                          ("rotation_ransac_threshold", "f8"), ("prior_eigen_form", "i4"), ("initializer", "i4"),
                          ("init_min_matches", "i4"), ("init_min_triangulation", "i4"), ("init_min_landmarks", "i4"),
-                         ("init_refine_imu", "i4"), ("init_min_parallax", "f8"), ("random_seed", "i4"), ("pad", "i4")], align=True)
+                         ("init_refine_imu", "i4"), ("init_min_parallax", "f8"), ("random_seed", "i4"), ("distortion_model", "i4"),
+                         ("distortion", "f8", 4)], align=True)
 imu_dtype = np.dtype([("t", "f8"), ("w", "f8", 3), ("a", "f8", 3)], align=True)
 pose_dtype = np.dtype([("q", "f8", 4), ("p", "f8", 3), ("t", "f8"), ("valid", "i4"), ("pad", "i4")], align=True)
 init_info_dtype = np.dtype([("attempts", "i4"), ("last_fail", "i4"), ("matches", "i4"), ("candidate", "i4"), ("landmarks", "i4"),

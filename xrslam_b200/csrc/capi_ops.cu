@@ -55,6 +55,20 @@ int xrvio_pyramid_layout(int w, int h, int *widths, int *heights, long long *off
     return XRVIO_OK;
 }
 
+int xrvio_op_undistort(const uint8_t *src, uint8_t *dst, int n, int w, int h, int model, const double K[4], const double D[4]) {
+    if (!src || !dst || !K || !D || n <= 0 || w <= 0 || h <= 0 || (model != XRVIO_DISTORTION_RADTAN && model != XRVIO_DISTORTION_EQUIDISTANT))
+        return fail_arg("xrvio_op_undistort: bad argument");
+    const size_t bytes = (size_t)n * w * h;
+    DevBuf d_src, d_dst, d_map;
+    CK(d_src.alloc(bytes)); CK(d_dst.alloc(bytes)); CK(d_map.alloc((size_t)w * h * sizeof(int2)));
+    CK(cudaMemcpy(d_src.p, src, bytes, cudaMemcpyHostToDevice));
+    xvfe::undistort_build_map(xund::make_model(model, K, D), w, h, d_map.as<int2>(), 0);
+    xvfe::undistort(d_src.as<uint8_t>(), nullptr, (size_t)w * h, d_dst.as<uint8_t>(), nullptr, (size_t)w * h, n, w, h, d_map.as<int2>(), 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(dst, d_dst.p, bytes, cudaMemcpyDeviceToHost));
+    return XRVIO_OK;
+}
+
 int xrvio_op_clahe(const uint8_t *src, uint8_t *dst, int n, int w, int h, double clip_limit, int tiles_x, int tiles_y) {
     if (!src || !dst || n <= 0 || w <= 0 || h <= 0 || tiles_x <= 0 || tiles_y <= 0) return fail_arg("xrvio_op_clahe: bad argument");
     const size_t bytes = (size_t)n * w * h;

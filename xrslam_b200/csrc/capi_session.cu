@@ -158,6 +158,8 @@ struct Lane {
     uint8_t *d_raw = nullptr;          // S * kImgQueue * w*h
     uint8_t *d_pyr = nullptr;          // S * kPyrSlots * L.total
     uint8_t *d_lut = nullptr;
+    uint8_t *d_und = nullptr;          // S * w*h undistorted images of the round (only with prm.distortion_model != 0)
+    int2 *d_und_map = nullptr;         // w*h source positions in 1/32 px
     unsigned long long *d_cand = nullptr; int *d_cand_count = nullptr; unsigned *d_maxval = nullptr;
     Arena<float> corners; Arena<int> corner_count;
     Arena<float> klt_prev, klt_next; Arena<int> klt_n; Arena<unsigned char> klt_status;
@@ -549,6 +551,13 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
     CKC(cudaMalloc((void **)&c->d_raw, (size_t)S * kImgQueue * P));
     CKC(cudaMalloc((void **)&c->d_pyr, (size_t)S * kPyrSlots * c->L.total));
     CKC(cudaMalloc((void **)&c->d_lut, (size_t)S * p->clahe_width * p->clahe_height * 256));
+    if (p->distortion_model != XRVIO_DISTORTION_NONE) {
+        if (p->distortion_model != XRVIO_DISTORTION_RADTAN && p->distortion_model != XRVIO_DISTORTION_EQUIDISTANT) { xrvio_set_error("xrvio_create: unknown distortion_model"); return XRVIO_ERR_ARG; }
+        CKC(cudaMalloc((void **)&c->d_und, (size_t)S * P));
+        CKC(cudaMalloc((void **)&c->d_und_map, P * sizeof(int2)));
+        xvfe::undistort_build_map(xund::make_model(p->distortion_model, c->K, p->distortion), p->width, p->height, c->d_und_map, c->st);
+        CKC(cudaGetLastError());
+    }
     CKC(cudaMalloc((void **)&c->d_cand, (size_t)S * xvfe::kMaxCand * 8));
     CKC(cudaMalloc((void **)&c->d_cand_count, S * sizeof(int)));
     CKC(cudaMalloc((void **)&c->d_maxval, S * sizeof(unsigned)));
@@ -584,6 +593,7 @@ static int lane_destroy(Lane *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     cudaFree(c->rig_d); cudaFree(c->d_raw); cudaFree(c->d_pyr); 
+    cudaFree(c->d_und); cudaFree(c->d_und_map);
     cudaFree(c->d_lut); cudaFree(c->d_cand); cudaFree(c->d_cand_count); cudaFree(c->d_maxval); cudaFree(c->d_prior);
     cudaStreamDestroy(c->st);
     delete c;

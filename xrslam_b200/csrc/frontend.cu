@@ -791,4 +791,46 @@ void poisson_filter(const double *pts, const int *n_preset, const int *n_total, 
     poisson_kernel<<<n, 32, smem, st>>>(pts, n_preset, n_total, veto, keep, radius);
 }
 
+// ================================================================================================
+// Undistortion: fixed-point bilinear remap with OpenCV's arithmetic (undistort_math.h)
+// ================================================================================================
+__global__ void __launch_bounds__(256) undistort_map_kernel(xund::Model m, int w, int h, int2 *__restrict__ map) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= w || v >= h) return;
+    int qx, qy;
+    xund::source_q5(m, u, v, &qx, &qy);
+    map[(size_t)v * w + u] = make_int2(qx, qy);
+}
+
+__global__ void __launch_bounds__(256) undistort_kernel(const uint8_t *__restrict__ src, const int *__restrict__ sidx, size_t sstride,
+                                                        uint8_t *__restrict__ dst, const int *__restrict__ didx, size_t dstride,
+                                                        int w, int h, const int2 *__restrict__ map) {
+    const int item = blockIdx.z;
+    const uint8_t *s = src + (size_t)(sidx ? sidx[item] : item) * sstride;
+    uint8_t *d = dst + (size_t)(didx ? didx[item] : item) * dstride;
+    const int v = blockIdx.y;
+    // four consecutive output pixels per thread: one 32-bit store, map reads as two 128-bit loads
+    const int u0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (u0 >= w) return;
+    const int2 *mrow = map + (size_t)v * w;
+    if (u0 + 3 < w && (w & 3) == 0) {
+        const int4 a = *reinterpret_cast<const int4 *>(mrow + u0), b = *reinterpret_cast<const int4 *>(mrow + u0 + 2);
+        const unsigned p0 = xund::remap_q5(s, w, w, h, a.x, a.y), p1 = xund::remap_q5(s, w, w, h, a.z, a.w);
+        const unsigned p2 = xund::remap_q5(s, w, w, h, b.x, b.y), p3 = xund::remap_q5(s, w, w, h, b.z, b.w);
+        *reinterpret_cast<unsigned *>(d + (size_t)v * w + u0) = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+    } else {
+        for (int u = u0; u < min(u0 + 4, w); ++u) d[(size_t)v * w + u] = xund::remap_q5(s, w, w, h, mrow[u].x, mrow[u].y);
+    }
+}
+
+void undistort_build_map(const xund::Model &m, int w, int h, int2 *map, cudaStream_t st) {
+    undistort_map_kernel<<<dim3((w + 255) / 256, h), 256, 0, st>>>(m, w, h, map);
+}
+
+void undistort(const uint8_t *src, const int *src_idx, size_t src_stride, uint8_t *dst, const int *dst_idx, size_t dst_stride,
+               int n, int w, int h, const int2 *map, cudaStream_t st) {
+    if (n <= 0) return;
+    undistort_kernel<<<dim3(((w + 3) / 4 + 255) / 256, h, n), 256, 0, st>>>(src, src_idx, src_stride, dst, dst_idx, dst_stride, w, h, map);
+}
+
 }  // namespace xvfe

@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "undistort_math.h"
 
 namespace xvfe {
 
@@ -55,5 +56,12 @@ void klt_track(const uint8_t *prev_pyr, const uint8_t *next_pyr, const int *prev
 // mode 1: permit+preset with an extra per-point veto flag (track).  pts: n * kMaxPts * 2 doubles.
 void poisson_filter(const double *pts, const int *n_preset, const int *n_total, const uint8_t *veto, uint8_t *keep,
                     int n, double radius, cudaStream_t st);
+
+// ---- undistortion (what the reference's dataset readers do with cv::undistort / cv::remap on the CPU).
+// map: w*h source positions in 1/32 px, built once per camera; apply: batch item i reads src + (src_idx ? src_idx[i] : i) *
+// src_stride and writes dst + (dst_idx ? dst_idx[i] : i) * dst_stride.  1 B read-gather + 1 B write + 8 B of map (L2-resident) per pixel.
+void undistort_build_map(const xund::Model &m, int w, int h, int2 *map, cudaStream_t st);
+void undistort(const uint8_t *src, const int *src_idx, size_t src_stride, uint8_t *dst, const int *dst_idx, size_t dst_stride,
+               int n, int w, int h, const int2 *map, cudaStream_t st);
 
 }  // namespace xvfe

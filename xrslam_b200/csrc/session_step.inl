@@ -81,8 +81,16 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
     pt.next(1);
     CKC(cudaMemcpyAsync(B.idx_raw.d, B.idx_raw.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
     CKC(cudaMemcpyAsync(B.idx_next.d, B.idx_next.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    const uint8_t *clahe_src = c->d_raw;
+    const int *clahe_idx = B.idx_raw.d;
+    if (c->d_und) {     // the reader's cv::undistort, on the device (row N2); counted with the CLAHE family
+        ProfScope ps(c, FAM_CLAHE, 1);
+        xvfe::undistort(c->d_raw, B.idx_raw.d, P, c->d_und, nullptr, P, n, w, h, c->d_und_map, c->st);
+        c->stats.kernels_launched += 1;
+        clahe_src = c->d_und; clahe_idx = nullptr;
+    }
     { ProfScope ps(c, FAM_CLAHE, 2);
-      xvfe::clahe(c->d_raw, B.idx_raw.d, P, c->d_pyr, B.idx_next.d, c->L.total, c->d_lut, n, w, h, c->prm.clahe_clip_limit,
+      xvfe::clahe(clahe_src, clahe_idx, P, c->d_pyr, B.idx_next.d, c->L.total, c->d_lut, n, w, h, c->prm.clahe_clip_limit,
                   c->prm.clahe_width, c->prm.clahe_height, c->st); }
     { ProfScope ps(c, FAM_PYRAMID, 3); xvfe::pyramid(c->d_pyr, B.idx_next.d, n, c->L, c->st); }
     { ProfScope ps(c, FAM_GFTT, 2);
