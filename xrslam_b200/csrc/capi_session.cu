@@ -526,6 +526,8 @@ int xrvio_default_params_impl(xrvio_params *p, int width, int height) {
     return XRVIO_OK;
 }
 
+static int lane_destroy(Lane *c);
+
 static int lane_create(const xrvio_params *p, int n_sessions, int device, int host_threads, Lane **out) {
     if (!p || !out || n_sessions <= 0) { xrvio_set_error("xrvio_create: bad argument"); return XRVIO_ERR_ARG; }
     if (p->sliding_window_size + 2 > XRVIO_MAX_ACTIVE || p->max_keypoint_detection > XRVIO_MAX_CORNERS) { xrvio_set_error("xrvio_create: window / detection limit exceeded"); return XRVIO_ERR_LIMIT; }
@@ -533,6 +535,7 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { xrvio_set_error("xrvio_create: no CUDA device (there is no CPU fallback)"); return XRVIO_ERR_CUDA; }
     CKC(cudaSetDevice(device));
     Lane *c = new Lane();
+    struct Guard { Lane *l; ~Guard() { if (l) lane_destroy(l); } } guard{c};      // releases everything on an early error return
     c->prm = *p; c->S = n_sessions; c->device = device;
     CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     c->L = xvfe::make_pyr_layout(p->width, p->height);
@@ -584,6 +587,7 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
         c->pool = std::make_unique<ThreadPool>(std::max(1, std::min(host_threads, S)));
     }
     for (int i = 0; i < S; ++i) { c->ses[i].idx = i; c->ses[i].ft_map.track_id_counter = &c->ses[i].track_id_counter; }
+    guard.l = nullptr;
     *out = c;
     return XRVIO_OK;
 }
@@ -591,11 +595,11 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
 static int lane_destroy(Lane *c) {
     if (!c) return XRVIO_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->st);
+    if (c->st) cudaStreamSynchronize(c->st);
     cudaFree(c->rig_d); cudaFree(c->d_raw); cudaFree(c->d_pyr); 
     cudaFree(c->d_und); cudaFree(c->d_und_map);
     cudaFree(c->d_lut); cudaFree(c->d_cand); cudaFree(c->d_cand_count); cudaFree(c->d_maxval); cudaFree(c->d_prior);
-    cudaStreamDestroy(c->st);
+    if (c->st) cudaStreamDestroy(c->st);
     delete c;
     return XRVIO_OK;
 }
