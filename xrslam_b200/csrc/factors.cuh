@@ -17,7 +17,7 @@ struct RpeEval {
 
 // reprojection_factor.h:25-90
 // tb: the two tangent vectors b1, b2 of the target bearing (lie_algebra.cpp:47-56), precomputed per observation
-__device__ __forceinline__ void rpe_eval(const Q4 &qt, const V3 &pt, const Q4 &qr, const V3 &pr, double inv_depth,
+XV_HD void rpe_eval(const Q4 &qt, const V3 &pt, const Q4 &qr, const V3 &pr, double inv_depth,
                                          const V3 &zt, const V3 &zr, const double *tb, const RigParams &rg, bool want_jac,
                                          bool want_ref_jac, RpeEval &e) {
     const Q4 cq = ld4(rg.cam_q);
@@ -74,7 +74,7 @@ __device__ __forceinline__ void rpe_eval(const Q4 &qt, const V3 &pt, const Q4 &q
 }
 
 // rotation_factor.h:23-59 ; Jq: 2x3
-__device__ __forceinline__ void rot_eval(const Q4 &qt, const Q4 &qr, const V3 &zt, const V3 &zr, const RigParams &rg,
+XV_HD void rot_eval(const Q4 &qt, const Q4 &qr, const V3 &zt, const V3 &zr, const RigParams &rg,
                                          bool want_jac, double r[2], double Jq[6]) {
     const Q4 cq = ld4(rg.cam_q);
     const V3 cp = ld3(rg.cam_p);
@@ -102,7 +102,7 @@ __device__ __forceinline__ void rot_eval(const Q4 &qt, const Q4 &qr, const V3 &z
         for (int c = 0; c < 3; ++c) Jq[a * 3 + c] = B[a][0] * Hz(0, c) + B[a][1] * Hz(1, c) + B[a][2] * Hz(2, c);
 }
 
-__device__ __forceinline__ void put3x3(double *J, int r0, int c0, const M3 &A) {   // J is 15x15 row-major
+XV_HD void put3x3(double *J, int r0, int c0, const M3 &A) {   // J is 15x15 row-major
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) J[(r0 + r) * 15 + c0 + c] = A(r, c);
 }
@@ -110,7 +110,7 @@ __device__ __forceinline__ void put3x3(double *J, int r0, int c0, const M3 &A) {
 // preintegration_factor.h:20-159.  si / sj: 16-double states (candidate values); bias0: frame_i's
 // bg (3) and ba (3) in user memory (the D10 quirk, :38-39).  r: UNWHITENED residual (15);
 // Ji / Jj: UNWHITENED 15x15 Jacobians in error-state order (caller multiplies by sqrt_inv_cov).
-__device__ inline void pre_eval(const double *si, const double *sj, const double *bias0, const double *pb,
+__host__ __device__ inline void pre_eval(const double *si, const double *sj, const double *bias0, const double *pb,
                                 const RigParams &rg, bool want_jac, double *r, double *Ji, double *Jj) {
     const V3 gravity = v3(0.0, 0.0, -9.80665);
     const Q4 q_ci = ld4(si), q_cj = ld4(sj);
@@ -164,7 +164,7 @@ __device__ inline void pre_eval(const double *si, const double *sj, const double
 
 // marginalization_factor.h:29-47 : error of one frame against its linearisation point (15), and
 // right_jacobian(rq)^-1 (:53-57).
-__device__ __forceinline__ void marg_dx(const double *s, const double *lin, double *dx, M3 *Jr_inv) {
+XV_HD void marg_dx(const double *s, const double *lin, double *dx, M3 *Jr_inv) {
     const V3 rq = logmap(qmul(qconj(ld4(lin)), ld4(s)));
     st3(dx, rq);
     for (int k = 0; k < 12; ++k) dx[3 + k] = s[4 + k] - lin[4 + k];
