@@ -199,6 +199,11 @@ typedef struct xrvio_params {
                                      XRVIO_DISTORTION_RADTAN / _EQUIDISTANT: the library undistorts every pushed image on the
                                      device with the readers' arithmetic (xrvio_op_undistort) before CLAHE */
     double distortion[4];         /* k1 k2 p1 p2 (radtan) or k1 k2 k3 k4 (equidistant); intrinsics are fx fy cx cy above */
+    int essential_ransac;         /* 1: run the per-frame 5-point essential RANSAC of Frame::track_keypoints (frame.cpp:108-114,
+                                     threshold 1.0) on the host; 0 (default): use its observable effect -- with that threshold
+                                     (2 * 3.84 in squared normalised image units) every match is an inlier, so the mask is all
+                                     ones, or all zeros below 5 points (tests/test_oracle_geometry.py shows it on a stream) */
+    int pad;
 } xrvio_params;
 
 typedef struct xrvio_imu { double t, w[3], a[3]; } xrvio_imu;
@@ -215,7 +220,8 @@ typedef struct xrvio_stats {
  * tried), 1 too few matches, 2 too little parallax, 3 pure rotation, 4 two-view triangulation, 5 visual BA unusable,
  * 6 scale outside [0.001, 1], 7 too few landmarks, 8 keyframe without IMU data, 9 fewer frames than the keyframe span */
 typedef struct xrvio_init_info {
-    int attempts, last_fail, matches, candidate, landmarks, pad;
+    int attempts, last_fail, matches, candidate, landmarks;
+    int essential_rejected;       /* matches rejected so far by the optional per-frame essential RANSAC (xrvio_params.essential_ransac) */
     double parallax, scale;
 } xrvio_init_info;
 

@@ -55,3 +55,21 @@ def test_initializer_can_be_disabled(xrvio):
     ctx, outs = drive.run_streams_cuda([s], 40, ctx=ctx, bootstrap=False)
     assert ctx.get_state(0) == 0 and len(outs[0]) == 0 and ctx.get_init_info(0)['attempts'] == 0
     ctx.close()
+
+
+def test_per_frame_essential_ransac_changes_nothing(xrvio, golden_dir):
+    """xrvio_params.essential_ransac = 1 runs the reference's per-frame 5-point RANSAC (frame.cpp:108-114) on the host; with its
+    threshold every match is an inlier, so the trajectory is the one of the default path (the committed golden)."""
+    ref = np.load(os.path.join(golden_dir, 'stream3_traj.npz'))['traj']
+    s = Stream(3)
+    p = drive.params_for(s)
+    p['essential_ransac'] = 1
+    from xrslam_b200 import capi
+    ctx = capi.Context(p, 1)
+    ctx, outs = drive.run_streams_cuda([s], 50, ctx=ctx)
+    got = np.array([[t] + list(q) + list(pp) for (t, q, pp) in outs[0]])
+    m = len(got)
+    assert m >= 10 and np.allclose(got[:, 0], ref[:m, 0])
+    assert np.linalg.norm(got[:, 5:8] - ref[:m, 5:8], axis=1).max() <= 2e-3
+    assert ctx.get_init_info(0)['essential_rejected'] == 0
+    ctx.close()

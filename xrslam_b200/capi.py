@@ -205,11 +205,11 @@ params_dtype = np.dtype([("width", "i4"), ("height", "i4"), ("fx", "f8"), ("fy",
                          ("rotation_ransac_threshold", "f8"), ("prior_eigen_form", "i4"), ("initializer", "i4"),
                          ("init_min_matches", "i4"), ("init_min_triangulation", "i4"), ("init_min_landmarks", "i4"),
                          ("init_refine_imu", "i4"), ("init_min_parallax", "f8"), ("random_seed", "i4"), ("distortion_model", "i4"),
-                         ("distortion", "f8", 4)], align=True)
+                         ("distortion", "f8", 4), ("essential_ransac", "i4"), ("pad", "i4")], align=True)
 imu_dtype = np.dtype([("t", "f8"), ("w", "f8", 3), ("a", "f8", 3)], align=True)
 pose_dtype = np.dtype([("q", "f8", 4), ("p", "f8", 3), ("t", "f8"), ("valid", "i4"), ("pad", "i4")], align=True)
 init_info_dtype = np.dtype([("attempts", "i4"), ("last_fail", "i4"), ("matches", "i4"), ("candidate", "i4"), ("landmarks", "i4"),
-                            ("pad", "i4"), ("parallax", "f8"), ("scale", "f8")], align=True)
+                            ("essential_rejected", "i4"), ("parallax", "f8"), ("scale", "f8")], align=True)
 stats_dtype = np.dtype([("frames_processed", "i8"), ("kernels_launched", "i8"), ("h2d_bytes", "i8"), ("d2h_bytes", "i8"),
                         ("window_solves", "i8"), ("localize_solves", "i8"), ("subwindow_solves", "i8"), ("marginalizations", "i8"),
                         ("last_window_cost_initial", "f8"), ("last_window_cost_final", "f8")], align=True)
@@ -301,7 +301,7 @@ class Context:
     def get_init_info(self, session):
         s = np.zeros(1, init_info_dtype)
         lib.check(lib.xrvio_get_init_info(self._h, int(session), _p(s)))
-        return {k: s[0][k].item() for k in init_info_dtype.names if k != 'pad'}
+        return {k: s[0][k].item() for k in init_info_dtype.names}
 
     def stats(self):
         s = np.zeros(1, stats_dtype)

@@ -111,6 +111,7 @@ struct Session {
     double out_t = 0;
     std::map<long long, State16> bootstrap;       // keyed by round(t * 1e6)
     xrvio_init_info init{};                       // outcome of the initializer attempts (session_init.inl)
+    long long essential_rejected = 0;             // matches rejected by the optional per-frame essential RANSAC
     bool init_now = false;                        // the initializer succeeded in this round
     int img_slot_next = 0;
     int pyr_next = 0;
@@ -824,6 +825,7 @@ int xrvio_get_init_info(xrvio_ctx *ctx, int session, xrvio_init_info *out) {
     LANE_OF(session, l, i);
     if (!out) { xrvio_set_error("xrvio_get_init_info: null output"); return XRVIO_ERR_ARG; }
     *out = l->ses[i].init;
+    out->essential_rejected = (int)std::min<long long>(l->ses[i].essential_rejected, 2147483647LL);
     return XRVIO_OK;
 }
 

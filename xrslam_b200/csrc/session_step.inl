@@ -176,6 +176,18 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         for (int k = 0; k < np; ++k) s.next_bearings[k] = remove_k(&s.klt_next[2 * k], c->K);
         // essential-matrix RANSAC mask (frame.cpp:108-114): all ones for n >= 5, all zeros otherwise
         if (np < 5) std::fill(s.klt_status.begin(), s.klt_status.end(), 0);
+        else if (c->prm.essential_ransac) {
+            std::vector<xvi::V2> ch(np), nh(np);
+            for (int k = 0; k < np; ++k) {
+                const V3 &a = last->bearings[k], &b = s.next_bearings[k];
+                ch[k] = {a.x / a.z, a.y / a.z}; nh[k] = {b.x / b.z, b.y / b.z};
+            }
+            M3 E = m3_identity();
+            std::vector<char> emask;
+            xvi::find_essential_matrix(ch, nh, 1.0, 0.999, 1000, 0, E, emask);
+            for (int k = 0; k < np; ++k) if (!emask[k]) s.klt_status[k] = 0;
+            s.essential_rejected += (long long)std::count(emask.begin(), emask.end(), (char)0);
+        }
         std::vector<char> mask;
         M3 R = find_rotation_matrix(last->bearings, s.next_bearings, mask, (M_PI / 180.0) * c->prm.rotation_ransac_threshold);
         std::vector<double> angles;
