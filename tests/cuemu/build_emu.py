@@ -13,7 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'xrslam_b200', 'csrc')
-OUT = os.path.join(HERE, '_build')
+SAN = os.environ.get('XRVIO_EMU_SANITIZE') == '1'      # AddressSanitizer build: out-of-bounds accesses of the kernels and the host glue
+OUT = os.path.join(HERE, '_build_asan' if SAN else '_build')
 LIB = os.path.join(OUT, 'libxrvio_emu.so')
 SOURCES = ['frontend.cu', 'backend_preint.cu', 'backend_solve.cu', 'backend_marg.cu', 'capi_ops.cu', 'capi_session.cu', 'xrslam_shim.cu']
 
@@ -87,6 +88,8 @@ def build(verbose=False):
             oh.write(fh.read())
     objs, procs = [], []
     flags = ['-O2', '-g0', '-std=c++17', '-fPIC', '-w', '-ffp-contract=off', '-I', os.path.join(HERE, 'include')]
+    if SAN:
+        flags = ['-O1', '-g', '-fsanitize=address', '-fno-omit-frame-pointer'] + flags[2:]
     for s in SOURCES:
         cpp = os.path.join(gen, s[:-3] + '.cpp')
         obj = os.path.join(OUT, s[:-3] + '.o')
@@ -106,7 +109,7 @@ def build(verbose=False):
             sys.stderr.write('g++ failed for %s:\n%s\n' % (s, o.decode()[:6000]))
     if bad:
         raise RuntimeError('emulated library build failed')
-    subprocess.check_call(['g++', '-shared', '-o', LIB] + objs + ['-lpthread'])
+    subprocess.check_call(['g++', '-shared', '-o', LIB] + objs + ['-lpthread'] + (['-fsanitize=address'] if SAN else []))
     return LIB
 
 

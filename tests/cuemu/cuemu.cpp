@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstdio>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #if !defined(__x86_64__)
@@ -150,12 +151,22 @@ unsigned ballot(unsigned mask, int pred) {
     return r;
 }
 
+// CUEMU_ORDER=reverse runs the fibers of a block from the last thread to the first: a kernel whose result depends on
+// the order in which threads reach a point (a missing __syncthreads / __syncwarp) shows up as a difference between
+// the two orders.
+static bool reverse_order() {
+    static const bool r = [] { const char *e = std::getenv("CUEMU_ORDER"); return e && std::string(e) == "reverse"; }();
+    return r;
+}
+
 static void run_block(Block &b) {
     g_blk = &b;
     const int n = (int)b.fibers.size();
+    const bool rev = reverse_order();
     while (b.live > 0) {
         bool progressed = false;
-        for (int i = 0; i < n; ++i) {
+        for (int ii = 0; ii < n; ++ii) {
+            const int i = rev ? n - 1 - ii : ii;
             Fiber &f = b.fibers[i];
             if (f.wait == DONE) continue;
             if (f.wait == W_BLOCK) { if (f.gen == b.block_gen) continue; f.wait = RUN; }
