@@ -28,8 +28,13 @@ struct CameraConfig {
 };
 
 inline bool yaml_numbers(const std::string &txt, const std::string &key, int n, double *out, size_t from) {
-    size_t p = txt.find(key + ":", from);
-    if (p == std::string::npos) return false;
+    size_t p = from;
+    while (true) {      // whole-key match: "size" must not hit "subframe_size"
+        p = txt.find(key + ":", p);
+        if (p == std::string::npos) return false;
+        if (p == 0 || !(isalnum((unsigned char)txt[p - 1]) || txt[p - 1] == '_')) break;
+        p += key.size();
+    }
     p += key.size() + 1;
     int got = 0;
     while (got < n && p < txt.size()) {
@@ -62,13 +67,7 @@ inline CameraConfig load_camera_config(const std::string &device_yaml) {
     double v[4];
     if (!yaml_numbers(txt, "intrinsics", 4, c.K, c0)) return c;
     if (yaml_numbers(txt, "camera_distortion_flag", 1, v, c0)) c.distortion_flag = (int)v[0];
-    {   // "distortion:" but not "distortion_model:" / "camera_distortion_flag:"
-        size_t p = c0;
-        while ((p = txt.find("distortion:", p)) != std::string::npos) {
-            if (p > 0 && (txt[p - 1] == ' ' || txt[p - 1] == '\n')) { yaml_numbers(txt, "distortion", 4, c.D, p); break; }
-            p += 11;
-        }
-    }
+    yaml_numbers(txt, "distortion", 4, c.D, c0);          // whole-key match: not "camera_distortion_flag" / "distortion_model"
     if (yaml_numbers(txt, "time_offset", 1, v, c0)) c.time_offset = v[0];
     c.ok = true;
     return c;

@@ -47,8 +47,13 @@ std::string slurp(const char *path) {
     return ss.str();
 }
 bool numbers_after(const std::string &txt, const std::string &key, int n, double *out, size_t from = 0) {
-    size_t p = txt.find(key + ":", from);
-    if (p == std::string::npos) return false;
+    size_t p = from;
+    while (true) {      // whole-key match: "size" must not hit "subframe_size"
+        p = txt.find(key + ":", p);
+        if (p == std::string::npos) return false;
+        if (p == 0 || !(isalnum((unsigned char)txt[p - 1]) || txt[p - 1] == '_')) break;
+        p += key.size();
+    }
     p += key.size() + 1;
     int got = 0;
     while (got < n && p < txt.size()) {
