@@ -8,6 +8,7 @@ Outputs:
   backend_problems.npz  one recorded problem of every solve kind + a marginalisation, before / after the oracle
   preint.npz            preintegration jobs and oracle results
   stream3_traj.npz      oracle trajectory of synthetic stream seed 3 (first 66 frames)
+  stream7_traj1200.npz  oracle trajectory of stream seed 7 over 60 s (BASELINE config 2; `make_golden.py minute`)
   stream7_init_traj.npz oracle trajectory of stream seed 7 initialised by the reference initializer (no bootstrap states)
   stream7_traj140.npz   oracle trajectory of synthetic stream seed 7, 140 frames (steady-state marginalisation)
 """
@@ -127,6 +128,15 @@ def long_trajectory():
     print('long trajectory rows', len(traj))
 
 
+def minute_trajectory():
+    """BASELINE config 2: one stream, 60 s = 1200 frames (about 11 min of oracle time)."""
+    s = Stream(7)
+    sess = run_stream(s, 1200)
+    traj = np.array([[t] + list(q) + list(p) for (t, q, p) in sess.outputs])
+    np.savez_compressed(os.path.join(HERE, 'stream7_traj1200.npz'), traj=traj)
+    print('60 s trajectory rows', len(traj))
+
+
 def initializer_trajectory():
     """Stream 7 WITHOUT ground-truth bootstrap: the oracle runs the reference initializer (oracle/initializer.py)."""
     s = Stream(7)
@@ -142,6 +152,9 @@ if __name__ == '__main__':
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == 'init':
         initializer_trajectory()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'minute':
+        minute_trajectory()
         sys.exit(0)
     long_trajectory()
     initializer_trajectory()
