@@ -73,6 +73,43 @@ struct DevOnly {
     template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+// One pinned host block and its device twin per lane.  A back-end phase packs all of its small inputs back to back
+// (put), uploads them with ONE copy, and reads its results back with ONE copy of a contiguous output prefix, instead of a
+// copy per array.  Every user ends with a stream synchronisation, so the block is free again when the next phase packs.
+struct Stage {
+    unsigned char *h = nullptr, *d = nullptr;
+    size_t cap = 0, off = 0;
+    ~Stage() { if (h) cudaFreeHost(h); if (d) cudaFree(d); }
+    cudaError_t reserve(size_t want) {
+        if (want <= cap) return cudaSuccess;
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        h = d = nullptr; cap = 0;
+        const size_t nc = want + want / 2 + 4096;
+        cudaError_t e = cudaHostAlloc((void **)&h, nc, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc((void **)&d, nc);
+        if (e != cudaSuccess) return e;
+        cap = nc;
+        return cudaSuccess;
+    }
+    void reset() { off = 0; }
+    static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+    // reserve room for `count` elements; returns the device pointer, *host receives the matching host pointer
+    template <class T> T *slot(size_t count, T **host) {
+        T *dp = reinterpret_cast<T *>(d + off);
+        *host = reinterpret_cast<T *>(h + off);
+        off += padded(count * sizeof(T));
+        return dp;
+    }
+    template <class T> T *put(const T *src, size_t count) {
+        T *hp;
+        T *dp = slot<T>(count, &hp);
+        if (count) std::memcpy(hp, src, count * sizeof(T));
+        return dp;
+    }
+};
+
 constexpr int kImgQueue = 4;       // frames per session that may wait on the device between steps
 constexpr int kPyrSlots = 3;       // pyramid buffers per session (previous, next, spare)
 
@@ -173,6 +210,7 @@ struct Lane {
     Arena<xvbe::MargDesc> mdesc; Arena<int> mrank;
     Arena<xvbe::TriJob> tjobs; Arena<double> tviews; Arena<double> tout;
     DevOnly scratch;
+    Stage stage;                       // packed inputs / outputs of one back-end launch
     // ---- optional per-kernel-family timing with CUDA events on the launch stream ----
     bool prof = false;
     struct ProfEv { int fam; cudaEvent_t a, b; };
@@ -304,9 +342,13 @@ int run_preint_jobs(Lane *c) {
     const int n = (int)c->pre_jobs.n;
     if (n == 0) return XRVIO_OK;
     CKC(c->pre_out.reserve((size_t)n * XRVIO_PRE_BLOCK));
-    CKC(cudaMemcpyAsync(c->pre_jobs.d, c->pre_jobs.h, n * sizeof(xvbe::PreintJob), cudaMemcpyHostToDevice, c->st));
-    CKC(cudaMemcpyAsync(c->imu.d, c->imu.h, c->imu.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    { ProfScope ps(c, FAM_PREINT, 1); xvbe::preintegrate(c->pre_jobs.d, n, c->imu.d, c->rig_d, c->pre_out.d, c->st); }
+    Stage &g = c->stage;
+    CKC(g.reserve(Stage::padded(n * sizeof(xvbe::PreintJob)) + Stage::padded(c->imu.n * sizeof(double)) + 512));
+    g.reset();
+    const xvbe::PreintJob *d_jobs = g.put(c->pre_jobs.h, (size_t)n);
+    const double *d_imu = g.put(c->imu.h, c->imu.n);
+    CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));
+    { ProfScope ps(c, FAM_PREINT, 1); xvbe::preintegrate(d_jobs, n, d_imu, c->rig_d, c->pre_out.d, c->st); }
     c->stats.kernels_launched += 1;
     CKC(cudaMemcpyAsync(c->pre_out.h, c->pre_out.d, (size_t)n * XRVIO_PRE_BLOCK * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CKC(cudaStreamSynchronize(c->st));
@@ -467,27 +509,41 @@ int run_solves(Lane *c) {
     }
     CKC(c->scratch.reserve(scratch * sizeof(double)));
     CKC(c->sout.reserve(n));
-    auto up = [&](void *dst, const void *src, size_t bytes) { c->stats.h2d_bytes += bytes; return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->st) : cudaSuccess; };
-    CKC(up(c->sdesc.d, c->sdesc.h, n * sizeof(xvbe::SolveDesc)));
-    CKC(up(c->states.d, c->states.h, c->states.n * sizeof(double)));
-    CKC(up(c->fflags.d, c->fflags.h, c->fflags.n));
-    CKC(up(c->invd.d, c->invd.h, c->invd.n * sizeof(double)));
-    CKC(up(c->rpe.d, c->rpe.h, c->rpe.n * sizeof(xvbe::RpeObs)));
-    CKC(up(c->rot.d, c->rot.h, c->rot.n * sizeof(xvbe::RotObs)));
-    CKC(up(c->pref.d, c->pref.h, c->pref.n * sizeof(xvbe::PreRef)));
-    CKC(up(c->pblocks.d, c->pblocks.h, c->pblocks.n * sizeof(double)));
-    CKC(up(c->mframes.d, c->mframes.h, c->mframes.n * sizeof(int)));
+    // one upload: [states | inv_depth | summaries] (also the download, they are updated in place) then the read-only inputs
+    Stage &g = c->stage;
+    const size_t in_bytes = c->states.n * 8 + c->invd.n * 8 + n * sizeof(xvbe::SolveOut) + n * sizeof(xvbe::SolveDesc) + c->fflags.n + c->rpe.n * sizeof(xvbe::RpeObs) +
+                            c->rot.n * sizeof(xvbe::RotObs) + c->pref.n * sizeof(xvbe::PreRef) + c->pblocks.n * 8 + c->mframes.n * sizeof(int);
+    CKC(g.reserve(in_bytes + 16 * 256));
+    g.reset();
     xvbe::SolveBatch b;
-    b.desc = c->sdesc.d; b.states = c->states.d; b.frame_flags = c->fflags.d; b.inv_depth = c->invd.d; b.rpe = c->rpe.d; b.rot = c->rot.d;
-    b.pre = c->pref.d; b.pre_blocks = c->pblocks.d; b.marg_frames = c->mframes.d; b.marg = c->d_prior; b.scratch = c->scratch.as<double>();
-    b.out = c->sout.d;
+    b.states = g.put(c->states.h, c->states.n);
+    b.inv_depth = g.put(c->invd.h, c->invd.n);
+    xvbe::SolveOut *h_out;
+    b.out = g.slot<xvbe::SolveOut>((size_t)n, &h_out);
+    const size_t out_bytes = g.off;
+    b.desc = g.put(c->sdesc.h, (size_t)n);
+    b.frame_flags = g.put(c->fflags.h, c->fflags.n);
+    b.rpe = g.put(c->rpe.h, c->rpe.n);
+    b.rot = g.put(c->rot.h, c->rot.n);
+    b.pre = g.put(c->pref.h, c->pref.n);
+    b.pre_blocks = g.put(c->pblocks.h, c->pblocks.n);
+    b.marg_frames = g.put(c->mframes.h, c->mframes.n);
+    b.marg = c->d_prior; b.scratch = c->scratch.as<double>();
+    CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));
+    c->stats.h2d_bytes += in_bytes - n * sizeof(xvbe::SolveOut);
     { ProfScope ps(c, FAM_SOLVE, 1); xvbe::solve(b, n, c->rig_d, c->st); }
     c->stats.kernels_launched += 1;
     CKC(cudaGetLastError());
-    CKC(cudaMemcpyAsync(c->states.h, c->states.d, c->states.n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    if (c->invd.n) CKC(cudaMemcpyAsync(c->invd.h, c->invd.d, c->invd.n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    CKC(cudaMemcpyAsync(c->sout.h, c->sout.d, n * sizeof(xvbe::SolveOut), cudaMemcpyDeviceToHost, c->st));
+    CKC(cudaMemcpyAsync(g.h, g.d, out_bytes, cudaMemcpyDeviceToHost, c->st));
     CKC(cudaStreamSynchronize(c->st));
+    // the rest of the step reads the results from the arenas' host arrays
+    {
+        const unsigned char *hp = g.h;
+        std::memcpy(c->states.h, hp, c->states.n * sizeof(double)); hp += Stage::padded(c->states.n * sizeof(double));
+        if (c->invd.n) std::memcpy(c->invd.h, hp, c->invd.n * sizeof(double));
+        hp += Stage::padded(c->invd.n * sizeof(double));
+        std::memcpy(c->sout.h, hp, n * sizeof(xvbe::SolveOut));
+    }
     c->stats.d2h_bytes += c->states.n * sizeof(double) + c->invd.n * sizeof(double) + n * sizeof(xvbe::SolveOut);
     return XRVIO_OK;
 }
@@ -583,6 +639,7 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
     CKC(c->tjobs.reserve((size_t)S * 512)); CKC(c->tviews.reserve((size_t)S * 256 * 8 * 16)); CKC(c->tout.reserve((size_t)S * 512 * 4));
     CKC(c->scratch.reserve((size_t)S * (xvbe::solve_scratch_doubles(XRVIO_MAX_ACTIVE, 768, 12, XRVIO_MAX_ACTIVE, 4096) + (size_t)2 * 180 * 180 + 8192) * sizeof(double)));
     CKC(c->sbuf.idx_raw.reserve(S)); CKC(c->sbuf.idx_next.reserve(S)); CKC(c->sbuf.idx_prev.reserve(S));
+    CKC(c->stage.reserve((size_t)S * (XRVIO_MAX_FRAMES * 16 * 8 + 1024 * 8 + 4096 * sizeof(xvbe::RpeObs) + 16 * XRVIO_PRE_BLOCK * 8 + 16 * 64 * 7 * 8 + 65536)));
     c->ses.resize(S);
     {
         c->pool = std::make_unique<ThreadPool>(std::max(1, std::min(host_threads, S)));

@@ -292,9 +292,13 @@ int run_triangulation(Lane *c) {
     const int n = (int)c->tjobs.n;
     if (n == 0) return XRVIO_OK;
     CKC(c->tout.reserve((size_t)n * 4));
-    CKC(cudaMemcpyAsync(c->tjobs.d, c->tjobs.h, n * sizeof(xvbe::TriJob), cudaMemcpyHostToDevice, c->st));
-    CKC(cudaMemcpyAsync(c->tviews.d, c->tviews.h, c->tviews.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    { ProfScope ps(c, FAM_TRI, 1); xvbe::triangulate(c->tjobs.d, n, c->tviews.d, c->tout.d, c->st); }
+    Stage &g = c->stage;
+    CKC(g.reserve(Stage::padded(n * sizeof(xvbe::TriJob)) + Stage::padded(c->tviews.n * sizeof(double)) + 512));
+    g.reset();
+    const xvbe::TriJob *d_jobs = g.put(c->tjobs.h, (size_t)n);
+    const double *d_views = g.put(c->tviews.h, c->tviews.n);
+    CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));
+    { ProfScope ps(c, FAM_TRI, 1); xvbe::triangulate(d_jobs, n, d_views, c->tout.d, c->st); }
     c->stats.kernels_launched += 1;
     CKC(cudaMemcpyAsync(c->tout.h, c->tout.d, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CKC(cudaStreamSynchronize(c->st));
@@ -794,17 +798,17 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         }
         CKC(c->scratch.reserve(scratch * sizeof(double)));
         CKC(c->mrank.reserve(nm));
-        CKC(cudaMemcpyAsync(c->mdesc.d, c->mdesc.h, nm * sizeof(xvbe::MargDesc), cudaMemcpyHostToDevice, c->st));
-        CKC(cudaMemcpyAsync(c->states.d, c->states.h, c->states.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-        if (c->invd.n) CKC(cudaMemcpyAsync(c->invd.d, c->invd.h, c->invd.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-        if (c->rpe.n) CKC(cudaMemcpyAsync(c->rpe.d, c->rpe.h, c->rpe.n * sizeof(xvbe::RpeObs), cudaMemcpyHostToDevice, c->st));
-        if (c->pref.n) CKC(cudaMemcpyAsync(c->pref.d, c->pref.h, c->pref.n * sizeof(xvbe::PreRef), cudaMemcpyHostToDevice, c->st));
-        if (c->pblocks.n) CKC(cudaMemcpyAsync(c->pblocks.d, c->pblocks.h, c->pblocks.n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-        CKC(cudaMemcpyAsync(c->mframes.d, c->mframes.h, c->mframes.n * sizeof(int), cudaMemcpyHostToDevice, c->st));
-        c->stats.h2d_bytes += nm * sizeof(xvbe::MargDesc) + c->states.n * 8 + c->invd.n * 8 + c->rpe.n * sizeof(xvbe::RpeObs) + c->pblocks.n * 8;
+        Stage &g = c->stage;
+        CKC(g.reserve(nm * sizeof(xvbe::MargDesc) + c->states.n * 8 + c->invd.n * 8 + c->rpe.n * sizeof(xvbe::RpeObs) + c->pref.n * sizeof(xvbe::PreRef) +
+                      c->pblocks.n * 8 + c->mframes.n * sizeof(int) + 16 * 256));
+        g.reset();
         xvbe::MargBatch mb;
-        mb.desc = c->mdesc.d; mb.states = c->states.d; mb.inv_depth = c->invd.d; mb.rpe = c->rpe.d; mb.pre = c->pref.d; mb.pre_blocks = c->pblocks.d;
-        mb.marg_frames = c->mframes.d; mb.marg = c->d_prior; mb.out = c->d_prior; mb.scratch = c->scratch.as<double>(); mb.rank_out = c->mrank.d;
+        mb.desc = g.put(c->mdesc.h, (size_t)nm); mb.states = g.put(c->states.h, c->states.n); mb.inv_depth = g.put(c->invd.h, c->invd.n);
+        mb.rpe = g.put(c->rpe.h, c->rpe.n); mb.pre = g.put(c->pref.h, c->pref.n); mb.pre_blocks = g.put(c->pblocks.h, c->pblocks.n);
+        mb.marg_frames = g.put(c->mframes.h, c->mframes.n);
+        CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));      // one upload for the whole batch of problems
+        c->stats.h2d_bytes += nm * sizeof(xvbe::MargDesc) + c->states.n * 8 + c->invd.n * 8 + c->rpe.n * sizeof(xvbe::RpeObs) + c->pblocks.n * 8;
+        mb.marg = c->d_prior; mb.out = c->d_prior; mb.scratch = c->scratch.as<double>(); mb.rank_out = c->mrank.d;
         { ProfScope ps(c, FAM_MARG, 1); xvbe::marginalize(mb, nm, c->rig_d, c->st); }
         c->stats.kernels_launched += 1;
         CKC(cudaGetLastError());
