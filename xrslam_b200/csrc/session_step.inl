@@ -15,13 +15,16 @@ template <class F> int for_sessions(Lane *c, std::vector<Session *> &act, F body
 
 int run_poisson(Lane *c, int n, bool with_veto) {
     const size_t pb = (size_t)n * xvfe::kMaxPts;
-    CKC(cudaMemcpyAsync(c->poi_pts.d, c->poi_pts.h, pb * 2 * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    CKC(cudaMemcpyAsync(c->poi_npre.d, c->poi_npre.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
-    CKC(cudaMemcpyAsync(c->poi_ntot.d, c->poi_ntot.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
-    if (with_veto) CKC(cudaMemcpyAsync(c->poi_veto.d, c->poi_veto.h, pb, cudaMemcpyHostToDevice, c->st));
+    Stage &g = c->stage;
+    CKC(g.reserve(pb * 2 * sizeof(double) + pb + 2 * n * sizeof(int) + 8 * 256));
+    g.reset();
+    const double *d_pts = g.put(c->poi_pts.h, pb * 2);
+    const int *d_npre = g.put(c->poi_npre.h, (size_t)n);
+    const int *d_ntot = g.put(c->poi_ntot.h, (size_t)n);
+    const uint8_t *d_veto = with_veto ? g.put(c->poi_veto.h, pb) : nullptr;
+    CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));
     { ProfScope ps(c, FAM_POISSON, 1);
-      xvfe::poisson_filter(c->poi_pts.d, c->poi_npre.d, c->poi_ntot.d, with_veto ? c->poi_veto.d : nullptr, c->poi_keep.d, n,
-                           c->prm.min_keypoint_distance, c->st); }
+      xvfe::poisson_filter(d_pts, d_npre, d_ntot, d_veto, c->poi_keep.d, n, c->prm.min_keypoint_distance, c->st); }
     c->stats.kernels_launched += 1;
     CKC(cudaMemcpyAsync(c->poi_keep.h, c->poi_keep.d, pb, cudaMemcpyDeviceToHost, c->st));
     CKC(cudaStreamSynchronize(c->st));
@@ -140,17 +143,26 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
     const int n_klt = n_klt_a.load();
     pt.next(3);
     if (n_klt > 0) {
-        const size_t pb = (size_t)n * xvfe::kMaxPts * 2 * sizeof(float);
-        CKC(cudaMemcpyAsync(c->klt_prev.d, c->klt_prev.h, pb, cudaMemcpyHostToDevice, c->st));
-        CKC(cudaMemcpyAsync(c->klt_next.d, c->klt_next.h, pb, cudaMemcpyHostToDevice, c->st));
-        CKC(cudaMemcpyAsync(c->klt_n.d, c->klt_n.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
-        CKC(cudaMemcpyAsync(B.idx_prev.d, B.idx_prev.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+        const size_t npt = (size_t)n * xvfe::kMaxPts, pb = npt * 2 * sizeof(float);
+        Stage &g = c->stage;
+        CKC(g.reserve(2 * pb + npt + 2 * n * sizeof(int) + 8 * 256));
+        g.reset();
+        // [next positions | status] first: they are what comes back
+        float *d_next = g.put(c->klt_next.h, npt * 2);
+        unsigned char *h_status;
+        unsigned char *d_status = g.slot<unsigned char>(npt, &h_status);
+        const size_t out_bytes = g.off;
+        const float *d_prev = g.put(c->klt_prev.h, npt * 2);
+        const int *d_n = g.put(c->klt_n.h, (size_t)n);
+        const int *d_idx_prev = g.put(B.idx_prev.h, (size_t)n);
+        CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));
         { ProfScope ps(c, FAM_KLT, 1);
-          xvfe::klt_track(c->d_pyr, c->d_pyr, B.idx_prev.d, B.idx_next.d, n, c->L, c->klt_prev.d, c->klt_next.d, c->klt_n.d, c->klt_status.d, c->st); }
+          xvfe::klt_track(c->d_pyr, c->d_pyr, d_idx_prev, B.idx_next.d, n, c->L, d_prev, d_next, d_n, d_status, c->st); }
         c->stats.kernels_launched += 1;
-        CKC(cudaMemcpyAsync(c->klt_next.h, c->klt_next.d, pb, cudaMemcpyDeviceToHost, c->st));
-        CKC(cudaMemcpyAsync(c->klt_status.h, c->klt_status.d, (size_t)n * xvfe::kMaxPts, cudaMemcpyDeviceToHost, c->st));
+        CKC(cudaMemcpyAsync(g.h, g.d, out_bytes, cudaMemcpyDeviceToHost, c->st));
         CKC(cudaStreamSynchronize(c->st));
+        std::memcpy(c->klt_next.h, g.h, pb);
+        std::memcpy(c->klt_status.h, g.h + Stage::padded(pb), npt);
         c->stats.h2d_bytes += 2 * pb + 2 * n * sizeof(int);
         c->stats.d2h_bytes += pb + (size_t)n * xvfe::kMaxPts;
     }
