@@ -17,6 +17,9 @@
 #include "thread_pool.hpp"
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstdlib>
 #include <map>
 #include <string>
@@ -776,29 +779,77 @@ static int lane_get_stats(Lane *c, xrvio_stats *st) {
 // so one lane's host bookkeeping overlaps the other lanes' kernels and small kernels of different
 // lanes share the GPU.  Sessions never interact, so the lane split does not change any result.
 // =================================================================================================
+// One persistent host thread per lane: xrvio_step hands every lane its step and waits for all of them (creating and
+// joining threads per call would put ~25 us per lane on the critical path of every step).
+struct LaneWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int(Lane *)> job;
+    bool has_job = false, done = true, quit = false;
+    int rc = 0;
+    std::string err;
+};
+
 struct xrvio_ctx {
     std::vector<Lane *> lanes;
+    std::vector<std::unique_ptr<LaneWorker>> workers;
     std::vector<std::pair<int, int>> where;     // session -> (lane, local index)
     int S = 0, device = 0;
     std::vector<std::vector<int>> tmp_idx;
 };
 
 namespace {
+void lane_worker_main(xrvio_ctx *ctx, int l) {
+    LaneWorker &w = *ctx->workers[l];
+    cudaSetDevice(ctx->device);
+    std::unique_lock<std::mutex> lk(w.mu);
+    while (true) {
+        w.cv.wait(lk, [&] { return w.has_job || w.quit; });
+        if (w.quit) return;
+        std::function<int(Lane *)> job = w.job;
+        w.has_job = false;
+        lk.unlock();
+        const int rc = job(ctx->lanes[l]);
+        std::string err = rc ? xrvio_last_error() : "";
+        lk.lock();
+        w.rc = rc; w.err = err; w.done = true;
+        w.cv.notify_all();
+    }
+}
+void start_workers(xrvio_ctx *ctx) {
+    const int L = (int)ctx->lanes.size();
+    if (L <= 1) return;
+    for (int l = 0; l < L; ++l) ctx->workers.emplace_back(new LaneWorker());
+    for (int l = 0; l < L; ++l) ctx->workers[l]->th = std::thread(lane_worker_main, ctx, l);
+}
+void stop_workers(xrvio_ctx *ctx) {
+    for (auto &w : ctx->workers) {
+        { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; }
+        w->cv.notify_all();
+        if (w->th.joinable()) w->th.join();
+    }
+    ctx->workers.clear();
+}
 template <class F> int each_lane(xrvio_ctx *ctx, F fn) {
     const int L = (int)ctx->lanes.size();
-    std::vector<int> rc(L, 0);
-    std::vector<std::string> errs(L);
-    if (L == 1) { rc[0] = fn(ctx->lanes[0]); return rc[0]; }
-    std::vector<std::thread> th;
-    for (int l = 0; l < L; ++l)
-        th.emplace_back([&, l] {
-            cudaSetDevice(ctx->device);
-            rc[l] = fn(ctx->lanes[l]);
-            if (rc[l]) errs[l] = xrvio_last_error();
-        });
-    for (auto &t : th) t.join();
-    for (int l = 0; l < L; ++l) if (rc[l]) { xrvio_set_error(errs[l]); return rc[l]; }
-    return XRVIO_OK;
+    if (L == 1 || ctx->workers.empty()) {
+        for (int l = 0; l < L; ++l) { const int rc = fn(ctx->lanes[l]); if (rc) return rc; }
+        return XRVIO_OK;
+    }
+    for (int l = 0; l < L; ++l) {
+        LaneWorker &w = *ctx->workers[l];
+        { std::lock_guard<std::mutex> lk(w.mu); w.job = fn; w.has_job = true; w.done = false; }
+        w.cv.notify_all();
+    }
+    int rc_all = XRVIO_OK;
+    for (int l = 0; l < L; ++l) {
+        LaneWorker &w = *ctx->workers[l];
+        std::unique_lock<std::mutex> lk(w.mu);
+        w.cv.wait(lk, [&] { return w.done; });
+        if (w.rc && rc_all == XRVIO_OK) { rc_all = w.rc; xrvio_set_error(w.err); }
+    }
+    return rc_all;
 }
 }  // namespace
 
@@ -827,12 +878,14 @@ int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **
         base += cnt;
     }
     ctx->tmp_idx.resize(L);
+    start_workers(ctx);
     *out = ctx;
     return XRVIO_OK;
 }
 
 int xrvio_destroy(xrvio_ctx *ctx) {
     if (!ctx) return XRVIO_OK;
+    stop_workers(ctx);
     for (Lane *l : ctx->lanes) lane_destroy(l);
     delete ctx;
     return XRVIO_OK;
