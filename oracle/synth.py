@@ -42,8 +42,12 @@ class Stream:
     ROOM = np.array([6.0, 5.0, 2.5])   # half extents of the box room [m]
     TEX = 1024                         # texels per wall side
 
-    def __init__(self, seed, width=640, height=480, cam_hz=20.0, imu_hz=200.0, static_prefix=0.0):
+    def __init__(self, seed, width=640, height=480, cam_hz=20.0, imu_hz=200.0, static_prefix=0.0, pause=None):
+        """pause = (t0, duration, ramp): the rig decelerates smoothly to a full stop at t0 + ramp, stands still for `duration`
+        seconds and accelerates again (a time warp of the same trajectory), to exercise the pure-rotation / no-translation
+        branches of the tracker (frame.cpp:132-134, sliding_window_tracker.cpp:370-465)."""
         self.seed = seed
+        self.pause = pause
         self.w, self.h = width, height
         self.cam_dt, self.imu_dt = 1.0 / cam_hz, 1.0 / imu_hz
         self.imu_per_cam = int(round(imu_hz / cam_hz))
@@ -73,20 +77,65 @@ class Stream:
         self._imu_cache = None
 
     # ------------------------------------------------------------------ trajectory
+    def _warp(self, t):
+        """tau(t), tau'(t), tau''(t) of the pause time warp (identity without a pause)."""
+        if self.pause is None:
+            return t, 1.0, 0.0
+        t0, dur, r = self.pause
+        # speed profile s(t) = tau'(t): 1 -> 0 over [t0, t0+r] (quintic smoothstep), 0 during the pause, 0 -> 1 over the next r
+        def sm(x):       # smoothstep with zero first and second derivative at both ends, its derivative and its integral
+            x = min(max(x, 0.0), 1.0)
+            return 6 * x ** 5 - 15 * x ** 4 + 10 * x ** 3, 30 * x ** 4 - 60 * x ** 3 + 30 * x ** 2, x ** 6 - 3 * x ** 5 + 2.5 * x ** 4
+        t = float(t)
+        if t <= t0:
+            return t, 1.0, 0.0
+        if t <= t0 + r:
+            x = (t - t0) / r
+            s, ds, I = sm(x)
+            return t0 + r * (x - I), 1.0 - s, -ds / r
+        tau_stop = t0 + r * 0.5                     # integral of (1 - smoothstep) over the ramp is r / 2
+        if t <= t0 + r + dur:
+            return tau_stop, 0.0, 0.0
+        t1 = t0 + r + dur
+        if t <= t1 + r:
+            x = (t - t1) / r
+            s, ds, I = sm(x)
+            return tau_stop + r * I, s, ds / r
+        return tau_stop + r * 0.5 + (t - t1 - r), 1.0, 0.0
+
+    def _p(self, tau):
+        tau = np.asarray(tau, dtype=np.float64)[..., None, None]
+        return np.sum(self.pa * np.sin(self.pf * tau + self.pp), axis=-1)
+
+    def _dp(self, tau):
+        tau = np.asarray(tau, dtype=np.float64)[..., None, None]
+        return np.sum(self.pa * self.pf * np.cos(self.pf * tau + self.pp), axis=-1)
+
+    def _ddp(self, tau):
+        tau = np.asarray(tau, dtype=np.float64)[..., None, None]
+        return np.sum(-self.pa * self.pf ** 2 * np.sin(self.pf * tau + self.pp), axis=-1)
+
     def position(self, t):
-        t = np.asarray(t, dtype=np.float64)[..., None, None]
-        return np.sum(self.pa * np.sin(self.pf * t + self.pp), axis=-1)
+        if self.pause is None:
+            return self._p(t)
+        return self._p(self._warp(t)[0])
 
     def velocity(self, t):
-        t = np.asarray(t, dtype=np.float64)[..., None, None]
-        return np.sum(self.pa * self.pf * np.cos(self.pf * t + self.pp), axis=-1)
+        if self.pause is None:
+            return self._dp(t)
+        tau, s, _ = self._warp(t)
+        return self._dp(tau) * s
 
     def acceleration(self, t):
-        t = np.asarray(t, dtype=np.float64)[..., None, None]
-        return np.sum(-self.pa * self.pf ** 2 * np.sin(self.pf * t + self.pp), axis=-1)
+        if self.pause is None:
+            return self._ddp(t)
+        tau, s, ds = self._warp(t)
+        return self._ddp(tau) * s * s + self._dp(tau) * ds
 
     def rotation(self, t):
         """R_wb(t) (3x3)."""
+        if self.pause is not None:
+            t = self._warp(t)[0]
         ang = np.sum(self.aa * np.sin(self.af * t + self.ap), axis=-1)  # roll, pitch, yaw offsets
         yaw = self.yaw0 + ang[2]
         cz, sz = np.cos(yaw), np.sin(yaw)

@@ -9,6 +9,7 @@ Outputs:
   preint.npz            preintegration jobs and oracle results
   stream3_traj.npz      oracle trajectory of synthetic stream seed 3 (first 66 frames)
   stream7_traj1200.npz  oracle trajectory of stream seed 7 over 60 s (BASELINE config 2; `make_golden.py minute`)
+  stream7_pause_traj.npz oracle trajectory of stream seed 7 with a 1.5 s full stop (pure-rotation branches)
   stream7_init_traj.npz oracle trajectory of stream seed 7 initialised by the reference initializer (no bootstrap states)
   stream7_traj140.npz   oracle trajectory of synthetic stream seed 7, 140 frames (steady-state marginalisation)
 """
@@ -137,6 +138,15 @@ def minute_trajectory():
     print('60 s trajectory rows', len(traj))
 
 
+def pause_trajectory():
+    """Stream 7 with a 1.5 s full stop: NO_TRANSLATION frames, pure-rotation sub-windows, subframe compaction."""
+    s = Stream(7, pause=(3.0, 1.5, 0.5))
+    sess = run_stream(s, 135)
+    traj = np.array([[t] + list(q) + list(p) for (t, q, p) in sess.outputs])
+    np.savez_compressed(os.path.join(HERE, 'stream7_pause_traj.npz'), traj=traj)
+    print('pause trajectory rows', len(traj))
+
+
 def initializer_trajectory():
     """Stream 7 WITHOUT ground-truth bootstrap: the oracle runs the reference initializer (oracle/initializer.py)."""
     s = Stream(7)
@@ -157,6 +167,7 @@ if __name__ == '__main__':
         minute_trajectory()
         sys.exit(0)
     long_trajectory()
+    pause_trajectory()
     initializer_trajectory()
     frontend_kat()
     preint()

@@ -82,6 +82,24 @@ def test_one_minute_stream_config2(xrvio, golden_dir):
     ctx.close()
 
 
+def test_pause_stream_no_translation_branches(xrvio, golden_dir):
+    """A stream that brakes to a full stop for 1.5 s and moves on: frames tagged NO_TRANSLATION (frame.cpp:132-134), the
+    pure-rotation sub-window solves and the compaction of long subframe runs (sliding_window_tracker.cpp:370-465), the lift
+    of a subframe to a keyframe when translation resumes (:152-175).  33 of the oracle's 81 sub-window solves on this stream
+    are of the pure-rotation kind and the subframe list is compacted five times."""
+    ref = np.load(os.path.join(golden_dir, 'stream7_pause_traj.npz'))['traj']
+    s = Stream(7, pause=(3.0, 1.5, 0.5))
+    ctx, outs = drive.run_streams_cuda([s], 135)
+    got = np.array([[t] + list(q) + list(p) for (t, q, p) in outs[0]])
+    assert got.shape == ref.shape and np.allclose(got[:, 0], ref[:, 0])
+    ate = _ate(ref[:, 5:8], got[:, 5:8])
+    raw = np.linalg.norm(got[:, 5:8] - ref[:, 5:8], axis=1).max()
+    assert ate <= 1e-3 and raw <= 2e-3, (ate, raw)
+    st = ctx.stats()
+    assert st['subwindow_solves'] >= 75 and st['window_solves'] >= 15
+    ctx.close()
+
+
 def test_batched_sessions_are_independent(xrvio):
     """Sessions advanced in one batch give exactly the result of the same stream run alone."""
     streams = [Stream(3), Stream(4), Stream(3)]
