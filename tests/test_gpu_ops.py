@@ -192,6 +192,30 @@ def test_solver_matches_oracle(xrvio, golden_problems, kind):
     assert np.abs(pb.inv_depth - ref_inv).max() < 1e-6
 
 
+def test_solver_rotation_prior_residuals(xrvio, golden_problems):
+    """K8b: rotation-prior residuals (rotation_factor.h:23-59) in the solve kernel.  The tracker only creates them for valid
+    but un-triangulated tracks of a pure-rotation sub-window (sliding_window_tracker.cpp:455-461), which the synthetic streams
+    never produce, so the problem is made here: a third of a sub-window problem's reprojection priors become rotation priors."""
+    import copy
+    from oracle import ceres_tr
+    pb = problem_io.problem_from_dict(golden_problems, 'subwindow_t/pre/')
+    idx = np.arange(len(pb.rpe_tgt))
+    to_rot = (idx % 3 == 0) & pb.rpe_prior
+    assert to_rot.sum() >= 10
+    pb.rot_tgt, pb.rot_ref = pb.rpe_tgt[to_rot].copy(), pb.rpe_ref[to_rot].copy()
+    pb.rot_z_tgt, pb.rot_z_ref = pb.rpe_z_tgt[to_rot].copy(), pb.rpe_z_ref[to_rot].copy()
+    keep = ~to_rot
+    for name in ('rpe_tgt', 'rpe_ref', 'rpe_lm', 'rpe_z_tgt', 'rpe_z_ref', 'rpe_prior'):
+        setattr(pb, name, getattr(pb, name)[keep].copy())
+    ref = copy.deepcopy(pb)
+    summ = ceres_tr.solve(ref)
+    out = bridge.solve_problem_cuda(pb)
+    assert int(out['iterations']) == len(summ.iterations)
+    assert abs(out['initial_cost'] - summ.initial_cost) <= 1e-9 * summ.initial_cost
+    assert abs(out['final_cost'] - summ.final_cost) <= 1e-6 * summ.final_cost
+    assert np.abs(pb.states[:, 0:4] - ref.states[:, 0:4]).max() < 1e-7 and np.abs(pb.states[:, 4:7] - ref.states[:, 4:7]).max() < 1e-6
+
+
 def test_solver_batch_of_mixed_problems(xrvio, golden_problems):
     pbs = [problem_io.problem_from_dict(golden_problems, k + '/pre/') for k in ('localize', 'window', 'subwindow_t', 'localize', 'init_ba')]
     pk = bridge.PackedProblems(pbs)

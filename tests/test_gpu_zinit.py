@@ -73,3 +73,31 @@ def test_per_frame_essential_ransac_changes_nothing(xrvio, golden_dir):
     assert np.linalg.norm(got[:, 5:8] - ref[:m, 5:8], axis=1).max() <= 2e-3
     assert ctx.get_init_info(0)['essential_rejected'] == 0
     ctx.close()
+
+
+def test_session_api_error_paths(xrvio):
+    """Errors are return codes with a message, never exceptions through the C boundary or silent acceptance."""
+    from xrslam_b200 import capi
+    p = capi.default_params(640, 480)
+    ctx = capi.Context(p, 2)
+    img = np.zeros((480, 640), np.uint8)
+    with pytest.raises(capi.XrvioError):
+        ctx.push_images([2], [img.ctypes.data], [0.0])                      # session index out of range
+    with pytest.raises(capi.XrvioError):
+        ctx.get_init_info(-1)
+    for k in range(4):                                                       # the image queue holds 4 frames per session
+        ctx.push_images([0], [img.ctypes.data], [0.05 * k])
+    with pytest.raises(capi.XrvioError) as e:
+        ctx.push_images([0], [img.ctypes.data], [0.25])
+    assert 'queue full' in str(e.value)
+    ctx.step()                                                               # no IMU yet: nothing is released, nothing breaks
+    assert ctx.get_state(0) == 0 and not ctx.get_pose(0)['valid']
+    ctx.close()
+    bad = capi.default_params(640, 480)
+    bad['sliding_window_size'] = 40                                          # beyond XRVIO_MAX_ACTIVE
+    with pytest.raises(capi.XrvioError):
+        capi.Context(bad, 1)
+    bad = capi.default_params(640, 480)
+    bad['distortion_model'] = 7
+    with pytest.raises(capi.XrvioError):
+        capi.Context(bad, 1)
