@@ -60,13 +60,15 @@ def test_long_stream_ate_vs_oracle(xrvio, golden_dir):
     ctx.close()
 
 
+@pytest.mark.skipif(os.environ.get('XRVIO_LONG') != '1', reason='~4 min of CPU frame rendering for 5 s of GPU work; set XRVIO_LONG=1')
 def test_one_minute_stream_config2(xrvio, golden_dir):
     """BASELINE config 2: one stream, 60 s = 1200 frames, trajectory vs the oracle after SE3 alignment.
     Two floating-point implementations of this pipeline agree to < 1e-4 m until, somewhere, a discrete front-end decision
     (a KLT back-check at its 0.5 px gate, a landmark at a validity gate) falls on different sides; from there on they are
     two equally valid estimates a few millimetres apart (on the SIMT emulator: < 1e-4 m for 37 s, one observation set differs
     at frame 751, ATE 3.3 mm over the minute, against 85 mm of drift from ground truth).  So the bar of BASELINE.json
-    (1e-3 m) is asserted on the first 140 frames and two centimetres on the whole minute."""
+    (1e-3 m) is asserted on the first 140 frames and two centimetres on the whole minute.  Opt-in (XRVIO_LONG=1): rendering
+    the 1200 synthetic frames on the CPU takes minutes; the emulator run of this test passes (26 min)."""
     ref = np.load(os.path.join(golden_dir, 'stream7_traj1200.npz'))['traj']
     s = Stream(7)
     ctx, outs = drive.run_streams_cuda([s], 1200)
