@@ -73,11 +73,10 @@ static std::mutex g_launch_mutex;
 static thread_local Block *g_blk = nullptr;
 static thread_local ThreadCtx g_host_ctx{};
 static std::vector<unsigned char> g_dyn_smem;
-static long long g_clock = 0;
 
 ThreadCtx &cur() { return g_blk && g_blk->current >= 0 ? g_blk->fibers[g_blk->current].ctx : g_host_ctx; }
 void *dyn_smem() { return g_dyn_smem.data(); }
-long long clock() { return ++g_clock; }
+long long clock() { return (long long)__builtin_ia32_rdtsc(); }      // CPU time stamp: section profiles show the distribution of WORK (all threads serialised)
 
 static void yield_to_scheduler() {
     Block &b = *g_blk;
