@@ -70,7 +70,7 @@ def rewrite(src):
 
 def build(verbose=False):
     os.makedirs(OUT, exist_ok=True)
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, 'cuemu.cpp'), os.path.join(HERE, 'include', 'cuda_runtime.h'),
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, 'cuemu.cpp'), os.path.join(HERE, 'prof.cpp'), os.path.join(HERE, 'include', 'cuda_runtime.h'),
                                                                  os.path.join(ROOT, 'include', 'xrvio.h'), __file__]
     if os.path.exists(LIB) and os.path.getmtime(LIB) > max(os.path.getmtime(s) for s in srcs):
         return LIB
@@ -87,7 +87,7 @@ def build(verbose=False):
         with open(os.path.join(ROOT, 'include', h)) as fh, open(os.path.join(OUT, 'include', h), 'w') as oh:
             oh.write(fh.read())
     objs, procs = [], []
-    flags = ['-O2', '-g0', '-std=c++17', '-fPIC', '-w', '-ffp-contract=off', '-I', os.path.join(HERE, 'include')]
+    flags = ['-O2', '-g' if os.environ.get('XRVIO_EMU_DEBUGINFO') == '1' else '-g0', '-std=c++17', '-fPIC', '-w', '-ffp-contract=off', '-I', os.path.join(HERE, 'include')]
     if SAN:
         flags = ['-O1', '-g', '-fsanitize=address', '-fno-omit-frame-pointer'] + flags[2:]
     for s in SOURCES:
@@ -98,6 +98,9 @@ def build(verbose=False):
         if verbose:
             print(' '.join(cmd))
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    pobj = os.path.join(OUT, 'prof.o')
+    procs.append(('prof.cpp', subprocess.Popen(['g++'] + flags + ['-c', os.path.join(HERE, 'prof.cpp'), '-o', pobj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    objs.append(pobj)
     obj = os.path.join(OUT, 'cuemu.o')
     procs.append(('cuemu.cpp', subprocess.Popen(['g++'] + flags + ['-c', os.path.join(HERE, 'cuemu.cpp'), '-o', obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     objs.append(obj)
@@ -109,7 +112,7 @@ def build(verbose=False):
             sys.stderr.write('g++ failed for %s:\n%s\n' % (s, o.decode()[:6000]))
     if bad:
         raise RuntimeError('emulated library build failed')
-    subprocess.check_call(['g++', '-shared', '-o', LIB] + objs + ['-lpthread'] + (['-fsanitize=address'] if SAN else []))
+    subprocess.check_call(['g++', '-shared', '-o', LIB] + objs + ['-lpthread', '-ldl'] + (['-fsanitize=address'] if SAN else []))
     return LIB
 
 

@@ -224,7 +224,9 @@ static void run_block(Block &b) {
     g_blk = nullptr;
 }
 
+bool replaying();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
+    if (replaying()) return;
     std::lock_guard<std::mutex> lock(g_launch_mutex);
     const int nthreads = (int)(block.x * block.y * block.z);
     if (nthreads <= 0 || grid.x == 0 || grid.y == 0 || grid.z == 0) return;
@@ -262,15 +264,38 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
 
 }  // namespace cuemu
 
+// ---- record / replay: CUEMU_RECORD=file stores every device->host copy; CUEMU_REPLAY=file skips the kernels and serves
+// the recorded bytes instead, so the deterministic host glue can be re-run (and profiled) at full speed ----
+#include <cstdio>
+namespace cuemu {
+static FILE *g_rec = nullptr, *g_rep = nullptr;
+static bool g_mode_init = false;
+static void mode_init() {
+    if (g_mode_init) return;
+    g_mode_init = true;
+    if (const char *p = std::getenv("CUEMU_RECORD")) g_rec = std::fopen(p, "wb");
+    if (const char *p = std::getenv("CUEMU_REPLAY")) g_rep = std::fopen(p, "rb");
+}
+bool replaying() { mode_init(); return g_rep != nullptr; }
+void d2h(void *dst, const void *src, size_t n) {
+    mode_init();
+    if (g_rep) { size_t m = 0; if (std::fread(&m, sizeof(m), 1, g_rep) != 1 || m != n || (n && std::fread(dst, 1, n, g_rep) != n)) { std::fprintf(stderr, "cuemu: replay out of sync (%zu vs %zu)\n", m, n); std::abort(); } return; }
+    if (n) std::memmove(dst, src, n);
+    if (g_rec) { std::fwrite(&n, sizeof(n), 1, g_rec); if (n) std::fwrite(dst, 1, n, g_rec); std::fflush(g_rec); }
+}
+void replay_rewind() { if (g_rep) std::rewind(g_rep); }
+}
+extern "C" void cuemu_replay_rewind() { cuemu::replay_rewind(); }
 // ---- runtime stubs ----
 struct cuemu_event { std::chrono::steady_clock::time_point t; };
 cudaError_t cudaMalloc(void **p, size_t n) { *p = std::aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMalloc(p, n); }
 cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
-cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind) { if (n) std::memmove(dst, src, n); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind k) { if (k == cudaMemcpyDeviceToHost) cuemu::d2h(dst, src, n); else if (n && !cuemu::replaying()) std::memmove(dst, src, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(dst, src, n, k); }
 cudaError_t cudaMemcpy2DAsync(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t) {
+    if (cuemu::replaying()) return cudaSuccess;
     for (size_t r = 0; r < height; ++r) std::memmove((char *)dst + r * dpitch, (const char *)src + r * spitch, width);
     return cudaSuccess;
 }
