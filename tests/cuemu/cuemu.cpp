@@ -94,9 +94,11 @@ static void fiber_main() {
     std::abort();                        // a finished fiber is never resumed
 }
 
+static long long g_stat_block_barriers = 0, g_stat_warp_barriers = 0;
 void sync_block() {
     Block &b = *g_blk;
     Fiber &f = b.fibers[b.current];
+    if (b.current == 0) g_stat_block_barriers++;
     f.wait = W_BLOCK; f.gen = b.block_gen;
     b.block_arrived++;
     yield_to_scheduler();
@@ -112,6 +114,7 @@ int sync_block_reduce(int pred, int mode) {
 static void warp_barrier(unsigned mask) {
     Block &b = *g_blk;
     Fiber &f = b.fibers[b.current];
+    if (b.current == 0) g_stat_warp_barriers++;
     WarpState &w = b.warps[f.ctx.warp];
     f.wait = W_WARP; f.warp_mask = mask; f.released = false;
     w.arrived |= 1u << f.ctx.lane;
@@ -260,6 +263,9 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
                 }
                 run_block(b);
             }
+    // CUEMU_STATS=1: barriers executed by thread 0 of the last block of every launch (a rough latency-chain length)
+    static const bool stats = std::getenv("CUEMU_STATS") != nullptr;
+    if (stats) std::fprintf(stderr, "cuemu launch grid %u block %u: block barriers %lld warp barriers %lld (cumulative, thread 0)\n", grid.x * grid.y * grid.z, block.x, g_stat_block_barriers, g_stat_warp_barriers);
 }
 
 }  // namespace cuemu
