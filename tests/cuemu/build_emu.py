@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'xrslam_b200', 'csrc')
 SAN = os.environ.get('XRVIO_EMU_SANITIZE') == '1'      # AddressSanitizer build: out-of-bounds accesses of the kernels and the host glue
-OUT = os.path.join(HERE, '_build_asan' if SAN else '_build')
+TSAN = os.environ.get('XRVIO_EMU_SANITIZE') == 'thread'   # ThreadSanitizer build: data races of the multi-threaded host glue (use with CUEMU_REPLAY: no fibers)
+OUT = os.path.join(HERE, '_build_asan' if SAN else ('_build_tsan' if TSAN else '_build'))
 LIB = os.path.join(OUT, 'libxrvio_emu.so')
 SOURCES = ['frontend.cu', 'backend_preint.cu', 'backend_solve.cu', 'backend_marg.cu', 'capi_ops.cu', 'capi_session.cu', 'xrslam_shim.cu']
 
@@ -90,6 +91,8 @@ def build(verbose=False):
     flags = ['-O2', '-g' if os.environ.get('XRVIO_EMU_DEBUGINFO') == '1' else '-g0', '-std=c++17', '-fPIC', '-w', '-ffp-contract=off', '-I', os.path.join(HERE, 'include')]
     if SAN:
         flags = ['-O1', '-g', '-fsanitize=address', '-fno-omit-frame-pointer'] + flags[2:]
+    if TSAN:
+        flags = ['-O1', '-g', '-fsanitize=thread', '-fno-omit-frame-pointer'] + flags[2:]
     for s in SOURCES:
         cpp = os.path.join(gen, s[:-3] + '.cpp')
         obj = os.path.join(OUT, s[:-3] + '.o')
@@ -112,7 +115,7 @@ def build(verbose=False):
             sys.stderr.write('g++ failed for %s:\n%s\n' % (s, o.decode()[:6000]))
     if bad:
         raise RuntimeError('emulated library build failed')
-    subprocess.check_call(['g++', '-shared', '-o', LIB] + objs + ['-lpthread', '-ldl'] + (['-fsanitize=address'] if SAN else []))
+    subprocess.check_call(['g++', '-shared', '-o', LIB] + objs + ['-lpthread', '-ldl'] + (['-fsanitize=address'] if SAN else []) + (['-fsanitize=thread'] if TSAN else []))
     return LIB
 
 

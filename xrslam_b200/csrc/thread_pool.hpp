@@ -1,4 +1,8 @@
 // Minimal persistent thread pool: parallel_for over independent sessions (host bookkeeping only).
+// Every parallel_for publishes a job object of its own (function, item count, next-item and pending counters);
+// workers pick the current job up under the mutex and touch nothing but that job, and parallel_for returns only
+// when every item is done AND every worker that picked the job up has let go of it, so a straggler can never
+// see the fields of the next job half-written (ThreadSanitizer-clean, tests/cuemu replay build).
 #pragma once
 #include <atomic>
 #include <condition_variable>
@@ -29,45 +33,60 @@ class ThreadPool {
     void parallel_for(int n, const std::function<void(int)> &fn) {
         if (n <= 0) return;
         if (workers_.empty() || n == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+        Job job;
+        job.fn = &fn; job.n = n; job.pending = n;
         {
             std::unique_lock<std::mutex> l(m_);
-            fn_ = &fn; n_ = n; next_.store(0); pending_ = n; generation_++;
+            job_ = &job;
+            generation_++;
         }
         cv_.notify_all();
-        run_some();
+        run_some(job);
         std::unique_lock<std::mutex> l(m_);
-        done_cv_.wait(l, [this] { return pending_ == 0; });
-        fn_ = nullptr;
+        job_ = nullptr;                                   // no new worker can pick it up from here on
+        done_cv_.wait(l, [&] { return job.pending == 0 && job.users == 0; });
     }
 
   private:
-    void run_some() {
+    struct Job {
+        const std::function<void(int)> *fn = nullptr;
+        int n = 0;
+        std::atomic<int> next{0};
+        int pending = 0;       // items not finished yet   (guarded by m_)
+        int users = 0;         // workers inside run_some  (guarded by m_)
+    };
+    void run_some(Job &job) {
         while (true) {
-            const int i = next_.fetch_add(1);
-            if (i >= n_) break;
-            (*fn_)(i);
+            const int i = job.next.fetch_add(1);
+            if (i >= job.n) break;
+            (*job.fn)(i);
             std::unique_lock<std::mutex> l(m_);
-            if (--pending_ == 0) done_cv_.notify_all();
+            if (--job.pending == 0) done_cv_.notify_all();
         }
     }
     void worker() {
         unsigned long long seen = 0;
         while (true) {
+            Job *job;
             {
                 std::unique_lock<std::mutex> l(m_);
-                cv_.wait(l, [&] { return stop_ || (generation_ != seen && fn_ != nullptr); });
+                cv_.wait(l, [&] { return stop_ || (generation_ != seen && job_ != nullptr); });
                 if (stop_) return;
                 seen = generation_;
+                job = job_;
+                job->users++;
             }
-            run_some();
+            run_some(*job);
+            {
+                std::unique_lock<std::mutex> l(m_);
+                if (--job->users == 0) done_cv_.notify_all();
+            }
         }
     }
     std::vector<std::thread> workers_;
     std::mutex m_;
     std::condition_variable cv_, done_cv_;
-    const std::function<void(int)> *fn_ = nullptr;
-    int n_ = 0, pending_ = 0;
-    std::atomic<int> next_{0};
+    Job *job_ = nullptr;
     unsigned long long generation_ = 0;
     bool stop_ = false;
 };
