@@ -379,11 +379,13 @@ struct Builder {
     bool with_motion = true;       // false: Solver::add_frame_states(frame, false) -- pose blocks only (initializer.cpp:342)
     void add_active(Frame *f) { if (f->tmp == -1) { f->tmp = -2; active.push_back(f); } }
     void touch(Frame *f) { if (f->tmp == -1) { f->tmp = -3; consts.push_back(f); } }
-    void add_rpe(Frame *f, Track *tr, bool prior) {
+    // kp: index of the observation among f's keypoints when the caller already has it (it usually iterates over them)
+    void add_rpe(Frame *f, Track *tr, bool prior, int kp = -1) {
         Frame *ref = tr->refs.front().first;
         touch(f); touch(ref);
         if (tr->tmp == -1) { tr->tmp = prior ? -3 : -2; (prior ? const_lm : free_lm).push_back(tr); }
-        rpe.push_back({f, ref, tr, prior, f->bearings[tr->get_keypoint_index(f)], ref->bearings[tr->refs.front().second]});
+        if (kp < 0) kp = tr->get_keypoint_index(f);
+        rpe.push_back({f, ref, tr, prior, f->bearings[kp], ref->bearings[tr->refs.front().second]});
     }
     void add_rot(Frame *f, Track *tr) {
         Frame *ref = tr->refs.front().first;

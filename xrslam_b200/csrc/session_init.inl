@@ -170,7 +170,7 @@ int initialize_session(Lane *c, Session &s, long long frame_id) {
         for (size_t k = 0; k < fb->keypoint_num(); ++k) {
             Track *tr = fb->tracks[k];
             if (!tr || tr->find(fi) < 0) continue;
-            if (tr->valid && tr->triangulated) b.add_rpe(fb, tr, true);
+            if (tr->valid && tr->triangulated) b.add_rpe(fb, tr, true, (int)k);
         }
         if (b.rpe.empty()) { fb->tmp = -1; continue; }
         xvbe::SolveOut so;
@@ -205,7 +205,7 @@ int initialize_session(Lane *c, Session &s, long long frame_id) {
                 Track *t = f->tracks[j];
                 if (!t || !(t->valid && t->triangulated)) continue;
                 if (f.get() == t->first_frame()) continue;
-                b.add_rpe(f.get(), t, false);
+                b.add_rpe(f.get(), t, false, (int)j);
             }
         if (b.rpe.empty()) { for (auto &f : m->frames) f->tmp = -1; info.last_fail = INIT_FAIL_SFM_BA; return XRVIO_OK; }
         xvbe::SolveOut so;

@@ -510,7 +510,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
                     Track *t = f->tracks[j];
                     if (!t || !(t->valid && t->triangulated)) continue;
                     if (f.get() == t->first_frame()) continue;
-                    b.add_rpe(f.get(), t, false);
+                    b.add_rpe(f.get(), t, false, (int)j);
                 }
             for (size_t j = 1; j < m->frame_num(); ++j) {
                 Frame *fi = m->frames[j - 1].get(), *fj = m->frames[j].get();
@@ -527,7 +527,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
             b.add_active(fj);
             if (s.pre_jobs[0] >= 0) b.add_pre(fi, fj, &fj->pre, true);
             for (size_t k = 0; k < fj->keypoint_num(); ++k)
-                if (Track *t = fj->tracks[k]) if (t->valid && t->triangulated && t->is_static) b.add_rpe(fj, t, true);
+                if (Track *t = fj->tracks[k]) if (t->valid && t->triangulated && t->is_static) b.add_rpe(fj, t, true, (int)k);
             return pack_problem(c, s, b, c->prm.solver_iteration_limit);
         }
         return 0; }); if (rc) return rc; }
@@ -645,7 +645,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
                     if (!t || !(t->valid && t->triangulated && t->is_static)) continue;
                     Frame *ff = t->first_frame();
                     if (!ff->keyframe || f.get() == ff) continue;
-                    b.add_rpe(f.get(), t, false);
+                    b.add_rpe(f.get(), t, false, (int)j);
                 }
             for (size_t j = 1; j < m->frame_num(); ++j) {
                 if (s.pre_jobs[j - 1] < 0) continue;
@@ -669,7 +669,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
             if (!rbranch)
                 for (size_t k = 0; k < sf->keypoint_num(); ++k)
                     if (Track *t = sf->tracks[k]) if (t->valid && t->triangulated && t->is_static) {
-                        if (t->first_frame()->keyframe) b.add_rpe(sf, t, true);
+                        if (t->first_frame()->keyframe) b.add_rpe(sf, t, true, (int)k);
                         // else branch (:451-454) is unreachable with the default configuration
                     }
         }
@@ -677,7 +677,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
             Frame *lastsf = frame->subframes.back().get();
             for (size_t k = 0; k < lastsf->keypoint_num(); ++k)
                 if (Track *t = lastsf->tracks[k]) if (t->valid) {
-                    if (t->triangulated) { if (t->is_static) b.add_rpe(lastsf, t, true); }
+                    if (t->triangulated) { if (t->is_static) b.add_rpe(lastsf, t, true, (int)k); }
                     else b.add_rot(lastsf, t);
                 }
         }
