@@ -169,6 +169,7 @@ struct Session {
     int be_mode = 0;                              // 0 none, 1 bootstrap, 2 track
     bool is_keyframe = false;
     Frame *new_i = nullptr, *new_j = nullptr;
+    bool mirror_prepended = false;                // mirror_frame merged the IMU samples of skipped frames into new_j
     int prob1 = -1, prob2 = -1, marg_job = -1;
     std::vector<int> sort_cnt;
     std::vector<Frame *> prob_frames;             // frame order of the last built problem

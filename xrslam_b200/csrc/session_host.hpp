@@ -39,6 +39,8 @@ struct Frame {
     State16 st;
     std::vector<Imu> imu;                  // preintegration.data
     std::vector<double> pre;               // last result of preintegration.integrate (XRVIO_PRE_BLOCK doubles)
+    bool pre_full = false;                 // pre holds Jacobians + covariance (flags 3), computed with the bias pre_bias
+    double pre_bias[6] = {0, 0, 0, 0, 0, 0};
     std::vector<double> kf_pre;            // keyframe_preintegration result
     std::vector<Imu> kf_imu;
     std::vector<V3> bearings;
@@ -56,6 +58,7 @@ struct Frame {
         f->id = id; f->t = t; f->st = st; f->imu = imu; f->pre = pre; f->bearings = bearings;
         f->tracks.assign(bearings.size(), nullptr);
         f->keyframe = keyframe; f->no_translation = no_translation; f->fix_pose = fix_pose; f->fix_motion = fix_motion;
+        f->pre_full = pre_full; std::memcpy(f->pre_bias, pre_bias, sizeof(pre_bias));
         f->pyr_slot = pyr_slot;
         return f;
     }

@@ -76,7 +76,12 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
                 }
             }
             if (!f->imu.empty()) {
-                s.pre_job = add_preint_job(s, f->imu, f->t, s.last->st, 0);
+                // a tracking session needs the same preintegration again in the back end, with Jacobians and covariance
+                // (mirror_frame, sliding_window_tracker.cpp:76): compute it once, in full, and let phase E reuse the block
+                const int fl = s.sw_map ? 3 : 0;
+                s.pre_job = add_preint_job(s, f->imu, f->t, s.last->st, fl);
+                f->pre_full = fl == 3;
+                std::memcpy(f->pre_bias, &s.last->st.d[10], sizeof(f->pre_bias));
             }
         }
         return 0; }); if (rc) return rc; }
@@ -376,6 +381,7 @@ bool mirror_frame(Lane *c, Session &s, long long frame_id) {
     if (ii < 0 || jj < 0) return false;
     Frame *old_i = ft.frames[ii].get(), *old_j = ft.frames[jj].get();
     std::unique_ptr<Frame> curr = old_j->clone();
+    s.mirror_prepended = jj - 1 > ii;
     for (long index = jj - 1; index > ii; --index) {
         const auto &od = ft.frames[index]->imu;
         curr->imu.insert(curr->imu.begin(), od.begin(), od.end());
@@ -468,7 +474,10 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         } else {
             s.be_mode = 2;
             if (!mirror_frame(c, s, frame_id)) { s.be_mode = 3; return 0; }
-            s.pre_jobs.push_back(s.new_j->imu.empty() ? -1 : add_preint_job(s, s.new_j->imu, s.new_j->t, s.new_i->st, 3));
+            // -2: the front end already integrated exactly these samples with exactly this bias (the clone carries the block)
+            const bool reuse = s.new_j->pre_full && !s.mirror_prepended && s.new_j->pre.size() == (size_t)XRVIO_PRE_BLOCK &&
+                               std::memcmp(s.new_j->pre_bias, &s.new_i->st.d[10], sizeof(s.new_j->pre_bias)) == 0;
+            s.pre_jobs.push_back(s.new_j->imu.empty() ? -1 : (reuse ? -2 : add_preint_job(s, s.new_j->imu, s.new_j->t, s.new_i->st, 3)));
         }
         return 0; }); if (rc) return rc; }
     { int rc = merge_preint_jobs(c, act); if (rc) return rc; }
@@ -522,10 +531,11 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         } else if (s.be_mode == 2) {
             // mirror_frame tail (:76-79) + localize_newframe (:119-143)
             Frame *fj = s.new_j, *fi = s.new_i;
-            if (s.pre_jobs[0] >= 0) { fetch_pre(c, s.pre_base + s.pre_jobs[0], fj->pre); pre_predict(fj->pre, fi->st, fj->st); }
+            if (s.pre_jobs[0] >= 0) fetch_pre(c, s.pre_base + s.pre_jobs[0], fj->pre);
+            if (s.pre_jobs[0] != -1) pre_predict(fj->pre, fi->st, fj->st);
             Builder b{c, &s};
             b.add_active(fj);
-            if (s.pre_jobs[0] >= 0) b.add_pre(fi, fj, &fj->pre, true);
+            if (s.pre_jobs[0] != -1) b.add_pre(fi, fj, &fj->pre, true);
             for (size_t k = 0; k < fj->keypoint_num(); ++k)
                 if (Track *t = fj->tracks[k]) if (t->valid && t->triangulated && t->is_static) b.add_rpe(fj, t, true, (int)k);
             return pack_problem(c, s, b, c->prm.solver_iteration_limit);
