@@ -67,10 +67,12 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
     if (tid == 0) s.flag = 1;
     __syncthreads();
     double *col = s.du, *idiag = s.dw;
-    // Register-resident Cholesky: the lower triangle is cut into 6x6 tiles, one tile per thread (n <= 180 ->
-    // <= 465 tiles), held in registers for the whole factorisation.  Per column: the owners of that column scale it
-    // and publish it in shared memory (barrier), every thread applies the rank-1 update to its tile from 12
-    // shared-memory reads (barrier).  Shared memory only carries the pivot column, not the matrix.
+    // Register-resident, panel-blocked Cholesky: the lower triangle is cut into 6x6 tiles, one tile per thread (n <= 180 ->
+    // <= 465 tiles), held in registers for the whole factorisation.  Per PANEL of six columns (three barriers instead of
+    // twelve): (1) the owner of the diagonal tile factorises it in registers and publishes its columns, (2) the owners of
+    // the tiles below it scale their six columns against that tile and publish them, (3) every tile to the right applies
+    // the six rank-1 updates from shared memory.  Every element sees the same operations in the same order as in a
+    // column-by-column right-looking factorisation, so the factor is bit-identical to it.
     {
         constexpr int TB = 6;
         const int nt = (n + TB - 1) / TB;
@@ -89,52 +91,83 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
                 const int gi = ti * TB + li, gk = tk * TB + lk;
                 a[li][lk] = (ti >= 0 && gi < n && gk <= gi) ? s.H[hidx(gi, gk)] : 0.0;
             }
-        if (tid == 0) s.sc[14] = a[0][0];
+        double *colp = s.colp;                       // colp[c * kNP + row]: column (panel * 6 + c), scaled
         __syncthreads();
-        for (int j = 0; j < n; ++j) {
-            const double d = s.sc[14];
-            if (!(d > 0.0) || !isfinite(d)) {
-                if (tid == 0) s.flag = 0;
-                break;                               // uniform: every thread reads the same d
-            }
-            const double inv = rsqrt(d);
-            const int jt = j / TB, lj = j - jt * TB;
-            if (tk == jt) {
+        for (int p = 0; p < nt; ++p) {
+            const int j0 = p * TB;
+            // ---- (1) diagonal tile ----
+            if (ti == p && tk == p) {
 #pragma unroll
-                for (int lk = 0; lk < TB; ++lk) {
-                    if (lk != lj) continue;
+                for (int c = 0; c < TB; ++c) {
+                    const int j = j0 + c;
+                    if (j < n && s.flag) {
+                        const double d = a[c][c];
+                        if (!(d > 0.0) || !isfinite(d)) s.flag = 0;
+                        else {
+                            const double inv = rsqrt(d);
+                            idiag[j] = inv;
 #pragma unroll
-                    for (int li = 0; li < TB; ++li) {
-                        const int gi = ti * TB + li;
-                        if (gi >= j && gi < n) {
-                            const double v = (gi == j) ? d * inv : a[li][lk] * inv;
-                            a[li][lk] = v;
-                            col[gi] = v;
-                            if (gi == j) idiag[j] = inv;
+                            for (int li = 0; li < TB; ++li) {
+                                if (li < c) continue;
+                                const int gi = j0 + li;
+                                double v = 0.0;
+                                if (gi < n) { v = (li == c) ? d * inv : a[li][c] * inv; a[li][c] = v; }
+                                colp[c * kNP + gi] = v;
+                            }
+#pragma unroll
+                            for (int li = 0; li < TB; ++li)
+#pragma unroll
+                                for (int lk = 0; lk < TB; ++lk)
+                                    if (li > c && lk > c && lk <= li) a[li][lk] -= a[li][c] * a[lk][c];
                         }
                     }
                 }
             }
             __syncthreads();
-            if (tk >= jt) {                          // tiles entirely left of column j are final
-                double ci[TB], ck[TB];
+            if (!s.flag) break;                      // uniform: written before the barrier by one thread
+            // ---- (2) tiles below the diagonal tile ----
+            if (tk == p && ti > p) {
 #pragma unroll
-                for (int l = 0; l < TB; ++l) {
-                    const int gi = ti * TB + l, gk = tk * TB + l;
-                    ci[l] = (gi > j && gi < n) ? col[gi] : 0.0;
-                    ck[l] = (gk > j && gk < n) ? col[gk] : 0.0;
-                }
+                for (int c = 0; c < TB; ++c) {
+                    const int j = j0 + c;
+                    if (j >= n) continue;
+                    const double inv = idiag[j];
 #pragma unroll
-                for (int li = 0; li < TB; ++li)
+                    for (int li = 0; li < TB; ++li) {
+                        const int gi = ti * TB + li;
+                        double v = 0.0;
+                        if (gi < n) { v = a[li][c] * inv; a[li][c] = v; }
+                        colp[c * kNP + gi] = v;
+                    }
 #pragma unroll
-                    for (int lk = 0; lk < TB; ++lk) a[li][lk] -= ci[li] * ck[lk];
-                const int jn = j + 1, jnt = jn / TB, ljn = jn - jnt * TB;
-                if (ti == jnt && tk == jnt) {
+                    for (int lk = 0; lk < TB; ++lk) {
+                        if (lk <= c) continue;
+                        const double ck = (j0 + lk < n) ? colp[c * kNP + j0 + lk] : 0.0;      // L_pp(lk, c), published in (1)
 #pragma unroll
-                    for (int l = 0; l < TB; ++l) if (l == ljn) s.sc[14] = a[l][l];
+                        for (int li = 0; li < TB; ++li) a[li][lk] -= a[li][c] * ck;
+                    }
                 }
             }
             __syncthreads();
+            // ---- (3) tiles to the right of the panel ----
+            if (tk > p) {
+#pragma unroll
+                for (int c = 0; c < TB; ++c) {
+                    if (j0 + c >= n) continue;
+                    double ci[TB], ck[TB];
+#pragma unroll
+                    for (int l = 0; l < TB; ++l) {
+                        const int gi = ti * TB + l, gk = tk * TB + l;
+                        ci[l] = gi < n ? colp[c * kNP + gi] : 0.0;
+                        ck[l] = gk < n ? colp[c * kNP + gk] : 0.0;
+                    }
+#pragma unroll
+                    for (int li = 0; li < TB; ++li)
+#pragma unroll
+                        for (int lk = 0; lk < TB; ++lk) a[li][lk] -= ci[li] * ck[lk];
+                }
+            }
+            __syncthreads();                         // colp is rewritten by the next panel
         }
         __syncthreads();
         if (s.flag) {
@@ -150,21 +183,46 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
     __syncthreads();
     if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[25], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
     if (!s.flag) { if (threadIdx.x == 0 && P.d.marg_k > 0) atomicAdd(&g_kprof[28], 1ull); return false; }
-    // forward / backward substitution (L z = b, L^T y = z), one barrier per column
+    // forward / backward substitution (L z = b, L^T y = z) in panels of six columns, two barriers per panel: thread 0
+    // solves the 6x6 triangle of the panel and publishes the six values, then every row outside the panel applies them in
+    // column order -- the same operations in the same order as a column-by-column substitution.
     // forward: work vector s.y (starts as b_red), result z in s.bred; backward: work vector s.bred, result in s.y.
-    // Each column reads one finished entry and writes a different array, so one barrier per column suffices.
     for (int c = tid; c < n; c += ST) s.y[c] = s.bred[c];
     __syncthreads();
-    for (int j = 0; j < n; ++j) {
-        const double zj = s.y[j] * idiag[j];
-        for (int i = j + 1 + tid; i < n; i += ST) s.y[i] -= s.H[hidx(i, j)] * zj;
-        if (tid == 0) s.bred[j] = zj;
+    for (int j0 = 0; j0 < n; j0 += 6) {
+        const int j1 = min(j0 + 6, n);
+        if (tid == 0) {
+            for (int j = j0; j < j1; ++j) {
+                const double zj = s.y[j] * idiag[j];
+                s.sc[j - j0] = zj;
+                s.bred[j] = zj;
+                for (int i = j + 1; i < j1; ++i) s.y[i] -= s.H[hidx(i, j)] * zj;
+            }
+        }
+        __syncthreads();
+        for (int i = j1 + tid; i < n; i += ST) {
+            double yi = s.y[i];
+            for (int j = j0; j < j1; ++j) yi -= s.H[hidx(i, j)] * s.sc[j - j0];
+            s.y[i] = yi;
+        }
         __syncthreads();
     }
-    for (int j = n - 1; j >= 0; --j) {
-        const double yj = s.bred[j] * idiag[j];
-        for (int i = tid; i < j; i += ST) s.bred[i] -= s.H[hidx(j, i)] * yj;
-        if (tid == 0) s.y[j] = yj;
+    for (int j1 = n; j1 > 0; j1 -= 6) {
+        const int j0 = max(j1 - 6, 0);
+        if (tid == 0) {
+            for (int j = j1 - 1; j >= j0; --j) {
+                const double yj = s.bred[j] * idiag[j];
+                s.sc[j - j0] = yj;
+                s.y[j] = yj;
+                for (int i = j0; i < j; ++i) s.bred[i] -= s.H[hidx(j, i)] * yj;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < j0; i += ST) {
+            double bi = s.bred[i];
+            for (int j = j1 - 1; j >= j0; --j) bi -= s.H[hidx(j, i)] * s.sc[j - j0];
+            s.bred[i] = bi;
+        }
         __syncthreads();
     }
     if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[26], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }

@@ -39,6 +39,7 @@ struct Smem {
     double us[kMaxFrames * 16];            // user memory (last state written back)
     double g[kNP], scale[kNP], D[kNP], y[kNP], bred[kNP];
     double du[kNP], dw[kNP];               // unscaled steepest-descent / Gauss-Newton directions of the current linearisation
+    double colp[6 * kNP];                  // the six scaled columns of the current Cholesky panel (gauss_newton)
     double red[NW];
     double jrinv[kMaxActive * 9];
     unsigned char col_free[kNP];
