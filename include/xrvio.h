@@ -43,7 +43,8 @@ extern "C" {
 #define XRVIO_MAX_CORNERS 256     /* slots per image in xrvio_op_gftt output   */
 #define XRVIO_MAX_PTS 512         /* keypoint slots per image (klt / poisson)  */
 #define XRVIO_PRE_BLOCK 512       /* doubles per preintegration result         */
-#define XRVIO_MAX_ACTIVE 12       /* free frames per solve                     */
+#define XRVIO_MAX_ACTIVE 12       /* free frames per solve (sliding window)    */
+#define XRVIO_MAX_ACTIVE_LARGE 32 /* free frames per solve, large-window kernel */
 #define XRVIO_MAX_FRAMES 96       /* frames referenced by one solve            */
 #define XRVIO_MAX_ITER 64
 

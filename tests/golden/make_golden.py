@@ -12,6 +12,7 @@ Outputs:
   stream7_pause_traj.npz oracle trajectory of stream seed 7 with a 1.5 s full stop (pure-rotation branches)
   stream7_init_traj.npz oracle trajectory of stream seed 7 initialised by the reference initializer (no bootstrap states)
   stream7_traj140.npz   oracle trajectory of synthetic stream seed 7, 140 frames (steady-state marginalisation)
+  stress_config5.npz    oracle cost trace / final states of BASELINE config 5 (30 keyframes x 2000 landmarks; `make_golden.py stress`)
 """
 import os
 import shutil
@@ -158,8 +159,23 @@ def initializer_trajectory():
     print('initializer trajectory rows', len(traj), tr['matches'], tr['candidate'], tr['landmarks'], tr['scale'])
 
 
+def stress_config5():
+    """BASELINE config 5: oracle cost trace and final states of the 30-keyframe x 2000-landmark solve (oracle/stress.py)."""
+    from oracle import stress, ceres_tr
+    seed, n_kf, n_lm = 5, 30, 2000
+    pb = stress.make_stress_problem(seed, n_kf, n_lm)
+    summ = ceres_tr.solve(pb)
+    np.savez_compressed(os.path.join(HERE, 'stress_config5.npz'), seed=seed, n_kf=n_kf, n_lm=n_lm,
+                        trace=np.array([it['cost'] for it in summ.iterations]), successful=np.array([it['successful'] for it in summ.iterations]),
+                        states=pb.states, inv_depth_sum=pb.inv_depth.sum(), final_cost=summ.final_cost)
+    print('stress config 5: cost %.6f -> %.6f in %d iterations' % (summ.initial_cost, summ.final_cost, len(summ.iterations) - 1))
+
+
 if __name__ == '__main__':
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'stress':
+        stress_config5()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'init':
         initializer_trajectory()
         sys.exit(0)
@@ -172,3 +188,4 @@ if __name__ == '__main__':
     frontend_kat()
     preint()
     backend_problems()
+    stress_config5()

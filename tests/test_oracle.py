@@ -123,6 +123,35 @@ def test_solver_golden_and_properties(golden_dir):
         assert all(b <= a + 1e-12 for a, b in zip(costs, costs[1:]))
 
 
+def test_stress_problem_oracle_golden_and_schur_identity(golden_dir):
+    """BASELINE config 5 (30 keyframes x 2000 landmarks x 29 targets, 29 IMU edges, dense 435 x 435 prior): the generator is
+    deterministic and the oracle reproduces the committed cost trace; at reduced size, the landmark Schur complement the CUDA
+    kernel forms (marginalization_factor.h:383-398) solves the same system as the oracle's full Cholesky."""
+    from oracle import stress
+    g = np.load(os.path.join(golden_dir, 'stress_config5.npz'))
+    pb = stress.make_stress_problem(int(g['seed']), int(g['n_kf']), int(g['n_lm']))
+    assert len(pb.rpe_tgt) == 58000 and len(pb.pre) == 29 and pb.marg.sqrt_inv_cov.shape == (435, 435) and pb.max_iterations == 10
+    summ = ceres_tr.solve(pb)
+    trace = np.array([it['cost'] for it in summ.iterations])
+    assert np.allclose(trace, g['trace'], rtol=1e-9, atol=0)
+    assert np.array_equal(np.array([it['successful'] for it in summ.iterations]), g['successful'])
+    assert np.abs(pb.states - g['states']).max() < 1e-8
+    # Schur identity on a small instance
+    small = stress.make_stress_problem(3, 14, 60)
+    lay = ceres_tr._Layout(small)
+    _, r, J, gvec = ceres_tr.evaluate(small, lay, small.states, small.inv_depth, True)
+    H = (J.T @ J).toarray() + 1e-6 * np.eye(lay.n_cols)
+    n = lay.n_frame_cols
+    Hpp, Hpl, hll = H[:n, :n], H[:n, n:], np.diag(H[n:, n:])
+    assert np.abs(H[n:, n:] - np.diag(hll)).max() == 0.0          # inverse depths are independent scalar blocks
+    S = Hpp - (Hpl / hll) @ Hpl.T
+    b = gvec[:n] - Hpl @ (gvec[n:] / hll)
+    yp = np.linalg.solve(S, b)
+    yl = (gvec[n:] - Hpl.T @ yp) / hll
+    full = np.linalg.solve(H, gvec)
+    assert np.allclose(np.concatenate([yp, yl]), full, rtol=1e-6, atol=1e-9)
+
+
 def test_marginalization_properties(golden_dir):
     g = np.load(os.path.join(golden_dir, 'backend_problems.npz'))
     d = {k[len('marg/pre/'):]: g[k] for k in g.files if k.startswith('marg/pre/')}

@@ -50,6 +50,9 @@ struct SolveBatch {
 };
 size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k, int n_rpe);
 void solve(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st);
+// large windows (n_active <= XRVIO_MAX_ACTIVE_LARGE): H in global scratch, FP64 tensor-pipe Schur complement
+size_t solve_large_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k, int n_rpe);
+void solve_large(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st);
 // A0 = S^T S for a prior (helper used when a prior arrives without it)
 void gram(const double *S, double *A0, int n, int n_priors, size_t stride, cudaStream_t st);
 

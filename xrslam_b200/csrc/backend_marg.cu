@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
     double *Gs = Gm;
     if ((size_t)rnk * n1 <= (size_t)HPACK) {            // factor fits in the (now free) shared H area
         for (int e = tid; e < rnk * n1; e += ST) s.H[e] = Gm[e];
-        Gs = s.H;
+        Gs = s.H.a;
         __syncthreads();
     }
     const int m = rnk + (rnk & 1);

@@ -1,5 +1,6 @@
 // K7-K11 driver: the Ceres-1.14-style trust-region loop around solve_core.cuh (see there).
 #include "solve_core.cuh"
+#include "solve_large.cuh"
 
 namespace xvbe {
 using namespace xv;
@@ -12,7 +13,7 @@ size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k,
 
 
 // q <- normalize(q * exp(d)) for free pose blocks, additive elsewhere (quaternion_parameterization.h:11-17)
-__device__ void make_candidate(const Prob &P, Smem &s, double c1, double c2) {
+template <class SM> __device__ void make_candidate(const Prob &P, SM &s, double c1, double c2) {
     const int tid = threadIdx.x;
     // delta_j = c1 * du_j + c2 * dw_j with du = -gs / D^2 * scale, dw = -y * scale (prepared per linearisation)
     for (int f = tid; f < P.d.n_frames; f += ST) {
@@ -34,7 +35,7 @@ __device__ void make_candidate(const Prob &P, Smem &s, double c1, double c2) {
     __syncthreads();
 }
 
-__device__ double ambient_sq(const Prob &P, Smem &s, const double *A, const double *B, const double *ia, const double *ib) {
+template <class SM> __device__ double ambient_sq(const Prob &P, SM &s, const double *A, const double *B, const double *ia, const double *ib) {
     // squared norm of (A - B) over the free blocks (B == nullptr: norm of A)
     double a = 0.0;
     for (int f = threadIdx.x; f < P.d.n_active; f += ST) {
@@ -49,7 +50,7 @@ __device__ double ambient_sq(const Prob &P, Smem &s, const double *A, const doub
 
 // Gauss-Newton step: (Hs + mu D^2) y = gs via Schur complement on the landmark block + Cholesky.
 // Returns false when the factorisation fails (LINEAR_SOLVER_FAILURE).  H is consumed.
-__device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
+template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.NPc, M = P.M, na = P.d.n_active;
     for (int c = tid; c < n; c += ST)
@@ -58,7 +59,8 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
     for (int c = tid; c < n; c += ST) s.bred[c] = s.g[c];
     __syncthreads();
     if (threadIdx.x == 0 && P.d.marg_k > 0) { s.sc[15] = (double)clock64(); atomicAdd(&g_kprof[27], 1ull); }
-    schur_landmarks(P, s, s.bred);
+    if constexpr (SM::kSharedH) schur_landmarks(P, s, s.bred);
+    else schur_landmarks_mma(P, s, s.bred);
     __syncthreads();
     if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[24], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
     // in-place right-looking Cholesky on the packed lower triangle.  The scaled pivot column is mirrored
@@ -73,7 +75,8 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
     // the tiles below it scale their six columns against that tile and publish them, (3) every tile to the right applies
     // the six rank-1 updates from shared memory.  Every element sees the same operations in the same order as in a
     // column-by-column right-looking factorisation, so the factor is bit-identical to it.
-    {
+    if constexpr (!SM::kSharedH) cholesky_global(s, n, col, idiag);
+    else {
         constexpr int TB = 6;
         const int nt = (n + TB - 1) / TB;
         int ti = -1, tk = -1;
@@ -91,7 +94,7 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
                 const int gi = ti * TB + li, gk = tk * TB + lk;
                 a[li][lk] = (ti >= 0 && gi < n && gk <= gi) ? s.H[hidx(gi, gk)] : 0.0;
             }
-        double *colp = s.colp;                       // colp[c * kNP + row]: column (panel * 6 + c), scaled
+        double *colp = s.colp;                       // colp[c * SM::NPv + row]: column (panel * 6 + c), scaled
         __syncthreads();
         for (int p = 0; p < nt; ++p) {
             const int j0 = p * TB;
@@ -112,7 +115,7 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
                                 const int gi = j0 + li;
                                 double v = 0.0;
                                 if (gi < n) { v = (li == c) ? d * inv : a[li][c] * inv; a[li][c] = v; }
-                                colp[c * kNP + gi] = v;
+                                colp[c * SM::NPv + gi] = v;
                             }
 #pragma unroll
                             for (int li = 0; li < TB; ++li)
@@ -137,12 +140,12 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
                         const int gi = ti * TB + li;
                         double v = 0.0;
                         if (gi < n) { v = a[li][c] * inv; a[li][c] = v; }
-                        colp[c * kNP + gi] = v;
+                        colp[c * SM::NPv + gi] = v;
                     }
 #pragma unroll
                     for (int lk = 0; lk < TB; ++lk) {
                         if (lk <= c) continue;
-                        const double ck = (j0 + lk < n) ? colp[c * kNP + j0 + lk] : 0.0;      // L_pp(lk, c), published in (1)
+                        const double ck = (j0 + lk < n) ? colp[c * SM::NPv + j0 + lk] : 0.0;      // L_pp(lk, c), published in (1)
 #pragma unroll
                         for (int li = 0; li < TB; ++li) a[li][lk] -= a[li][c] * ck;
                     }
@@ -158,8 +161,8 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
 #pragma unroll
                     for (int l = 0; l < TB; ++l) {
                         const int gi = ti * TB + l, gk = tk * TB + l;
-                        ci[l] = gi < n ? colp[c * kNP + gi] : 0.0;
-                        ck[l] = gk < n ? colp[c * kNP + gk] : 0.0;
+                        ci[l] = gi < n ? colp[c * SM::NPv + gi] : 0.0;
+                        ck[l] = gk < n ? colp[c * SM::NPv + gk] : 0.0;
                     }
 #pragma unroll
                     for (int li = 0; li < TB; ++li)
@@ -243,10 +246,7 @@ __device__ bool gauss_newton(const Prob &P, Smem &s, double mu) {
     return allok != 0;
 }
 
-__global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigParams *__restrict__ rig_g) {
-    extern __shared__ unsigned char smem_raw[];
-    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
-    __shared__ RigParams rg;
+template <class SM> __device__ void solve_body(const SolveBatch &b, const RigParams *__restrict__ rig_g, SM &s, RigParams &rg) {
     const int tid = threadIdx.x;
     if (tid == 0) rg = *rig_g;
     Prob P;
@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigPar
         P.inv_x = sc; sc += Mp; P.inv_c = sc; sc += Mp; P.h_ll = sc; sc += Mp; P.g_l = sc; sc += Mp;
         P.sc_l = sc; sc += Mp; P.D_l = sc; sc += Mp; P.y_l = sc; sc += Mp; P.ht_l = sc; sc += Mp;
         P.W = sc; sc += (size_t)P.d.n_active * 6 * Mp;
-        P.Hcopy = sc; sc += HPACK;
+        if constexpr (!SM::kSharedH) { s.H.a = sc; sc += SM::HP; }
+        P.Hcopy = sc; sc += SM::HP;
         P.pre_s = sc; sc += (size_t)P.d.n_pre * kPreScratch;
         P.m_dx = sc; sc += n + 32; P.m_r = sc; sc += n + 32; P.m_v = sc; sc += n + 32; sc += n + 32;
         P.m_T = sc; sc += n * n;
@@ -278,12 +279,12 @@ __global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigPar
     SolveOut &out = b.out[blockIdx.x];
     // ---- load user memory ----
     for (int i = tid; i < P.d.n_frames * 16; i += ST) { const double v = P.states_g[i]; s.us[i] = v; s.xs[i] = v; s.cs[i] = v; }
-    for (int f = tid; f < kMaxActive; f += ST) {
+    for (int f = tid; f < SM::kA; f += ST) {
         const unsigned char fl = f < P.d.n_active ? P.flags_g[f] : 0;
         s.pose_free[f] = fl & 1; s.motion_free[f] = (fl >> 1) & 1;
     }
     __syncthreads();
-    for (int c = tid; c < kNP; c += ST) {
+    for (int c = tid; c < SM::NPv; c += ST) {
         const int f = c / 15, k = c % 15;
         s.col_free[c] = (c < P.NPc) && (k < 6 ? s.pose_free[f] : s.motion_free[f]);
         s.scale[c] = 1.0; s.D[c] = 1.0; s.y[c] = 0.0;
@@ -507,6 +508,36 @@ __global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigPar
         out.iterations = n_rec; out.termination = termination; out.n_successful = n_succ; out.n_unsuccessful = n_unsucc;
         out.final_cost = minimum_cost;
     }
+}
+
+__global__ void __launch_bounds__(ST, 1) solve_kernel(SolveBatch b, const RigParams *__restrict__ rig_g) {
+    extern __shared__ unsigned char smem_raw[];
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    __shared__ RigParams rg;
+    solve_body(b, rig_g, s, rg);
+}
+
+// Large windows (BASELINE config 5: 30 keyframes x 2000 landmarks): same trust-region loop, H in global scratch, Schur
+// complement on the FP64 tensor pipe, panel Cholesky on the L2-resident triangle (solve_large.cuh).
+__global__ void __launch_bounds__(ST, 1) solve_large_kernel(SolveBatch b, const RigParams *__restrict__ rig_g) {
+    extern __shared__ unsigned char smem_raw[];
+    SmemL &s = *reinterpret_cast<SmemL *>(smem_raw);
+    __shared__ RigParams rg;
+    solve_body(b, rig_g, s, rg);
+}
+
+size_t solve_large_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k, int n_rpe) {
+    return solve_scratch_doubles(n_active, n_lm_free, n_pre, marg_k, n_rpe) - HPACK + 2 * (size_t)SmemL::HP;
+}
+
+void solve_large(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
+    if (n_problems <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(solve_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemL));
+        attr_set = true;
+    }
+    solve_large_kernel<<<n_problems, ST, sizeof(SmemL), st>>>(b, rig);
 }
 
 void solve(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {

@@ -192,17 +192,20 @@ int xrvio_op_solve(const xrvio_rig *rig, xrvio_solve_desc *desc, int n_problems,
                    long long n_marg_doubles, xrvio_solve_out *out) {
     if (!rig || !desc || !states || !frame_flags || !out || n_problems <= 0 || n_frames <= 0) return fail_arg("xrvio_op_solve: bad argument");
     long long scratch = 0;
+    bool large = false;
+    for (int p = 0; p < n_problems; ++p) large = large || desc[p].n_active > XRVIO_MAX_ACTIVE;
     for (int p = 0; p < n_problems; ++p) {
         xrvio_solve_desc &d = desc[p];
-        if (d.n_active > XRVIO_MAX_ACTIVE || d.n_frames > XRVIO_MAX_FRAMES || d.n_active > d.n_frames || d.max_iterations >= XRVIO_MAX_ITER - 2) {
-            xrvio_set_error("xrvio_op_solve: problem exceeds XRVIO_MAX_ACTIVE / XRVIO_MAX_FRAMES / XRVIO_MAX_ITER");
+        if (d.n_active > (large ? XRVIO_MAX_ACTIVE_LARGE : XRVIO_MAX_ACTIVE) || d.n_frames > XRVIO_MAX_FRAMES || d.n_active > d.n_frames || d.max_iterations >= XRVIO_MAX_ITER - 2) {
+            xrvio_set_error("xrvio_op_solve: problem exceeds XRVIO_MAX_ACTIVE(_LARGE) / XRVIO_MAX_FRAMES / XRVIO_MAX_ITER");
             return XRVIO_ERR_LIMIT;
         }
         if (d.frame_off < 0 || d.frame_off + d.n_frames > n_frames || d.lm_off + d.n_lm > n_lm || d.rpe_off + d.n_rpe > n_rpe ||
             d.rot_off + d.n_rot > n_rot || d.pre_off + d.n_pre > n_pre || d.n_lm_free > d.n_lm || d.marg_frames_off + d.marg_k > n_marg_frames)
             return fail_arg("xrvio_op_solve: descriptor out of range");
         d.scratch_off = scratch;
-        scratch += (long long)xvbe::solve_scratch_doubles(d.n_active, d.n_lm_free, d.n_pre, d.marg_k, d.n_rpe);
+        scratch += (long long)(large ? xvbe::solve_large_scratch_doubles(d.n_active, d.n_lm_free, d.n_pre, d.marg_k, d.n_rpe)
+                                     : xvbe::solve_scratch_doubles(d.n_active, d.n_lm_free, d.n_pre, d.marg_k, d.n_rpe));
     }
     DevBuf d_rig, d_desc, d_states, d_flags, d_inv, d_rpe, d_rot, d_pre, d_pb, d_mf, d_marg, d_scr, d_out;
     CK(d_rig.alloc(sizeof(xrvio_rig))); CK(cudaMemcpy(d_rig.p, rig, sizeof(xrvio_rig), cudaMemcpyHostToDevice));
@@ -231,7 +234,8 @@ int xrvio_op_solve(const xrvio_rig *rig, xrvio_solve_desc *desc, int n_problems,
     b.inv_depth = d_inv.as<double>(); b.rpe = d_rpe.as<xrvio_rpe>(); b.rot = d_rot.as<xrvio_rot>(); b.pre = d_pre.as<xrvio_pre_ref>();
     b.pre_blocks = d_pb.as<double>(); b.marg_frames = d_mf.as<int>(); b.marg = d_marg.as<double>(); b.scratch = d_scr.as<double>();
     b.out = d_out.as<xrvio_solve_out>();
-    xvbe::solve(b, n_problems, d_rig.as<xrvio_rig>(), 0);
+    if (large) xvbe::solve_large(b, n_problems, d_rig.as<xrvio_rig>(), 0);
+    else xvbe::solve(b, n_problems, d_rig.as<xrvio_rig>(), 0);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(states, d_states.p, (size_t)n_frames * 16 * 8, cudaMemcpyDeviceToHost));

@@ -15,7 +15,7 @@ using namespace xv;
 
 constexpr int ST = 512;                    // threads per CTA
 constexpr int NW = ST / 32;
-constexpr int HPACK = kNP * (kNP + 1) / 2;
+constexpr int HPACK = kNP * (kNP + 1) / 2;          // sliding-window instance (Smem)
 constexpr int kPreScratch = 1024;          // doubles of scratch per preintegration factor
 
 // Ceres 1.14 Solver::Options defaults (Appendix C of SURVEY.md)
@@ -32,25 +32,44 @@ struct KProf {
     __device__ void mark(int i) { if (on) { long long t = clock64(); atomicAdd(&g_kprof[i], (unsigned long long)(t - last)); last = t; } }
 };
 
-struct Smem {
-    double H[HPACK];                       // packed lower-triangular, row i at i(i+1)/2
+// H of the reduced camera system, packed lower-triangular (row i at i(i+1)/2): inside the CTA's shared memory for sliding
+// windows (<= kMaxActive frames), in global memory (L2-resident scratch) for large windows (backend_solve_large.cu).
+template <int HP, bool SHARED> struct HStore;
+template <int HP> struct HStore<HP, true> {
+    double a[HP];
+    __device__ __forceinline__ double &operator[](int i) { return a[i]; }
+    __device__ __forceinline__ const double &operator[](int i) const { return a[i]; }
+};
+template <int HP> struct HStore<HP, false> {
+    double *a;
+    __device__ __forceinline__ double &operator[](int i) { return a[i]; }
+    __device__ __forceinline__ const double &operator[](int i) const { return a[i]; }
+};
+
+template <int KA, bool SHARED> struct SmemT {
+    static constexpr int kA = KA;              // free frames per problem
+    static constexpr int NPv = 15 * KA;        // pose / motion columns
+    static constexpr int HP = NPv * (NPv + 1) / 2;
+    static constexpr bool kSharedH = SHARED;
+    HStore<HP, SHARED> H;                  // packed lower-triangular, row i at i(i+1)/2
     double xs[kMaxFrames * 16];            // current iterate
     double cs[kMaxFrames * 16];            // candidate
     double us[kMaxFrames * 16];            // user memory (last state written back)
-    double g[kNP], scale[kNP], D[kNP], y[kNP], bred[kNP];
-    double du[kNP], dw[kNP];               // unscaled steepest-descent / Gauss-Newton directions of the current linearisation
-    double colp[6 * kNP];                  // the six scaled columns of the current Cholesky panel (gauss_newton)
+    double g[NPv], scale[NPv], D[NPv], y[NPv], bred[NPv];
+    double du[NPv], dw[NPv];               // unscaled steepest-descent / Gauss-Newton directions of the current linearisation
+    double colp[6 * NPv];                  // the six scaled columns of the current Cholesky panel (gauss_newton)
     double red[NW];
-    double jrinv[kMaxActive * 9];
-    unsigned char col_free[kNP];
-    unsigned char pose_free[kMaxActive], motion_free[kMaxActive];
+    double jrinv[KA * 9];
+    unsigned char col_free[NPv];
+    unsigned char pose_free[KA], motion_free[KA];
     double sc[16];                         // broadcast scalars
     int flag;
 };
+using Smem = SmemT<kMaxActive, true>;
 
 __device__ __forceinline__ int hidx(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
-__device__ __forceinline__ double block_sum(double v, Smem &s) {
+template <class SM> __device__ __forceinline__ double block_sum(double v, SM &s) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) s.red[threadIdx.x >> 5] = v;
@@ -59,7 +78,7 @@ __device__ __forceinline__ double block_sum(double v, Smem &s) {
     for (int k = 0; k < NW; ++k) t += s.red[k];
     return t;
 }
-__device__ __forceinline__ double block_max(double v, Smem &s) {
+template <class SM> __device__ __forceinline__ double block_max(double v, SM &s) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     __syncthreads();
     if ((threadIdx.x & 31) == 0) s.red[threadIdx.x >> 5] = v;
@@ -132,14 +151,14 @@ static __device__ void prepare_prior(Prob &P, const double *arena, double *St) {
 // With want_jac the unscaled H (pose/motion block, packed in shared memory), g, W, h_ll, g_l are
 // rebuilt.  Constant blocks and "user memory" reads come from us / invd_user.
 // ------------------------------------------------------------------------------------------------
-static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const double *inv, const RigParams &rg,
+template <class SM> static __device__ double evaluate(const Prob &P, SM &s, const double *S, const double *inv, const RigParams &rg,
                            bool want_jac, bool robust = true, KProf *kp = nullptr) {
     const int kb = want_jac ? 0 : 8;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M;
     if (want_jac) {
-        for (int i = tid; i < HPACK; i += ST) s.H[i] = 0.0;
-        for (int i = tid; i < kNP; i += ST) s.g[i] = 0.0;
+        for (int i = tid; i < SM::HP; i += ST) s.H[i] = 0.0;
+        for (int i = tid; i < SM::NPv; i += ST) s.g[i] = 0.0;
         for (int i = tid; i < M; i += ST) { P.h_ll[i] = 0.0; P.g_l[i] = 0.0; }
         const int nw = P.d.n_active * 6 * M;
         for (int i = tid; i < nw; i += ST) P.W[i] = 0.0;
@@ -442,7 +461,7 @@ static __device__ double evaluate(const Prob &P, Smem &s, const double *S, const
 // Eliminate the (scalar) inverse-depth blocks: H_pp -= sum_l w_l w_l^T / ht_l and
 // rhs_p -= sum_l w_l g_l / ht_l, with ht_l = P.ht_l (landmarks with a non-finite 1/ht_l are skipped,
 // marginalization_factor.h:384-386).  One warp per pair of frame slots, lanes over landmarks.
-static __device__ void schur_landmarks(const Prob &P, Smem &s, double *rhs) {
+template <class SM> static __device__ void schur_landmarks(const Prob &P, SM &s, double *rhs) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M, na = P.d.n_active;
     (void)tid;

@@ -1,0 +1,160 @@
+// Large-window variant of the solve kernel (BASELINE.json config 5: 30 keyframes x 2000 landmarks, 58 000 reprojection
+// residuals, 29 preintegration edges, dense 435 x 435 prior).  The trust-region loop, the factor evaluation and the
+// J^T J assembly are the templated code of solve_core.cuh / backend_solve.cu; what differs from the sliding-window
+// instance is where the reduced camera matrix lives and how it is reduced and factorised:
+//   * H (packed lower triangle, 480 * 481 / 2 doubles = 0.9 MB) does not fit in shared memory: it lives in the problem's
+//     global scratch and stays L2-resident (64 problems x 2 copies = 118 MB against 126 MB of L2);
+//   * landmark Schur complement S = H_pp - W diag(1/ht) W^T (solver.cpp:179, marginalization_factor.h:383-398) is a true
+//     contraction over the landmarks (180 x 2000 SYRK): FP64 tensor pipe, mma.sync.m8n8k4.f64 (tcgen05 has no FP64 kind);
+//   * Cholesky of the 450 x 450 system: right-looking, panels of six columns, trailing update streamed over the
+//     L2-resident triangle (the register-tile factorisation of the small instance needs n <= 180).
+#pragma once
+#include "solve_core.cuh"
+
+namespace xvbe {
+
+constexpr int kMaxActiveLarge = XRVIO_MAX_ACTIVE_LARGE;
+using SmemL = SmemT<kMaxActiveLarge, false>;
+
+// D(8x8) += A(8x4) B(4x8), FP64.  Fragments (PTX ISA, mma.m8n8k4 .f64): with g = lane >> 2, t = lane & 3 a lane holds
+// A[g][t], B[t][g] and D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+#ifdef CUEMU
+    // test-only SIMT emulator: the same contraction spelled with shuffles, so the fragment layout is what gets tested
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int k = 0; k < 4; ++k) {
+        const double ak = __shfl_sync(0xffffffffu, a, g * 4 + k);
+        const double b0 = __shfl_sync(0xffffffffu, b, (2 * t) * 4 + k);
+        const double b1 = __shfl_sync(0xffffffffu, b, (2 * t + 1) * 4 + k);
+        d0 += ak * b0;
+        d1 += ak * b1;
+    }
+#else
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+#endif
+}
+
+// Same contract as schur_landmarks() (solve_core.cuh).  The 6 * n_active pose rows of W (row r = 6 * frame + k, landmarks
+// fastest) are cut into 16 x 16 blocks of the lower triangle, one warp per block and four m8n8k4 accumulators per warp;
+// the contraction runs over the landmarks four at a time.  Every output element is owned by exactly one lane.
+template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM &s, double *rhs) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = P.M, na = P.d.n_active;
+    if (M <= 0) return;
+    const int R = 6 * na;
+    const int nb = (R + 15) / 16;
+    const int g = lane >> 2, t = lane & 3;
+    for (int blk = warp; blk < nb * (nb + 1) / 2; blk += NW) {
+        int bi = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
+        while (bi * (bi + 1) / 2 > blk) --bi;
+        while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+        const int bj = blk - bi * (bi + 1) / 2;        // bi >= bj
+        double acc[2][2][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) (&acc[0][0][0])[i] = 0.0;
+        const int ra0 = bi * 16 + g, ra1 = ra0 + 8;      // rows of the two A fragments
+        const int cb0 = bj * 16 + g, cb1 = cb0 + 8;      // columns of the two B fragments
+        const double *wa0 = P.W + (size_t)ra0 * M, *wa1 = P.W + (size_t)ra1 * M;
+        const double *wb0 = P.W + (size_t)cb0 * M, *wb1 = P.W + (size_t)cb1 * M;
+        for (int l0 = 0; l0 < M; l0 += 4) {
+            const int l = l0 + t;
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            if (l < M) {
+                double ih = 1.0 / P.ht_l[l];
+                if (!isfinite(ih)) ih = 0.0;
+                if (ra0 < R) a0 = wa0[l];
+                if (ra1 < R) a1 = wa1[l];
+                if (cb0 < R) b0 = wb0[l] * ih;
+                if (cb1 < R) b1 = wb1[l] * ih;
+            }
+            dmma_m8n8k4(acc[0][0][0], acc[0][0][1], a0, b0);
+            dmma_m8n8k4(acc[0][1][0], acc[0][1][1], a0, b1);
+            dmma_m8n8k4(acc[1][0][0], acc[1][0][1], a1, b0);
+            dmma_m8n8k4(acc[1][1][0], acc[1][1][1], a1, b1);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int r = bi * 16 + rr * 8 + g, c = bj * 16 + cc * 8 + 2 * t + i;
+                    if (r >= R || c > r) continue;
+                    const int fa = r / 6, fb = c / 6;
+                    if (!s.pose_free[fa] || !s.pose_free[fb]) continue;
+                    s.H[hidx(15 * fa + r % 6, 15 * fb + c % 6)] -= acc[rr][cc][i];
+                }
+    }
+    // b_red = gs_p - sum_l w_l gs_l / ht_l
+    for (int c = warp; c < R; c += NW) {
+        const int a = c / 6, k = c % 6;
+        if (!s.pose_free[a]) continue;
+        double v = 0.0;
+        for (int l = lane; l < M; l += 32) { double ih = 1.0 / P.ht_l[l]; if (!isfinite(ih)) ih = 0.0; v += P.W[(size_t)c * M + l] * P.g_l[l] * ih; }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) rhs[15 * a + k] -= v;
+    }
+}
+
+// In-place right-looking Cholesky of the packed lower triangle s.H (global memory), panels of six columns.  Per panel:
+// (1) thread 0 factorises the 6 x 6 diagonal block, (2) one thread per row below it solves the row against that block and
+// publishes the six scaled columns (s.colp, also written back), (3) the trailing triangle takes the rank-6 update, one warp
+// per row and lanes along the row (coalesced in the packed layout).  Every element sees the updates of the columns in
+// ascending order, as in a column-by-column factorisation.  s.flag = 0 on a non-positive or non-finite pivot
+// (-> LINEAR_SOLVER_FAILURE, the caller raises mu); 1 / L_jj is left in idiag[] for the substitutions.
+template <class SM> static __device__ void cholesky_global(SM &s, int n, double *col, double *idiag) {
+    (void)col;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int TB = 6;
+    double *colp = s.colp;                               // colp[c * NPv + row]
+    for (int j0 = 0; j0 < n; j0 += TB) {
+        const int j1 = min(j0 + TB, n), w = j1 - j0;
+        if (tid == 0) {
+            double a[TB][TB];
+            for (int i = 0; i < w; ++i)
+                for (int k = 0; k <= i; ++k) a[i][k] = s.H[hidx(j0 + i, j0 + k)];
+            for (int c = 0; c < w && s.flag; ++c) {
+                const double d = a[c][c];
+                if (!(d > 0.0) || !isfinite(d)) { s.flag = 0; break; }
+                const double inv = rsqrt(d);
+                idiag[j0 + c] = inv;
+                a[c][c] = d * inv;
+                for (int i = c + 1; i < w; ++i) a[i][c] *= inv;
+                for (int i = c + 1; i < w; ++i)
+                    for (int k = c + 1; k <= i; ++k) a[i][k] -= a[i][c] * a[k][c];
+            }
+            if (s.flag)
+                for (int i = 0; i < w; ++i)
+                    for (int k = 0; k <= i; ++k) { s.H[hidx(j0 + i, j0 + k)] = a[i][k]; colp[k * SM::NPv + j0 + i] = a[i][k]; }
+        }
+        __syncthreads();
+        if (!s.flag) return;                             // uniform
+        // (2) rows below the panel: L(i, j0 + c) = (a(i, c) - sum_{k < c} L(i, j0 + k) L(j0 + c, j0 + k)) / L(j0 + c, j0 + c)
+        for (int i = j1 + tid; i < n; i += ST) {
+            double v[TB];
+            for (int c = 0; c < w; ++c) v[c] = s.H[hidx(i, j0 + c)];
+            for (int c = 0; c < w; ++c) {
+                v[c] *= idiag[j0 + c];
+                for (int k = c + 1; k < w; ++k) v[k] -= v[c] * colp[c * SM::NPv + j0 + k];
+            }
+            for (int c = 0; c < w; ++c) { s.H[hidx(i, j0 + c)] = v[c]; colp[c * SM::NPv + i] = v[c]; }
+        }
+        __syncthreads();
+        // (3) trailing triangle
+        for (int i = j1 + warp; i < n; i += NW) {
+            double ci[TB];
+            for (int c = 0; c < TB; ++c) ci[c] = c < w ? colp[c * SM::NPv + i] : 0.0;
+            double *row = &s.H[hidx(i, 0)];
+            for (int k = j1 + lane; k <= i; k += 32) {
+                double a = row[k];
+#pragma unroll
+                for (int c = 0; c < TB; ++c)
+                    if (c < w) a -= ci[c] * colp[c * SM::NPv + k];
+                row[k] = a;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace xvbe
