@@ -360,8 +360,53 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def run_ba_stress(args):
+    """Secondary line (not the driver's): BASELINE config 5, a batch of 30-keyframe x 2000-landmark window solves, 10 trust-region
+    iterations each, through xrvio_op_solve (host buffers in, host buffers out = e2e); `value` uses the device time of the solve
+    kernel alone (xrvio_debug_last_solve_ms, CUDA events on the launch stream).  Flop count per iteration: SURVEY.md 8(d),
+    ~0.3 GFLOP (Schur SYRK 130 M, pose-block J^T J 33 M, prior 110 M, Cholesky 30 M); FP64 peak is not in MEASURED_PEAKS.json,
+    the datasheet's 40 TFLOP/s is used and named as such."""
+    import ctypes
+    import numpy as np
+    from xrslam_b200 import capi
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    from oracle import stress, bridge                     # problem generator + packer only (test infrastructure, not timed)
+    capi.lib.xrvio_debug_last_solve_ms.restype = ctypes.c_double
+    pbs = [stress.make_stress_problem(100 + i, 30, 2000) for i in range(args.problems)]
+    pk = bridge.PackedProblems(pbs)
+    rig = bridge.rig_from_problem(pbs[0])
+    st0, inv0 = pk.states.copy(), pk.inv_depth.copy()
+    kern_ms, wall_ms, iters = [], [], 0
+    for k in range(args.warmup + args.steps):
+        pk.states[:], pk.inv_depth[:] = st0, inv0
+        t0 = time.perf_counter()
+        out = pk.solve(rig)
+        t1 = time.perf_counter()
+        if k >= args.warmup:
+            kern_ms.append(float(capi.lib.xrvio_debug_last_solve_ms()))
+            wall_ms.append((t1 - t0) * 1e3)
+            iters = int(sum(int(o['iterations']) - 1 for o in out))
+    km, wm = float(np.mean(kern_ms)), float(np.mean(wall_ms))
+    flops = 0.3e9 * iters
+    h2d = int(pk.states.nbytes + pk.inv_depth.nbytes + pk.rpe.nbytes + pk.pre_blocks.nbytes + pk.marg.nbytes)
+    print(json.dumps({
+        'metric': 'BA iterations/sec (30 keyframes x 2000 landmarks)', 'value': iters / (km * 1e-3), 'unit': 'iterations/s', 'n_gpus': 1,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': km, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': 'ba_stress_30kf_2000lm', 'problems': args.problems, 'iterations': 10,
+                                                          'residuals_per_problem': 58000, 'l2': 'inputs_larger_than_L2' if h2d > 126e6 else 'not flushed'},
+        'e2e': {'value': iters / (wm * 1e-3), 'unit': 'iterations/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(pk.states.nbytes + pk.inv_depth.nbytes),
+                'ms_per_step': wm},
+        'gpu_launches': args.steps * (1 + args.problems),
+        'roofline': {'bound': 'tensor', 'kernel': 'solve_large', 'achieved': flops / (km * 1e-3) / 1e12, 'peak': 40.0, 'peak_source': 'datasheet FP64 (unmeasured)',
+                     'unit': 'TFLOP/s', 'frac': flops / (km * 1e-3) / 1e12 / 40.0, 'traffic': None},
+        'final_cost_mean': float(np.mean([o['final_cost'] for o in out]))}))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--workload', default='streams', choices=['streams', 'ba_stress'],
+                    help='streams: BASELINE config 3 (the metric line); ba_stress: config 5, batch of large-window solves')
+    ap.add_argument('--problems', type=int, default=64)
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
@@ -371,6 +416,10 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.workload == 'ba_stress':
+        if rank == 0:
+            run_ba_stress(args)
+        return
     if args.impl == 'reference':
         run_reference_arm(args, rank, world)
         return

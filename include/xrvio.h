@@ -254,6 +254,9 @@ int xrvio_get_phase_times(xrvio_ctx *ctx, double *ms, int capacity);
 /* Diagnostics: clock64 cycles accumulated per section of the solve kernel over all window problems (32 slots, slot 31 =
  * number of problems); see tools/phase_probe.py for the slot names. */
 int xrvio_debug_kprof(unsigned long long *out32, int reset);
+/* Diagnostics: device time (CUDA events on the launch stream) of the solve kernel launched by the last xrvio_op_solve call of this
+ * thread's process, in ms; < 0 before the first call.  bench.py --workload ba_stress reads it for the config-5 roofline line. */
+double xrvio_debug_last_solve_ms(void);
 
 #ifdef __cplusplus
 }

@@ -318,3 +318,4 @@ const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no er
 cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new cuemu_event(); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }

@@ -66,6 +66,7 @@ const char *cudaGetErrorString(cudaError_t e);
 cudaError_t cudaEventCreate(cudaEvent_t *e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
+cudaError_t cudaEventDestroy(cudaEvent_t e);
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class T> inline cudaError_t cudaMemcpyFromSymbol(void *dst, const T &sym, size_t n) { std::memcpy(dst, &sym, n); return cudaSuccess; }
 template <class T> inline cudaError_t cudaMemcpyToSymbol(T &sym, const void *src, size_t n) { std::memcpy(&sym, src, n); return cudaSuccess; }

@@ -550,11 +550,11 @@ void solve(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream
     solve_kernel<<<n_problems, ST, sizeof(Smem), st>>>(b, rig);
 }
 
-// A0 = S^T S, one CTA per prior
+// A0 = S^T S; blockIdx.x = prior, blockIdx.y = slice of the n^2 entries (one entry per thread and pass, rows of S in order)
 __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ S, double *__restrict__ A0, int n, size_t stride) {
     const double *Sp = S + (size_t)blockIdx.x * stride;
     double *Ap = A0 + (size_t)blockIdx.x * stride;
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < n * n; e += gridDim.y * blockDim.x) {
         const int i = e / n, j = e % n;
         double a = 0.0;
         for (int r = 0; r < n; ++r) a += Sp[(size_t)r * n + i] * Sp[(size_t)r * n + j];
@@ -563,7 +563,8 @@ __global__ void __launch_bounds__(256) gram_kernel(const double *__restrict__ S,
 }
 void gram(const double *S, double *A0, int n, int n_priors, size_t stride, cudaStream_t st) {
     if (n_priors <= 0 || n <= 0) return;
-    gram_kernel<<<n_priors, 256, 0, st>>>(S, A0, n, stride);
+    const int slices = min(max((n * n + 1023) / 1024, 1), 296);
+    gram_kernel<<<dim3(n_priors, slices), 256, 0, st>>>(S, A0, n, stride);
 }
 
 }  // namespace xvbe

@@ -185,6 +185,9 @@ int xrvio_op_preintegrate(const xrvio_rig *rig, const xrvio_preint_job *jobs, in
     return XRVIO_OK;
 }
 
+static double g_last_solve_ms = -1.0;
+double xrvio_debug_last_solve_ms(void) { return g_last_solve_ms; }
+
 int xrvio_op_solve(const xrvio_rig *rig, xrvio_solve_desc *desc, int n_problems, double *states, int n_frames,
                    const uint8_t *frame_flags, double *inv_depth, int n_lm, const xrvio_rpe *rpe, int n_rpe,
                    const xrvio_rot *rot, int n_rot, const xrvio_pre_ref *pre, int n_pre, const double *pre_blocks,
@@ -234,10 +237,16 @@ int xrvio_op_solve(const xrvio_rig *rig, xrvio_solve_desc *desc, int n_problems,
     b.inv_depth = d_inv.as<double>(); b.rpe = d_rpe.as<xrvio_rpe>(); b.rot = d_rot.as<xrvio_rot>(); b.pre = d_pre.as<xrvio_pre_ref>();
     b.pre_blocks = d_pb.as<double>(); b.marg_frames = d_mf.as<int>(); b.marg = d_marg.as<double>(); b.scratch = d_scr.as<double>();
     b.out = d_out.as<xrvio_solve_out>();
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, 0));
     if (large) xvbe::solve_large(b, n_problems, d_rig.as<xrvio_rig>(), 0);
     else xvbe::solve(b, n_problems, d_rig.as<xrvio_rig>(), 0);
+    CK(cudaEventRecord(ev1, 0));
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
+    { float ms = -1.f; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) g_last_solve_ms = ms; }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     CK(cudaMemcpy(states, d_states.p, (size_t)n_frames * 16 * 8, cudaMemcpyDeviceToHost));
     if (n_lm) CK(cudaMemcpy(inv_depth, d_inv.p, (size_t)n_lm * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out, d_out.p, n_problems * sizeof(xrvio_solve_out), cudaMemcpyDeviceToHost));
