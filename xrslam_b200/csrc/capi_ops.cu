@@ -199,7 +199,9 @@ int xrvio_op_solve(const xrvio_rig *rig, xrvio_solve_desc *desc, int n_problems,
     for (int p = 0; p < n_problems; ++p) large = large || desc[p].n_active > XRVIO_MAX_ACTIVE;
     for (int p = 0; p < n_problems; ++p) {
         xrvio_solve_desc &d = desc[p];
-        if (d.n_active > (large ? XRVIO_MAX_ACTIVE_LARGE : XRVIO_MAX_ACTIVE) || d.n_frames > XRVIO_MAX_FRAMES || d.n_active > d.n_frames || d.max_iterations >= XRVIO_MAX_ITER - 2) {
+        const int max_active = large ? XRVIO_MAX_ACTIVE_LARGE : XRVIO_MAX_ACTIVE;
+        if (d.n_active > max_active || d.marg_k > max_active || d.n_pre > 34 || d.n_frames > XRVIO_MAX_FRAMES || d.n_active > d.n_frames ||
+            d.max_iterations >= XRVIO_MAX_ITER - 2) {
             xrvio_set_error("xrvio_op_solve: problem exceeds XRVIO_MAX_ACTIVE(_LARGE) / XRVIO_MAX_FRAMES / XRVIO_MAX_ITER");
             return XRVIO_ERR_LIMIT;
         }

@@ -44,6 +44,11 @@ template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM
     const int R = 6 * na;
     const int nb = (R + 15) / 16;
     const int g = lane >> 2, t = lane & 3;
+    // 1 / ht_l once per landmark (non-finite -> 0: the landmark is skipped, marginalization_factor.h:384-386); y_l is free
+    // until the back-substitution at the end of gauss_newton()
+    double *ihv = P.y_l;
+    for (int l = tid; l < M; l += ST) { double ih = 1.0 / P.ht_l[l]; if (!isfinite(ih)) ih = 0.0; ihv[l] = ih; }
+    __syncthreads();
     for (int blk = warp; blk < nb * (nb + 1) / 2; blk += NW) {
         int bi = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
         while (bi * (bi + 1) / 2 > blk) --bi;
@@ -60,8 +65,7 @@ template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM
             const int l = l0 + t;
             double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
             if (l < M) {
-                double ih = 1.0 / P.ht_l[l];
-                if (!isfinite(ih)) ih = 0.0;
+                const double ih = ihv[l];
                 if (ra0 < R) a0 = wa0[l];
                 if (ra1 < R) a1 = wa1[l];
                 if (cb0 < R) b0 = wb0[l] * ih;
@@ -90,7 +94,7 @@ template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM
         const int a = c / 6, k = c % 6;
         if (!s.pose_free[a]) continue;
         double v = 0.0;
-        for (int l = lane; l < M; l += 32) { double ih = 1.0 / P.ht_l[l]; if (!isfinite(ih)) ih = 0.0; v += P.W[(size_t)c * M + l] * P.g_l[l] * ih; }
+        for (int l = lane; l < M; l += 32) v += P.W[(size_t)c * M + l] * P.g_l[l] * ihv[l];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) rhs[15 * a + k] -= v;
     }
