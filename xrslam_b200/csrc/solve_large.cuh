@@ -6,8 +6,8 @@
 //     global scratch and stays L2-resident (64 problems x 2 copies = 118 MB against 126 MB of L2);
 //   * landmark Schur complement S = H_pp - W diag(1/ht) W^T (solver.cpp:179, marginalization_factor.h:383-398) is a true
 //     contraction over the landmarks (180 x 2000 SYRK): FP64 tensor pipe, mma.sync.m8n8k4.f64 (tcgen05 has no FP64 kind);
-//   * Cholesky of the 450 x 450 system: right-looking, panels of six columns, trailing update streamed over the
-//     L2-resident triangle (the register-tile factorisation of the small instance needs n <= 180).
+//   * Cholesky of the 450 x 450 system: right-looking, panels of six columns, the trailing rank-6 update as 8 x 8 DMMA tiles
+//     streamed over the L2-resident triangle (the register-tile factorisation of the small instance needs n <= 180).
 #pragma once
 #include "solve_core.cuh"
 
@@ -102,9 +102,8 @@ template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM
 
 // In-place right-looking Cholesky of the packed lower triangle s.H (global memory), panels of six columns.  Per panel:
 // (1) thread 0 factorises the 6 x 6 diagonal block, (2) one thread per row below it solves the row against that block and
-// publishes the six scaled columns (s.colp, also written back), (3) the trailing triangle takes the rank-6 update, one warp
-// per row and lanes along the row (coalesced in the packed layout).  Every element sees the updates of the columns in
-// ascending order, as in a column-by-column factorisation.  s.flag = 0 on a non-positive or non-finite pivot
+// publishes the six scaled columns (s.colp, also written back), (3) the trailing triangle takes the rank-6 update on the
+// tensor pipe.  s.flag = 0 on a non-positive or non-finite pivot
 // (-> LINEAR_SOLVER_FAILURE, the caller raises mu); 1 / L_jj is left in idiag[] for the substitutions.
 template <class SM> static __device__ void cholesky_global(SM &s, int n, double *col, double *idiag) {
     (void)col;
@@ -144,7 +143,40 @@ template <class SM> static __device__ void cholesky_global(SM &s, int n, double 
             for (int c = 0; c < w; ++c) { s.H[hidx(i, j0 + c)] = v[c]; colp[c * SM::NPv + i] = v[c]; }
         }
         __syncthreads();
-        // (3) trailing triangle
+        // (3) trailing triangle: A -= Lp Lp^T with Lp the (n - j1) x 6 panel just published -- a rank-6 contraction, on the FP64
+        // tensor pipe as 8 x 8 tiles (k padded to 8 with zeros: two m8n8k4 steps).  One warp per row of tiles: its A fragment
+        // (-Lp rows) is loaded once, per tile the B fragment comes from shared memory and the C tile from the packed rows of
+        // H (two consecutive doubles per lane).  -DXRVIO_LARGE_CHOL_SCALAR keeps the CUDA-core version for A/B timing.
+#ifndef XRVIO_LARGE_CHOL_SCALAR
+        {
+            const int g = lane >> 2, t = lane & 3;
+            const int T = (n - j1 + 7) / 8;
+            for (int ti = warp; ti < T; ti += NW) {
+                const int r = j1 + 8 * ti + g;
+                double a0 = 0.0, a1 = 0.0;
+                if (r < n) {
+                    if (t < w) a0 = -colp[t * SM::NPv + r];
+                    if (4 + t < w) a1 = -colp[(4 + t) * SM::NPv + r];
+                }
+                double *row = &s.H[hidx(r < n ? r : n - 1, 0)];
+                for (int tk = 0; tk <= ti; ++tk) {
+                    const int cb = j1 + 8 * tk + g;
+                    double b0 = 0.0, b1 = 0.0;
+                    if (cb < n) {
+                        if (t < w) b0 = colp[t * SM::NPv + cb];
+                        if (4 + t < w) b1 = colp[(4 + t) * SM::NPv + cb];
+                    }
+                    const int c = j1 + 8 * tk + 2 * t;
+                    const bool v0 = r < n && c <= r, v1 = r < n && c + 1 <= r;
+                    double d0 = v0 ? row[c] : 0.0, d1 = v1 ? row[c + 1] : 0.0;
+                    dmma_m8n8k4(d0, d1, a0, b0);
+                    dmma_m8n8k4(d0, d1, a1, b1);
+                    if (v0) row[c] = d0;
+                    if (v1) row[c + 1] = d1;
+                }
+            }
+        }
+#else
         for (int i = j1 + warp; i < n; i += NW) {
             double ci[TB];
             for (int c = 0; c < TB; ++c) ci[c] = c < w ? colp[c * SM::NPv + i] : 0.0;
@@ -157,6 +189,7 @@ template <class SM> static __device__ void cholesky_global(SM &s, int n, double 
                 row[k] = a;
             }
         }
+#endif
         __syncthreads();
     }
 }
