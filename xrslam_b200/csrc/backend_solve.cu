@@ -267,7 +267,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
         P.inv_x = sc; sc += Mp; P.inv_c = sc; sc += Mp; P.h_ll = sc; sc += Mp; P.g_l = sc; sc += Mp;
         P.sc_l = sc; sc += Mp; P.D_l = sc; sc += Mp; P.y_l = sc; sc += Mp; P.ht_l = sc; sc += Mp;
         P.W = sc; sc += (size_t)P.d.n_active * 6 * Mp;
-        if constexpr (!SM::kSharedH) { s.H.a = sc; sc += SM::HP; }
+        if constexpr (!SM::kSharedH) { if (tid == 0) s.H.a = sc; sc += SM::HP; }     // published by the barrier in prepare_tangents()
         P.Hcopy = sc; sc += SM::HP;
         P.pre_s = sc; sc += (size_t)P.d.n_pre * kPreScratch;
         P.m_dx = sc; sc += n + 32; P.m_r = sc; sc += n + 32; P.m_v = sc; sc += n + 32; sc += n + 32;

@@ -42,8 +42,14 @@ template <int HP> struct HStore<HP, true> {
 };
 template <int HP> struct HStore<HP, false> {
     double *a;
-    __device__ __forceinline__ double &operator[](int i) { return a[i]; }
-    __device__ __forceinline__ const double &operator[](int i) const { return a[i]; }
+    __device__ __forceinline__ double *base() const {
+#ifndef CUEMU
+        __builtin_assume(__isGlobal(a));       // lets the compiler emit LDG / STG / RED.F64 instead of generic accesses
+#endif
+        return a;
+    }
+    __device__ __forceinline__ double &operator[](int i) { return base()[i]; }
+    __device__ __forceinline__ const double &operator[](int i) const { return base()[i]; }
 };
 
 template <int KA, bool SHARED> struct SmemT {
