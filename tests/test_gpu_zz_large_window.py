@@ -38,6 +38,26 @@ def test_large_window_matches_oracle(xrvio, n_kf, n_lm):
     _check(out, pb, ref, summ)
 
 
+def test_large_window_with_fixed_gauge_and_rotation_priors(xrvio):
+    """Constant blocks inside a large window: keyframe 0 fixed (pose and motion: its columns are unit-diagonal in the reduced
+    system and masked out of the tensor-pipe Schur update), keyframe 1 with a fixed pose only, and some observations turned
+    into rotation priors (rotation_factor.h:23-59)."""
+    pb = stress.make_stress_problem(8, 16, 80)
+    pb.fix_pose[0] = pb.fix_motion[0] = True
+    pb.fix_pose[1] = True
+    idx = np.arange(len(pb.rpe_tgt))
+    to_rot = idx % 11 == 0
+    pb.rot_tgt, pb.rot_ref = pb.rpe_tgt[to_rot].copy(), pb.rpe_ref[to_rot].copy()
+    pb.rot_z_tgt, pb.rot_z_ref = pb.rpe_z_tgt[to_rot].copy(), pb.rpe_z_ref[to_rot].copy()
+    for name in ('rpe_tgt', 'rpe_ref', 'rpe_lm', 'rpe_z_tgt', 'rpe_z_ref', 'rpe_prior'):
+        setattr(pb, name, getattr(pb, name)[~to_rot].copy())
+    ref = copy.deepcopy(pb)
+    summ = ceres_tr.solve(ref)
+    out = bridge.solve_problem_cuda(pb)
+    _check(out, pb, ref, summ)
+    assert np.array_equal(pb.states[0], ref.states[0]) and np.array_equal(pb.states[1, 0:7], ref.states[1, 0:7])
+
+
 def test_large_window_limits(xrvio):
     pb = stress.make_stress_problem(5, 33, 20)
     with pytest.raises(xrvio.XrvioError):
