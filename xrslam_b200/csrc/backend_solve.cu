@@ -14,6 +14,7 @@ size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k,
 
 // q <- normalize(q * exp(d)) for free pose blocks, additive elsewhere (quaternion_parameterization.h:11-17)
 template <class SM> __device__ void make_candidate(const Prob &P, SM &s, double c1, double c2) {
+    XV_ASSUME_SHARED(&s);
     const int tid = threadIdx.x;
     // delta_j = c1 * du_j + c2 * dw_j with du = -gs / D^2 * scale, dw = -y * scale (prepared per linearisation)
     for (int f = tid; f < P.d.n_frames; f += ST) {
@@ -51,6 +52,7 @@ template <class SM> __device__ double ambient_sq(const Prob &P, SM &s, const dou
 // Gauss-Newton step: (Hs + mu D^2) y = gs via Schur complement on the landmark block + Cholesky.
 // Returns false when the factorisation fails (LINEAR_SOLVER_FAILURE).  H is consumed.
 template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu) {
+    XV_ASSUME_SHARED(&s);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.NPc, M = P.M, na = P.d.n_active;
     for (int c = tid; c < n; c += ST)
@@ -247,6 +249,7 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
 }
 
 template <class SM> __device__ void solve_body(const SolveBatch &b, const RigParams *__restrict__ rig_g, SM &s, RigParams &rg) {
+    XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(&rg);
     const int tid = threadIdx.x;
     if (tid == 0) rg = *rig_g;
     Prob P;

@@ -32,6 +32,16 @@ struct KProf {
     __device__ void mark(int i) { if (on) { long long t = clock64(); atomicAdd(&g_kprof[i], (unsigned long long)(t - last)); last = t; } }
 };
 
+// Address-space facts the compiler cannot see once a function is not inlined into the kernel (the large-window instance):
+// without them every access through `s` or H becomes a generic LD.E / ST.E / CAS-loop atomic.
+#ifndef CUEMU
+#define XV_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#define XV_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#else
+#define XV_ASSUME_SHARED(p) ((void)0)
+#define XV_ASSUME_GLOBAL(p) ((void)0)
+#endif
+
 // H of the reduced camera system, packed lower-triangular (row i at i(i+1)/2): inside the CTA's shared memory for sliding
 // windows (<= kMaxActive frames), in global memory (L2-resident scratch) for large windows (backend_solve_large.cu).
 template <int HP, bool SHARED> struct HStore;
@@ -43,9 +53,7 @@ template <int HP> struct HStore<HP, true> {
 template <int HP> struct HStore<HP, false> {
     double *a;
     __device__ __forceinline__ double *base() const {
-#ifndef CUEMU
-        __builtin_assume(__isGlobal(a));       // lets the compiler emit LDG / STG / RED.F64 instead of generic accesses
-#endif
+        XV_ASSUME_GLOBAL(a);                   // lets the compiler emit LDG / STG / RED.F64 instead of generic accesses
         return a;
     }
     __device__ __forceinline__ double &operator[](int i) { return base()[i]; }
@@ -76,6 +84,7 @@ using Smem = SmemT<kMaxActive, true>;
 __device__ __forceinline__ int hidx(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
 
 template <class SM> __device__ __forceinline__ double block_sum(double v, SM &s) {
+    XV_ASSUME_SHARED(&s);
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) s.red[threadIdx.x >> 5] = v;
@@ -85,6 +94,7 @@ template <class SM> __device__ __forceinline__ double block_sum(double v, SM &s)
     return t;
 }
 template <class SM> __device__ __forceinline__ double block_max(double v, SM &s) {
+    XV_ASSUME_SHARED(&s);
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     __syncthreads();
     if ((threadIdx.x & 31) == 0) s.red[threadIdx.x >> 5] = v;
@@ -162,6 +172,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
     const int kb = want_jac ? 0 : 8;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M;
+    XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(S); XV_ASSUME_GLOBAL(inv);   // S is s.xs or s.cs, inv is P.inv_x or P.inv_c
     if (want_jac) {
         for (int i = tid; i < SM::HP; i += ST) s.H[i] = 0.0;
         for (int i = tid; i < SM::NPv; i += ST) s.g[i] = 0.0;
@@ -468,6 +479,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
 // rhs_p -= sum_l w_l g_l / ht_l, with ht_l = P.ht_l (landmarks with a non-finite 1/ht_l are skipped,
 // marginalization_factor.h:384-386).  One warp per pair of frame slots, lanes over landmarks.
 template <class SM> static __device__ void schur_landmarks(const Prob &P, SM &s, double *rhs) {
+    XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(rhs);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M, na = P.d.n_active;
     (void)tid;

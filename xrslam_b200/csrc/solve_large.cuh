@@ -38,6 +38,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 // fastest) are cut into 16 x 16 blocks of the lower triangle, one warp per block and four m8n8k4 accumulators per warp;
 // the contraction runs over the landmarks four at a time.  Every output element is owned by exactly one lane.
 template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM &s, double *rhs) {
+    XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(rhs);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M, na = P.d.n_active;
     if (M <= 0) return;
@@ -107,6 +108,7 @@ template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM
 // (-> LINEAR_SOLVER_FAILURE, the caller raises mu); 1 / L_jj is left in idiag[] for the substitutions.
 template <class SM> static __device__ void cholesky_global(SM &s, int n, double *col, double *idiag) {
     (void)col;
+    XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(idiag);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int TB = 6;
     double *colp = s.colp;                               // colp[c * NPv + row]
