@@ -366,12 +366,11 @@ def run_ba_stress(args):
     kernel alone (xrvio_debug_last_solve_ms, CUDA events on the launch stream).  Flop count per iteration: SURVEY.md 8(d),
     ~0.3 GFLOP (Schur SYRK 130 M, pose-block J^T J 33 M, prior 110 M, Cholesky 30 M); FP64 peak is not in MEASURED_PEAKS.json,
     the datasheet's 40 TFLOP/s is used and named as such."""
-    import ctypes
     import numpy as np
     from xrslam_b200 import capi
-    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
     from oracle import stress, bridge                     # problem generator + packer only (test infrastructure, not timed)
-    capi.lib.xrvio_debug_last_solve_ms.restype = ctypes.c_double
     pbs = [stress.make_stress_problem(100 + i, 30, 2000) for i in range(args.problems)]
     pk = bridge.PackedProblems(pbs)
     rig = bridge.rig_from_problem(pbs[0])
@@ -383,7 +382,7 @@ def run_ba_stress(args):
         out = pk.solve(rig)
         t1 = time.perf_counter()
         if k >= args.warmup:
-            kern_ms.append(float(capi.lib.xrvio_debug_last_solve_ms()))
+            kern_ms.append(capi.last_solve_ms())
             wall_ms.append((t1 - t0) * 1e3)
             iters = int(sum(int(o['iterations']) - 1 for o in out))
     km, wm = float(np.mean(kern_ms)), float(np.mean(wall_ms))

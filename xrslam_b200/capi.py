@@ -173,6 +173,13 @@ def op_solve(rig, desc, states, flags, inv_depth, rpe, rot, pre, pre_blocks, mar
     return out
 
 
+def last_solve_ms():
+    """Device time of the solve kernel launched by the last op_solve call (CUDA events), ms."""
+    f = lib.xrvio_debug_last_solve_ms
+    f.restype = C.c_double
+    return float(f())
+
+
 def op_marginalize(rig, desc, states, inv_depth, rpe, pre, pre_blocks, marg_frames, marg, n_out):
     out = np.zeros(n_out, np.float64)
     rank = np.zeros(len(desc), np.int32)

@@ -77,7 +77,7 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
     // the tiles below it scale their six columns against that tile and publish them, (3) every tile to the right applies
     // the six rank-1 updates from shared memory.  Every element sees the same operations in the same order as in a
     // column-by-column right-looking factorisation, so the factor is bit-identical to it.
-    if constexpr (!SM::kSharedH) cholesky_global(s, n, col, idiag);
+    if constexpr (!SM::kSharedH) cholesky_global(s, n, idiag);
     else {
         constexpr int TB = 6;
         const int nt = (n + TB - 1) / TB;

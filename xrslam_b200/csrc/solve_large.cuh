@@ -106,8 +106,7 @@ template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM
 // publishes the six scaled columns (s.colp, also written back), (3) the trailing triangle takes the rank-6 update on the
 // tensor pipe.  s.flag = 0 on a non-positive or non-finite pivot
 // (-> LINEAR_SOLVER_FAILURE, the caller raises mu); 1 / L_jj is left in idiag[] for the substitutions.
-template <class SM> static __device__ void cholesky_global(SM &s, int n, double *col, double *idiag) {
-    (void)col;
+template <class SM> static __device__ void cholesky_global(SM &s, int n, double *idiag) {
     XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(idiag);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int TB = 6;
