@@ -257,6 +257,9 @@ int xrvio_debug_kprof(unsigned long long *out32, int reset);
 /* Diagnostics: device time (CUDA events on the launch stream) of the solve kernel launched by the last xrvio_op_solve call of this
  * thread's process, in ms; < 0 before the first call.  bench.py --workload ba_stress reads it for the config-5 roofline line. */
 double xrvio_debug_last_solve_ms(void);
+/* Diagnostics: measured FP64 rates of the current device in TFLOP/s (register-resident DFMA loop; mma.sync.m8n8k4.f64 loop), the
+ * roofline denominators of the large-window solve -- MEASURED_PEAKS.json has no FP64 entry. */
+int xrvio_debug_fp64_peak(double *dfma_tflops, double *dmma_tflops);
 
 #ifdef __cplusplus
 }

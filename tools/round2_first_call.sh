@@ -2,7 +2,7 @@
 # One gpurun call that collects everything round 1 left unmeasured:
 #   gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'
 # Outputs under gpurun_out/: gpu_tests.log (every GPU test under its own timeout), bench.json, bench_ba_stress.json,
-# fp64_probe.txt, launches.csv (ncu launch list of the bench command), ncu_solve_large.ncu-rep (+ raw csv).
+# fp64_probe.txt (tools/fp64_probe + the library probe inside bench_ba_stress.json), launches.csv (ncu launch list of the bench command), ncu_solve_large.ncu-rep (+ raw csv).
 mkdir -p gpurun_out
 PER_TEST_TIMEOUT=${PER_TEST_TIMEOUT:-240} bash tools/gpu_tests.sh > gpurun_out/gpu_tests_summary.txt 2>&1
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err

@@ -180,6 +180,13 @@ def last_solve_ms():
     return float(f())
 
 
+def fp64_peak():
+    """(DFMA TFLOP/s, DMMA TFLOP/s) measured on the current device."""
+    a, b = C.c_double(0.0), C.c_double(0.0)
+    lib.check(lib.xrvio_debug_fp64_peak(C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
 def op_marginalize(rig, desc, states, inv_depth, rpe, pre, pre_blocks, marg_frames, marg, n_out):
     out = np.zeros(n_out, np.float64)
     rank = np.zeros(len(desc), np.int32)

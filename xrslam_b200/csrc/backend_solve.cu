@@ -572,6 +572,75 @@ void gram(const double *S, double *A0, int n, int n_priors, size_t stride, cudaS
 
 }  // namespace xvbe
 
+// ---- FP64 peak probe: the denominators of the config-5 roofline (MEASURED_PEAKS.json has no FP64 entry) ----
+#ifdef CUEMU
+extern "C" int xrvio_debug_fp64_peak(double *, double *) { return -1; }      // a rate measured on the emulator means nothing
+#else
+namespace xvbe {
+__global__ void __launch_bounds__(256) fp64_fma_probe_kernel(double *out, int iters, double a, double b) {
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = threadIdx.x + k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = x[k] * a + b;
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += x[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+__global__ void __launch_bounds__(256) fp64_mma_probe_kernel(double *out, int iters, double a, double b) {
+    double c[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { c[k][0] = k; c[k][1] = k + 0.5; }
+    const double fa = a + threadIdx.x * 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dmma_m8n8k4(c[k][0], c[k][1], fa, b);
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r += c[k][0] + c[k][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+}  // namespace xvbe
+
+// Measured FP64 rates of this GPU in TFLOP/s: a register-resident DFMA loop and an mma.sync.m8n8k4.f64 loop on every SM
+// (8 CTAs of 256 threads per SM, CUDA events).  Diagnostics for bench.py --workload ba_stress.
+extern "C" int xrvio_debug_fp64_peak(double *dfma_tflops, double *dmma_tflops) {
+    if (!dfma_tflops || !dmma_tflops) return -1;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return -1;
+    const int grid = sms * 8, iters = 8192;
+    double *out = nullptr;
+    if (cudaMalloc(&out, (size_t)grid * 256 * sizeof(double)) != cudaSuccess) return -1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms = 0.f;
+    int rc = 0;
+    for (int pass = 0; pass < 2; ++pass) {          // pass 0 warms up
+        cudaEventRecord(e0, 0);
+        xvbe::fp64_fma_probe_kernel<<<grid, 256, 0, 0>>>(out, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1, 0);
+        if (cudaEventSynchronize(e1) != cudaSuccess) rc = -1;
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    *dfma_tflops = 2.0 * 8.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+    for (int pass = 0; pass < 2; ++pass) {
+        cudaEventRecord(e0, 0);
+        xvbe::fp64_mma_probe_kernel<<<grid, 256, 0, 0>>>(out, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1, 0);
+        if (cudaEventSynchronize(e1) != cudaSuccess) rc = -1;
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    *dmma_tflops = 2.0 * 8 * 8 * 4 * 4.0 * iters * 8.0 * grid / (ms * 1e-3) / 1e12;     // 4 mma of 8x8x4 per warp and iteration, 8 warps
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    return rc;
+}
+#endif
+
 extern "C" int xrvio_debug_kprof(unsigned long long *out32, int reset) {
     if (cudaMemcpyFromSymbol(out32, xvbe::g_kprof, 32 * sizeof(unsigned long long)) != cudaSuccess) return -1;
     if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(xvbe::g_kprof, z, sizeof(z)); }
