@@ -62,20 +62,28 @@ template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM
         const int cb0 = bj * 16 + g, cb1 = cb0 + 8;      // columns of the two B fragments
         const double *wa0 = P.W + (size_t)ra0 * M, *wa1 = P.W + (size_t)ra1 * M;
         const double *wb0 = P.W + (size_t)cb0 * M, *wb1 = P.W + (size_t)cb1 * M;
-        for (int l0 = 0; l0 < M; l0 += 4) {
-            const int l = l0 + t;
-            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-            if (l < M) {
-                const double ih = ihv[l];
-                if (ra0 < R) a0 = wa0[l];
-                if (ra1 < R) a1 = wa1[l];
-                if (cb0 < R) b0 = wb0[l] * ih;
-                if (cb1 < R) b1 = wb1[l] * ih;
+        // four k-steps per pass: the 16 fragment loads (L2 latency) are issued before the 16 tensor-pipe instructions
+        for (int l0 = 0; l0 < M; l0 += 16) {
+            double a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int l = l0 + 4 * u + t;
+                a0[u] = a1[u] = b0[u] = b1[u] = 0.0;
+                if (l < M) {
+                    const double ih = ihv[l];
+                    if (ra0 < R) a0[u] = wa0[l];
+                    if (ra1 < R) a1[u] = wa1[l];
+                    if (cb0 < R) b0[u] = wb0[l] * ih;
+                    if (cb1 < R) b1[u] = wb1[l] * ih;
+                }
             }
-            dmma_m8n8k4(acc[0][0][0], acc[0][0][1], a0, b0);
-            dmma_m8n8k4(acc[0][1][0], acc[0][1][1], a0, b1);
-            dmma_m8n8k4(acc[1][0][0], acc[1][0][1], a1, b0);
-            dmma_m8n8k4(acc[1][1][0], acc[1][1][1], a1, b1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                dmma_m8n8k4(acc[0][0][0], acc[0][0][1], a0[u], b0[u]);
+                dmma_m8n8k4(acc[0][1][0], acc[0][1][1], a0[u], b1[u]);
+                dmma_m8n8k4(acc[1][0][0], acc[1][0][1], a1[u], b0[u]);
+                dmma_m8n8k4(acc[1][1][0], acc[1][1][1], a1[u], b1[u]);
+            }
         }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr)
@@ -160,20 +168,36 @@ template <class SM> static __device__ void cholesky_global(SM &s, int n, double 
                     if (4 + t < w) a1 = -colp[(4 + t) * SM::NPv + r];
                 }
                 double *row = &s.H[hidx(r < n ? r : n - 1, 0)];
-                for (int tk = 0; tk <= ti; ++tk) {
-                    const int cb = j1 + 8 * tk + g;
-                    double b0 = 0.0, b1 = 0.0;
-                    if (cb < n) {
-                        if (t < w) b0 = colp[t * SM::NPv + cb];
-                        if (4 + t < w) b1 = colp[(4 + t) * SM::NPv + cb];
+                // four tiles per pass: loads of the C tiles and B fragments first, then the tensor-pipe instructions, then the
+                // stores (spelled out so that the L2 round trips of independent tiles overlap)
+                for (int tk0 = 0; tk0 <= ti; tk0 += 4) {
+                    double d0[4], d1[4], b0[4], b1[4];
+                    bool v0[4], v1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int tk = tk0 + u;
+                        const int cb = j1 + 8 * tk + g, c = j1 + 8 * tk + 2 * t;
+                        b0[u] = b1[u] = 0.0;
+                        if (tk <= ti && cb < n) {
+                            if (t < w) b0[u] = colp[t * SM::NPv + cb];
+                            if (4 + t < w) b1[u] = colp[(4 + t) * SM::NPv + cb];
+                        }
+                        v0[u] = tk <= ti && r < n && c <= r;
+                        v1[u] = tk <= ti && r < n && c + 1 <= r;
+                        d0[u] = v0[u] ? row[c] : 0.0;
+                        d1[u] = v1[u] ? row[c + 1] : 0.0;
                     }
-                    const int c = j1 + 8 * tk + 2 * t;
-                    const bool v0 = r < n && c <= r, v1 = r < n && c + 1 <= r;
-                    double d0 = v0 ? row[c] : 0.0, d1 = v1 ? row[c + 1] : 0.0;
-                    dmma_m8n8k4(d0, d1, a0, b0);
-                    dmma_m8n8k4(d0, d1, a1, b1);
-                    if (v0) row[c] = d0;
-                    if (v1) row[c + 1] = d1;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        dmma_m8n8k4(d0[u], d1[u], a0, b0[u]);
+                        dmma_m8n8k4(d0[u], d1[u], a1, b1[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = j1 + 8 * (tk0 + u) + 2 * t;
+                        if (v0[u]) row[c] = d0[u];
+                        if (v1[u]) row[c + 1] = d1[u];
+                    }
                 }
             }
         }
