@@ -162,6 +162,56 @@ static __device__ void prepare_prior(Prob &P, const double *arena, double *St) {
     __syncthreads();
 }
 
+// ---- warp-uniform fast path of the J^T J accumulation (large windows) ----
+// When the 32 observations of a warp share (target, reference) -- the normal case in a 30-keyframe x 2000-landmark window --
+// the 90 block entries (tt 21, g_t 6, tr 36, rr 21, g_r 6) are summed by three reduce-scatters of 32 values (31 shuffle rounds
+// each, lane k ends up with entry 32 c + k) instead of 90 segmented sums of 5 rounds; every lane then adds its own entries.
+__device__ __forceinline__ void tri_decode(int t, int &i, int &j) {
+    i = (t >= 15) ? 5 : (t >= 10) ? 4 : (t >= 6) ? 3 : (t >= 3) ? 2 : (t >= 1) ? 1 : 0;
+    j = t - i * (i + 1) / 2;
+}
+__device__ __forceinline__ double jtj_entry(const RpeEval &e, int idx) {
+    int i, j;
+    if (idx < 21) { tri_decode(idx, i, j); return e.Jt[i] * e.Jt[j] + e.Jt[6 + i] * e.Jt[6 + j]; }
+    if (idx < 27) { i = idx - 21; return e.Jt[i] * e.r[0] + e.Jt[6 + i] * e.r[1]; }
+    if (idx < 63) { i = (idx - 27) / 6; j = (idx - 27) % 6; return e.Jt[i] * e.Jr[j] + e.Jt[6 + i] * e.Jr[6 + j]; }
+    if (idx < 84) { tri_decode(idx - 63, i, j); return e.Jr[i] * e.Jr[j] + e.Jr[6 + i] * e.Jr[6 + j]; }
+    if (idx < 90) { i = idx - 84; return e.Jr[i] * e.r[0] + e.Jr[6 + i] * e.r[1]; }
+    return 0.0;
+}
+// v[0] of lane k becomes the sum over all lanes of v[k]
+__device__ __forceinline__ double reduce_scatter32(double (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const double send = upper ? v[i] : v[i + o];
+            const double keep = upper ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+template <class SM> __device__ __forceinline__ void jtj_uniform_warp(SM &s, const RpeEval &e, int ts, int rs, int lane) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = jtj_entry(e, 32 * c + k);
+        const double sum = reduce_scatter32(v, lane);
+        const int idx = 32 * c + lane;
+        int i, j;
+        if (idx < 21) { tri_decode(idx, i, j); atomicAdd(&s.H[hidx(15 * ts + i, 15 * ts + j)], sum); }
+        else if (idx < 27) atomicAdd(&s.g[15 * ts + idx - 21], sum);
+        else if (idx < 63) {
+            const int a = 15 * ts + (idx - 27) / 6, b = 15 * rs + (idx - 27) % 6;
+            atomicAdd(&s.H[a > b ? hidx(a, b) : hidx(b, a)], sum);
+        } else if (idx < 84) { tri_decode(idx - 63, i, j); atomicAdd(&s.H[hidx(15 * rs + i, 15 * rs + j)], sum); }
+        else if (idx < 90) atomicAdd(&s.g[15 * rs + idx - 84], sum);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Residual (+ Jacobian) evaluation at S (= xs or cs) / inv (= inv_x or inv_c).  Returns the cost.
 // With want_jac the unscaled H (pose/motion block, packed in shared memory), g, W, h_ll, g_l are
@@ -214,8 +264,14 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
             for (int k = 0; k < 12; ++k) e.Jt[k] *= w;
             if (!prior) { for (int k = 0; k < 12; ++k) e.Jr[k] *= w; e.Jl[0] *= w; e.Jl[1] *= w; }
         }
+        bool fast = false;
+        if constexpr (!SM::kSharedH) {
+            const int ts0 = __shfl_sync(0xffffffffu, ts, 0), rs0 = __shfl_sync(0xffffffffu, rs, 0);
+            fast = __all_sync(0xffffffffu, valid && !prior && tf && rf && ts == ts0 && rs == rs0 && ts != rs) != 0;
+            if (fast) jtj_uniform_warp(s, e, ts, rs, lane);
+        }
         // --- (tgt,tgt) block + g_tgt : segments keyed by tgt ---
-        {
+        if (!fast) {
             const int key = (valid && tf) ? ts : -1 - lane;
             const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);   // unconditional: every lane must take part
             const bool head = (lane == 0) || (key_prev != key);
@@ -240,6 +296,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
             const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);   // unconditional: every lane must take part
             const bool head = (lane == 0) || (key_prev != key);
             const bool act_tr = valid && tf && rf, act_rr = valid && rf;
+            if (!fast) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
 #pragma unroll
@@ -260,6 +317,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
                 double gv = act_rr ? (e.Jr[i] * e.r[0] + e.Jr[6 + i] * e.r[1]) : 0.0;
                 gv = seg_sum(gv, key, lane);
                 if (act_rr && head) atomicAdd(&s.g[15 * rs + i], gv);
+            }
             }
             // landmark column: h_ll, g_l, W (W[slot][k][l], l fastest)
             if (valid && lf) {
