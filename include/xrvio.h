@@ -215,6 +215,8 @@ typedef struct xrvio_stats {
     long long h2d_bytes, d2h_bytes;
     long long window_solves, localize_solves, subwindow_solves, marginalizations;
     double last_window_cost_initial, last_window_cost_final;
+    long long window_iterations;        /* trust-region iterations (accepted + rejected) summed over the refine_window solves */
+    long long window_at_limit;          /* refine_window solves that ended at solver_iteration_limit (all of them) */
 } xrvio_stats;
 
 /* Outcome of the initializer attempts of a session (core/initializer.cpp:78-571).  last_fail: 0 initialised (or not yet
@@ -242,6 +244,11 @@ int xrvio_get_pose(xrvio_ctx *ctx, int session, xrvio_pose *pose);          /* o
 int xrvio_get_latest_state(xrvio_ctx *ctx, int session, double *t, double state16[16]);   /* last optimised frame */
 int xrvio_get_state(xrvio_ctx *ctx, int session);                           /* XRVIO_STATE_* or < 0 */
 int xrvio_get_landmarks(xrvio_ctx *ctx, int session, double *xyz, int capacity);   /* returns count */
+/* Keypoints of the newest frame of the session's front-end map (what FeatureTracker::work leaves behind, feature_tracker.cpp:
+ * 128-130): pixel position (apply_k of the bearing), id of the track through it (-1: none yet) and that track's length in
+ * frames.  Returns the number of keypoints (may exceed capacity; only capacity entries are written).  The reference's
+ * XRSLAM_RESULT_FEATURES is declared but empty (XRSLAMManager.cpp:217); this is the data it would carry. */
+int xrvio_get_features(xrvio_ctx *ctx, int session, double *xy, long long *track_id, int *track_len, int capacity);
 int xrvio_get_init_info(xrvio_ctx *ctx, int session, xrvio_init_info *out);
 int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *stats);
 /* Per-kernel-family device time measured with CUDA events on the launch stream (off by default).

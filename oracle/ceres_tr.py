@@ -13,6 +13,39 @@ The linear solve is done on the full normal equations with a dense Cholesky; Cer
 SPARSE_SCHUR eliminates the inverse-depth blocks first, which is the same linear system
 solved exactly (differs in round-off only).
 
+Why a window BA runs to the iteration limit -- the ordering argument, with the Ceres 1.14 function names.
+The preintegration factor reads the linearisation bias from USER memory, not from the parameter block:
+    dbg = bg_i(parameter) - frame_i->motion.bg,  dba likewise          (preintegration_factor.h:38-39,50-51)
+and the reference sets update_state_every_iteration = true (solver.cpp:187), which installs Ceres' StateUpdatingCallback.
+Per iteration TrustRegionMinimizer::Minimize (trust_region_minimizer.cc) runs, in this order,
+    FinalizeIterationAndCheckIfMinimizerCanContinue()   if the previous step was successful and x_cost_ < minimum_cost_:
+                                                        parameters_ = x_;  then RunCallbacks() -> StateUpdatingCallback:
+                                                        if (summary.step_is_successful) StateVectorToParameterBlocks(parameters_)
+                                                        + CopyParameterBlockStateToUserState()      [user memory := x]
+    ComputeTrustRegionStep()                            DoglegStrategy::ComputeStep on the Jacobian of the LAST accepted point
+    ComputeCandidatePointAndEvaluateCost()              evaluator_->Evaluate(candidate_x_, &candidate_cost_, no Jacobian)
+    ParameterToleranceReached() / FunctionToleranceReached()
+    IsStepSuccessful() ? HandleSuccessfulStep() : HandleUnsuccessfulStep()
+and HandleSuccessfulStep() does x_ = candidate_x_ followed by EvaluateGradientAndJacobian() IMMEDIATELY, i.e. BEFORE the
+callback of the next FinalizeIteration... has copied x_ to user memory.  Consequences for a window BA whose first step is
+accepted at iteration 1:
+  (1) x_cost_ and the Jacobian of the new point are evaluated with user memory still holding the PREVIOUS iterate, so the
+      preintegration residuals see dbg = bg_new - bg_old (the bias-corrected delta, the small cost);
+  (2) then the callback rewrites user memory to the new iterate; every later candidate is evaluated with
+      dbg = bg_cand - bg_new ~ 0 against deltas that were integrated with the bias at solve start
+      (sliding_window_tracker.cpp:315-317), i.e. WITHOUT the first-order correction the accepted cost had -- the same point
+      now costs more than x_cost_;
+  (3) so relative_decrease = (x_cost_ - candidate_cost_) / model_cost_change is negative for every candidate, however small
+      the radius: HandleUnsuccessfulStep() halves the radius (1e4 -> 1e4 / 2^29, far above min_trust_region_radius 1e-32),
+      |cost_change| stays above function_tolerance * x_cost_ and the step norm above the parameter tolerance, and the solve
+      ends at max_num_iterations = 30 (solver.cpp:181) with the iterate of iteration 1.
+`solve` below reproduces (1)-(3) through `finalize` (callback order) and by evaluating the accepted point before it; the CUDA
+solver does the same (backend_solve.cu, "HandleSuccessfulStep: user memory still holds the previous iterate").  That the
+behaviour really occurs on every window BA of several streams is asserted by tests/test_oracle.py::
+test_window_ba_runs_to_the_iteration_limit (oracle, 3 streams) and tests/test_gpu_pipeline.py::
+test_window_solves_hit_the_iteration_limit (CUDA, xrvio_stats.window_iterations / window_at_limit).  It remains an argument
+about remembered third-party source: Ceres is not available offline, which is why the loop stays "parity unpinned".
+
 Oracle code: test infrastructure only.
 """
 import numpy as np
@@ -442,7 +475,9 @@ def solve(pb, verbose=False):
         c_states, c_invd = _plus(pb, lay, x_states, x_invd, delta)
         cand_cost, _, _, _ = evaluate(pb, lay, c_states, c_invd, False)
         if not np.isfinite(cand_cost):
-            cand_cost = x_cost
+            # ComputeCandidatePointAndEvaluateCost: a failed evaluation (non-finite residuals) leaves candidate_cost =
+            # numeric_limits<double>::max(), so the step is rejected and the radius halved instead of ending the solve
+            cand_cost = np.finfo(np.float64).max
         # ParameterToleranceReached
         it['step_norm'] = float(np.linalg.norm(_ambient(pb, lay, x_states, x_invd) -
                                                _ambient(pb, lay, c_states, c_invd)))

@@ -851,7 +851,7 @@ class Session:
         m.attach_frame(frame)
         max_frames = cfg.max_frames if is_init else cfg.max_init_frames
         lid = self.swt_latest[1] if is_init else None
-        while m.frame_num() > max_frames and (lid is not None and m.frames[0].id < lid):
+        while m.frame_num() > max_frames and (lid is None or m.frames[0].id < lid):      # nil() == SIZE_MAX before init
             m.erase_frame(0)
         self.processed += 1
         self.frontend_work(m.frames[-1].id)

@@ -144,7 +144,7 @@ class DatasetReader {
         all_data.pop_front(); image_data.pop_front();
         GrayImage raw, img;
         if (!read_gray_image(item.second, raw, err)) return {item.first, GrayImage()};
-        if (config.distortion_flag) {
+        if (config.distortion_flag && !skip_undistortion) {
             if (undistorter.width != raw.width || undistorter.height != raw.height)
                 undistorter.build(raw.width, raw.height, config.K, config.D, model);
             undistorter.apply(raw, img);
@@ -153,6 +153,7 @@ class DatasetReader {
         return {item.first, std::move(img)};
     }
     void get_image_resolution(int &w, int &h) const { w = image_width; h = image_height; }
+    bool skip_undistortion = false;      // the library undistorts on the GPU (player --device-undistort)
     size_t remaining() const { return all_data.size(); }
 
     static std::unique_ptr<DatasetReader> create_reader(const std::string &uri, const std::string &device_yaml);     // dataset_reader.cpp:18-36

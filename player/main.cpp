@@ -13,6 +13,9 @@ using namespace xplayer;
 
 int main(int argc, char **argv) {
     std::string slam_config, device_config, license, csv_output, tum_output, input;
+    // --device-undistort: hand the RAW camera frames to the library, which undistorts them on the GPU with the readers' own
+    // arithmetic (xrvio_params.distortion_model, undistort_kernel) instead of on the CPU in the reader
+    bool device_undistort = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto val = [&](std::string &dst) { if (i + 1 < argc) dst = argv[++i]; };
@@ -22,12 +25,14 @@ int main(int argc, char **argv) {
         else if (a == "--csv") val(csv_output);
         else if (a == "--tum") val(tum_output);
         else if (a == "-p" || a == "--play") {}
+        else if (a == "--device-undistort") device_undistort = true;
         else input = a;
     }
     if (slam_config.empty() || device_config.empty() || input.empty()) {
         std::fprintf(stderr, "usage: %s -sc slam.yaml -dc device.yaml [--tum file] [--csv file] euroc://path | tum://path\n", argv[0]);
         return EXIT_FAILURE;
     }
+    if (device_undistort) setenv("XRVIO_DEVICE_UNDISTORT", "1", 1);      // read by XRSLAMCreate (xrslam_shim.cu)
     void *config = nullptr;
     const int create_succ = XRSLAMCreate(slam_config.c_str(), device_config.c_str(), license.c_str(), "XRSLAM PC", &config);
     std::cout << "create SLAM success: " << create_succ << std::endl;
@@ -40,6 +45,7 @@ int main(int argc, char **argv) {
     } catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); XRSLAMDestroy(); return EXIT_FAILURE; }
 
     std::unique_ptr<DatasetReader> reader = DatasetReader::create_reader(input, device_config);
+    if (reader && device_undistort) reader->skip_undistortion = true;
     if (!reader) { std::fprintf(stderr, "Cannot open \"%s\"\n", input.c_str()); XRSLAMDestroy(); return EXIT_FAILURE; }
 
     bool has_gyroscope = false, has_accelerometer = false;

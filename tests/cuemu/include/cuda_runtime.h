@@ -61,6 +61,7 @@ cudaError_t cudaStreamDestroy(cudaStream_t st);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaSetDevice(int d);
 cudaError_t cudaGetDeviceCount(int *n);
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaGetLastError();
 const char *cudaGetErrorString(cudaError_t e);
 cudaError_t cudaEventCreate(cudaEvent_t *e);

@@ -60,28 +60,84 @@ def test_long_stream_ate_vs_oracle(xrvio, golden_dir):
     ctx.close()
 
 
-@pytest.mark.skipif(os.environ.get('XRVIO_LONG') != '1', reason='~4 min of CPU frame rendering for 5 s of GPU work; set XRVIO_LONG=1')
-def test_one_minute_stream_config2(xrvio, golden_dir):
+_EMU_SHORT = os.environ.get('XRVIO_EMU') == '1' and os.environ.get('XRVIO_LONG') != '1'
+
+
+@pytest.fixture(scope='module')
+def stream7_frames():
+    """The 1200 frames of stream 7 (BASELINE config 2: 60 s at 20 Hz), rendered once by a pool of host workers."""
+    from oracle.synth import render_frames
+    return render_frames(Stream(7), 1200)
+
+
+def _traj(outs):
+    return np.array([[t] + list(q) + list(p) for (t, q, p) in outs])
+
+
+@pytest.mark.skipif(_EMU_SHORT, reason='26 min on the SIMT emulator; set XRVIO_LONG=1')
+def test_one_minute_stream_config2(xrvio, golden_dir, stream7_frames):
     """BASELINE config 2: one stream, 60 s = 1200 frames, trajectory vs the oracle after SE3 alignment.
     Two floating-point implementations of this pipeline agree to < 1e-4 m until, somewhere, a discrete front-end decision
     (a KLT back-check at its 0.5 px gate, a landmark at a validity gate) falls on different sides; from there on they are
-    two equally valid estimates a few millimetres apart (on the SIMT emulator: < 1e-4 m for 37 s, one observation set differs
-    at frame 751, ATE 3.3 mm over the minute, against 85 mm of drift from ground truth).  So the bar of BASELINE.json
-    (1e-3 m) is asserted on the first 140 frames and two centimetres on the whole minute.  Opt-in (XRVIO_LONG=1): rendering
-    the 1200 synthetic frames on the CPU takes minutes; the emulator run of this test passes (26 min)."""
+    two equally valid estimates a few millimetres apart (DESIGN.md 4c names the decision: tools/bisect_config2.py).  So the
+    bar of BASELINE.json (1e-3 m) is asserted up to the last frame before that decision and two centimetres on the whole
+    minute; both numbers are printed for the record."""
     ref = np.load(os.path.join(golden_dir, 'stream7_traj1200.npz'))['traj']
     s = Stream(7)
-    ctx, outs = drive.run_streams_cuda([s], 1200)
-    got = np.array([[t] + list(q) + list(p) for (t, q, p) in outs[0]])
+    ctx, outs = drive.run_streams_cuda([s], 1200, frames=[stream7_frames])
+    got = _traj(outs[0])
     assert got.shape == ref.shape and np.allclose(got[:, 0], ref[:, 0])
+    raw = np.linalg.norm(got[:, 5:8] - ref[:, 5:8], axis=1)
+    first_off = int(np.argmax(raw > 1e-3)) if (raw > 1e-3).any() else len(raw)
+    ate_all = _ate(ref[:, 5:8], got[:, 5:8])
+    print('config 2: ATE vs oracle over 1200 frames %.3e m; first pose more than 1e-3 m off at index %d of %d (t = %.2f s); '
+          'ATE up to there %.3e m' % (ate_all, first_off, len(raw), got[min(first_off, len(raw) - 1), 0], _ate(ref[:max(first_off, 10), 5:8], got[:max(first_off, 10), 5:8])))
     head = 104                                  # poses of the first 140 frames
     assert _ate(ref[:head, 5:8], got[:head, 5:8]) <= 1e-3
-    assert _ate(ref[:, 5:8], got[:, 5:8]) <= 2e-2
+    assert first_off >= 600, first_off          # at least 30 s of sub-millimetre agreement (observed: 37 s)
+    assert _ate(ref[:first_off, 5:8], got[:first_off, 5:8]) <= 1e-3
+    assert ate_all <= 2e-2
     gt = np.array([s.gt_state(t)[1] for t in got[:, 0]])
     assert abs(_ate(gt, got[:, 5:8]) - _ate(gt, ref[:, 5:8])) < 2e-2 and _ate(gt, got[:, 5:8]) < 0.1
     st = ctx.stats()
     assert st['window_solves'] >= 250 and st['marginalizations'] >= 250
     ctx.close()
+
+
+@pytest.mark.skipif(_EMU_SHORT, reason='long stream; set XRVIO_LONG=1 on the emulator')
+def test_prior_form_and_essential_ransac_long_stream(xrvio, stream7_frames):
+    """640 frames (32 s, ~150 marginalisations) of one stream under the three settings that VERDICT r1 asked to be held against
+    each other: the session default, the other form of the marginalisation prior (xrvio_params.prior_eigen_form: eigen form
+    sqrt(lambda) V^T with the 1e-8 cut of marginalization_factor.h:440-454 vs rank-revealing Cholesky factor of the same
+    matrix) and the per-frame 5-point essential RANSAC of frame.cpp:108-114 switched on.  S^T S, S^T infovec and |infovec|^2
+    are what the solver reads from a prior and they agree between the forms to round-off, so the trajectories must too."""
+    s = Stream(7)
+    n = 640
+    frames = [stream7_frames[:n]]
+
+    def run(**over):
+        p = drive.params_for(s)
+        for k, v in over.items():
+            p[k] = v
+        ctx = xrvio.Context(p, 1)
+        ctx, outs = drive.run_streams_cuda([s], n, frames=frames, ctx=ctx)
+        st = ctx.stats()
+        info = ctx.get_init_info(0)
+        ctx.close()
+        return _traj(outs[0]), st, info
+    base, st0, _ = run()
+    assert st0['marginalizations'] >= 120
+    default_form = int(drive.params_for(s)['prior_eigen_form'][0])
+    other, st1, _ = run(prior_eigen_form=1 - default_form)
+    ess, st2, info2 = run(essential_ransac=1)
+    assert other.shape == base.shape == ess.shape
+    d_form = np.linalg.norm(other[:, 5:8] - base[:, 5:8], axis=1)
+    d_ess = np.linalg.norm(ess[:, 5:8] - base[:, 5:8], axis=1)
+    print('prior form %d vs %d over %d frames: max |dp| %.3e m (median %.3e); essential RANSAC on vs off: max |dp| %.3e m, %d matches rejected'
+          % (default_form, 1 - default_form, n, d_form.max(), np.median(d_form), d_ess.max(), int(info2['essential_rejected'])))
+    assert d_form.max() <= 1e-6, d_form.max()
+    assert d_ess.max() <= 1e-6 and int(info2['essential_rejected']) == 0
+    assert st1['window_solves'] == st0['window_solves'] == st2['window_solves']
 
 
 def test_pause_stream_no_translation_branches(xrvio, golden_dir):
@@ -172,4 +228,19 @@ def test_xrslam_c_abi_shim_player_protocol(xrvio, golden_dir):
     got = np.array(poses)
     assert got.shape == ref.shape and np.allclose(got[:, 0], ref[:, 0])
     assert np.abs(got[:, 1:] - ref[:, 1:]).max() < 1e-6
+    ctx.close()
+
+
+def test_window_solves_hit_the_iteration_limit(xrvio):
+    """SURVEY.md D10 on the CUDA path (argument: oracle/ceres_tr.py header): every refine_window solve of three different
+    streams runs its 30 trust-region iterations -- one or two accepted steps, then only rejections -- like the oracle's
+    (tests/test_oracle.py::test_window_ba_runs_to_the_iteration_limit)."""
+    streams = [Stream(3), Stream(7), Stream(11)]
+    ctx, _ = drive.run_streams_cuda(streams, 60, collect=False)
+    st = ctx.stats()
+    # the first window solve of a session is the bootstrap BA (counted in window_solves, not a refine_window)
+    refine = int(st['window_solves']) - len(streams)
+    assert refine >= 12
+    assert int(st['window_at_limit']) == refine
+    assert int(st['window_iterations']) == 30 * refine
     ctx.close()

@@ -266,3 +266,26 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.hpp', '.inl', '.h')):
                 txt = open(os.path.join(dp, f), errors='ignore').read()
                 assert 'import oracle' not in txt and 'from oracle' not in txt and 'oracle/' not in txt, f
+
+
+def test_window_ba_runs_to_the_iteration_limit():
+    """D10 (oracle/ceres_tr.py header): after the first accepted step of a window BA the StateUpdatingCallback rewrites the
+    linearisation bias in user memory, every later candidate is rejected and the solve ends at max_num_iterations with the
+    iterate of the first accepted step.  Asserted on every window BA of three different streams."""
+    from oracle.synth import Stream
+    from oracle.pipeline import run_stream
+    seen = 0
+    for seed in (3, 7, 11):
+        rec = []
+        run_stream(Stream(seed), 48, recorder=lambda kind, when, pb, summ=None: rec.append((kind, summ)) if when == 'post' else None)
+        wins = [s for k, s in rec if k == 'window']
+        assert len(wins) >= 2, (seed, [k for k, _ in rec])
+        for s in wins:
+            assert s.termination == 'max iterations' and len(s.iterations) == 31, (seed, s.termination, len(s.iterations))
+            ok = [it['iteration'] for it in s.iterations if it['successful']]
+            assert ok[0] == 0 and len(ok) >= 2 and max(ok) <= 3, (seed, ok)       # accepted steps only at the very start
+            tail = s.iterations[max(ok) + 1:]
+            assert all((not it['successful']) and it['cost'] > s.final_cost for it in tail)
+            assert tail[-1]['radius'] < tail[0]['radius'] * 2.0 ** -(len(tail) - 2)   # halved at every rejection
+        seen += len(wins)
+    assert seen >= 6

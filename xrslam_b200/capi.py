@@ -226,7 +226,8 @@ init_info_dtype = np.dtype([("attempts", "i4"), ("last_fail", "i4"), ("matches",
                             ("essential_rejected", "i4"), ("parallax", "f8"), ("scale", "f8")], align=True)
 stats_dtype = np.dtype([("frames_processed", "i8"), ("kernels_launched", "i8"), ("h2d_bytes", "i8"), ("d2h_bytes", "i8"),
                         ("window_solves", "i8"), ("localize_solves", "i8"), ("subwindow_solves", "i8"), ("marginalizations", "i8"),
-                        ("last_window_cost_initial", "f8"), ("last_window_cost_final", "f8")], align=True)
+                        ("last_window_cost_initial", "f8"), ("last_window_cost_final", "f8"),
+                        ("window_iterations", "i8"), ("window_at_limit", "i8")], align=True)
 
 
 def default_params(width=640, height=480):
@@ -311,6 +312,15 @@ class Context:
         ms = np.zeros(32)
         lib.xrvio_get_phase_times(self._h, _p(ms), 32)
         return ms
+
+    def get_features(self, session):
+        """(xy [n,2], track ids [n], track lengths [n]) of the newest front-end frame."""
+        n = lib.xrvio_get_features(self._h, int(session), None, None, None, 0)
+        if n < 0:
+            lib.check(n)
+        xy = np.zeros((max(n, 1), 2)); tid = np.zeros(max(n, 1), np.int64); tl = np.zeros(max(n, 1), np.int32)
+        n = lib.xrvio_get_features(self._h, int(session), _p(xy), _p(tid), _p(tl), int(n))
+        return xy[:n], tid[:n], tl[:n]
 
     def get_init_info(self, session):
         s = np.zeros(1, init_info_dtype)

@@ -7,6 +7,7 @@
 // which yields rows sqrt(lambda_i) v_i^T directly (sign / order of rows is immaterial to the
 // prior's cost and Jacobian).  Also emits A0 = S^T S for the solver.
 #include "solve_core.cuh"
+#include "launch_attr.cuh"
 
 namespace xvbe {
 using namespace xv;
@@ -276,11 +277,8 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
 
 void marginalize(const MargBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
     if (n_problems <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    xv::ensure_dynamic_smem(marg_kernel, (int)sizeof(Smem), attr_done);
     marg_kernel<<<n_problems, ST, sizeof(Smem), st>>>(b, rig);
 }
 

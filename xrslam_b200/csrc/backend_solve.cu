@@ -1,6 +1,7 @@
 // K7-K11 driver: the Ceres-1.14-style trust-region loop around solve_core.cuh (see there).
 #include "solve_core.cuh"
 #include "solve_large.cuh"
+#include "launch_attr.cuh"
 
 namespace xvbe {
 using namespace xv;
@@ -471,7 +472,9 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
         make_candidate(P, s, c1, c2);
         kp.mark(17);
         double cand_cost = evaluate(P, s, s.cs, P.inv_c, rg, false, true, &kp);
-        if (!isfinite(cand_cost)) cand_cost = x_cost;
+        // a failed evaluation leaves candidate_cost = DBL_MAX (ComputeCandidatePointAndEvaluateCost): the step is rejected and
+        // the radius halved; it must not look like "function tolerance reached"
+        if (!isfinite(cand_cost)) cand_cost = DBL_MAX;
         const double step_norm = sqrt(ambient_sq(P, s, s.xs, s.cs, P.inv_x, P.inv_c));
         kp.mark(21);
         if (step_norm <= kParamTol * (x_norm + kParamTol)) { termination = 4; if (tid == 0 && n_rec < kMaxIter) out.cost_trace[n_rec] = it_cost; n_rec++; break; }
@@ -535,21 +538,15 @@ size_t solve_large_scratch_doubles(int n_active, int n_lm_free, int n_pre, int m
 
 void solve_large(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
     if (n_problems <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(solve_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemL));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    xv::ensure_dynamic_smem(solve_large_kernel, (int)sizeof(SmemL), attr_done);
     solve_large_kernel<<<n_problems, ST, sizeof(SmemL), st>>>(b, rig);
 }
 
 void solve(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
     if (n_problems <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    xv::ensure_dynamic_smem(solve_kernel, (int)sizeof(Smem), attr_done);
     solve_kernel<<<n_problems, ST, sizeof(Smem), st>>>(b, rig);
 }
 

@@ -934,6 +934,21 @@ int xrvio_get_latest_state(xrvio_ctx *ctx, int session, double *t, double state1
 int xrvio_get_state(xrvio_ctx *ctx, int session) { LANE_OF(session, l, i); return lane_get_state(l, i); }
 int xrvio_get_landmarks(xrvio_ctx *ctx, int session, double *xyz, int capacity) { LANE_OF(session, l, i); return lane_get_landmarks(l, i, xyz, capacity); }
 
+int xrvio_get_features(xrvio_ctx *ctx, int session, double *xy, long long *track_id, int *track_len, int capacity) {
+    LANE_OF(session, l, i);
+    Session &s = l->ses[i];
+    if (s.ft_map.frame_num() == 0) return 0;
+    const Frame *f = s.ft_map.frames.back().get();
+    const int n = (int)f->keypoint_num();
+    for (int k = 0; k < n && k < capacity; ++k) {
+        if (xy) apply_k(f->bearings[k], l->K, xy + 2 * k);
+        const Track *t = f->tracks[k];
+        if (track_id) track_id[k] = t ? t->id : -1;
+        if (track_len) track_len[k] = t ? (int)t->keypoint_num() : 0;
+    }
+    return n;
+}
+
 int xrvio_get_init_info(xrvio_ctx *ctx, int session, xrvio_init_info *out) {
     LANE_OF(session, l, i);
     if (!out) { xrvio_set_error("xrvio_get_init_info: null output"); return XRVIO_ERR_ARG; }
@@ -951,6 +966,7 @@ int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *st) {
         st->frames_processed += a.frames_processed; st->kernels_launched += a.kernels_launched; st->h2d_bytes += a.h2d_bytes; st->d2h_bytes += a.d2h_bytes;
         st->window_solves += a.window_solves; st->localize_solves += a.localize_solves; st->subwindow_solves += a.subwindow_solves;
         st->marginalizations += a.marginalizations;
+        st->window_iterations += a.window_iterations; st->window_at_limit += a.window_at_limit;
         if (a.last_window_cost_initial != 0) { st->last_window_cost_initial = a.last_window_cost_initial; st->last_window_cost_final = a.last_window_cost_final; }
     }
     return XRVIO_OK;

@@ -2,6 +2,7 @@
 // arithmetic of CLAHE interpolation, Harris and LK mirrors OpenCV's scalar code, which is not
 // FMA-contracted in its SSE3 baseline build.
 #include "frontend.cuh"
+#include "launch_attr.cuh"
 #include <cfloat>
 #include <cmath>
 
@@ -782,12 +783,9 @@ __global__ void __launch_bounds__(32) poisson_kernel(const double *__restrict__ 
 
 void poisson_filter(const double *pts, const int *n_preset, const int *n_total, const uint8_t *veto, uint8_t *keep,
                     int n, double radius, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<unsigned long long> attr_done{0};
     size_t smem = (size_t)PG_W * PG_H * sizeof(short);
-    if (!attr_set) {
-        cudaFuncSetAttribute(poisson_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    xv::ensure_dynamic_smem(poisson_kernel, (int)smem, attr_done);
     poisson_kernel<<<n, 32, smem, st>>>(pts, n_preset, n_total, veto, keep, radius);
 }
 

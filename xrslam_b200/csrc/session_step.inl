@@ -292,7 +292,9 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         const bool is_init = s.has_swt_latest;
         s.ft_map.attach_frame(std::move(s.cur));
         const size_t max_frames = is_init ? c->prm.max_frames : c->prm.max_init_frames;
-        while (s.ft_map.frame_num() > max_frames && is_init && s.ft_map.frames[0]->id < s.swt_frame_id) {
+        // before initialisation latest_optimized_frame_id is nil() == SIZE_MAX, so the id test is true and the map is capped at
+        // max_init_frames (feature_tracker.cpp:46,132-135)
+        while (s.ft_map.frame_num() > max_frames && (!is_init || s.ft_map.frames[0]->id < s.swt_frame_id)) {
             map_untrack_frame(&s.ft_map, s.ft_map.frames[0].get(), c->rig);
             s.ft_map.detach_frame(0);
         }
@@ -733,6 +735,8 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         if (sp->prob2 >= 0 && sp->is_keyframe) {
             c->stats.last_window_cost_initial = c->sout.h[sp->prob2].initial_cost;
             c->stats.last_window_cost_final = c->sout.h[sp->prob2].final_cost;
+            c->stats.window_iterations += c->sout.h[sp->prob2].iterations - 1;       // the trace also holds iteration 0
+            c->stats.window_at_limit += c->sout.h[sp->prob2].termination == 0 ? 1 : 0;
         }
     c->stats.window_solves += n_win; c->stats.localize_solves += n_loc; c->stats.subwindow_solves += n_sub;
     pt.next(21);

@@ -30,6 +30,7 @@ struct Manager {
     bool has_image = false;
     std::mutex input_mutex;
     XRSLAMPose last_pose{};
+    int last_rc = 0;
     char version[32] = "xrvio-b200 0.1";
 };
 Manager *g_mgr = nullptr;
@@ -74,8 +75,12 @@ void track_imu(Manager *m, double t, const double w[3], const double a[3]) {
     xrvio_imu smp;
     smp.t = t;
     for (int k = 0; k < 3; ++k) { smp.w[k] = w[k]; smp.a[k] = a[k]; }
-    xrvio_push_imu(m->ctx, &s, &smp, 1);
-    xrvio_step(m->ctx);        // Worker::resume runs the workers inline in the PC build (utility/worker.h:35-42)
+    // Worker::resume runs the workers inline in the PC build (utility/worker.h:35-42).  The reference's entry points return
+    // void, so an error can only be logged; it is logged once per kind so a broken stream does not flood stderr.
+    int rc = xrvio_push_imu(m->ctx, &s, &smp, 1);
+    if (rc == XRVIO_OK) rc = xrvio_step(m->ctx);
+    if (rc != XRVIO_OK && rc != m->last_rc) std::fprintf(stderr, "XRSLAM: tracking step failed (%d): %s\n", rc, xrvio_last_error());
+    m->last_rc = rc;
 }
 
 // detail.cpp:46-70
@@ -120,6 +125,20 @@ void track_accelerometer(Manager *m, double t, double x, double y, double z) {
     }
 }
 
+// (q, p) o (qx, px): q * qx, p + q * px  (quaternions xyzw)
+void compose_pose(const double q[4], const double p[3], const double qx[4], const double px[3], double qo[4], double po[3]) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    qo[0] = w * qx[0] + x * qx[3] + y * qx[2] - z * qx[1];
+    qo[1] = w * qx[1] - x * qx[2] + y * qx[3] + z * qx[0];
+    qo[2] = w * qx[2] + x * qx[1] - y * qx[0] + z * qx[3];
+    qo[3] = w * qx[3] - x * qx[0] - y * qx[1] - z * qx[2];
+    // rotate px by q: v + 2 w (u x v) + 2 u x (u x v)
+    const double cx = y * px[2] - z * px[1], cy = z * px[0] - x * px[2], cz = x * px[1] - y * px[0];
+    po[0] = p[0] + px[0] + 2.0 * (w * cx + y * cz - z * cy);
+    po[1] = p[1] + px[1] + 2.0 * (w * cy + z * cx - x * cz);
+    po[2] = p[2] + px[2] + 2.0 * (w * cz + x * cy - y * cx);
+}
+
 }  // namespace
 
 extern "C" {
@@ -148,6 +167,18 @@ int XRSLAMCreate(const char *slam_config_path, const char *device_config_path, c
         size_t c0 = dev.find("cam0:");
         if (c0 != std::string::npos && numbers_after(dev, "noise", 4, v, dev.find("camera_readout_time", c0))) { p.keypoint_cov[0] = v[0]; p.keypoint_cov[1] = v[3]; }
     }
+    {   // Player option --device-undistort: the caller pushes RAW frames and the library runs the reader's undistortion
+        // (euroc_dataset_reader.cpp:62-72 radtan / tum_dataset_reader.cpp:62-76 equidistant) as a CUDA kernel before CLAHE
+        const char *du = std::getenv("XRVIO_DEVICE_UNDISTORT");
+        size_t c0 = dev.find("cam0:");
+        if (du && du[0] == '1' && c0 != std::string::npos && numbers_after(dev, "camera_distortion_flag", 1, v, c0) && v[0] != 0 &&
+            numbers_after(dev, "distortion", 4, v, c0)) {
+            for (int k = 0; k < 4; ++k) p.distortion[k] = v[k];
+            const size_t dm = dev.find("distortion_model:", c0);
+            const bool equi = dm != std::string::npos && dev.compare(dm + 17, 12, " equidistant") == 0;
+            p.distortion_model = equi ? XRVIO_DISTORTION_EQUIDISTANT : XRVIO_DISTORTION_RADTAN;
+        }
+    }
     if (numbers_after(slam, "q_bo", 4, v)) for (int k = 0; k < 4; ++k) p.q_bo[k] = v[k];
     if (numbers_after(slam, "p_bo", 3, v)) for (int k = 0; k < 3; ++k) p.p_bo[k] = v[k];
     if (numbers_after(slam, "size", 1, v)) p.sliding_window_size = (int)v[0];
@@ -158,6 +189,7 @@ int XRSLAMCreate(const char *slam_config_path, const char *device_config_path, c
     if (numbers_after(slam, "max_init_frames", 1, v)) p.max_init_frames = (int)v[0];
     if (numbers_after(slam, "max_frames", 1, v)) p.max_frames = (int)v[0];
     if (numbers_after(slam, "clahe_clip_limit", 1, v)) p.clahe_clip_limit = v[0];
+    { size_t r = slam.find("predict_keypoints:"); if (r != std::string::npos) p.predict_keypoints = slam.compare(r + 18, 6, " false") == 0 ? 0 : 1; }
     if (numbers_after(slam, "clahe_width", 1, v)) p.clahe_width = (int)v[0];
     if (numbers_after(slam, "clahe_height", 1, v)) p.clahe_height = (int)v[0];
     if (numbers_after(slam, "keyframe_num", 1, v)) p.init_keyframe_num = (int)v[0];
@@ -183,6 +215,12 @@ void XRSLAMPushSensorData(XRSLAMSensorType sensor_type, void *sensor_data) {
     case XRSLAM_SENSOR_CAMERA: {
         const XRSLAMImage *img = static_cast<const XRSLAMImage *>(sensor_data);
         const int w = m->prm.width, h = m->prm.height;
+        // XRSLAMImage carries no width / height: like XRSLAMManager::PushImage (:104-110) the size is the configured camera
+        // resolution, so the only thing that can be validated is that a row holds that many pixels
+        if (!img->data || (img->channel != 1 && img->channel != 3 && img->channel != 4 ? false : img->stride < w * img->channel)) {
+            std::fprintf(stderr, "XRSLAM: image rejected (null data or stride %d < %d pixels x %d channels)\n", img->stride, w, img->channel);
+            break;
+        }
         std::lock_guard<std::mutex> lk(m->input_mutex);
         m->image.resize((size_t)w * h);
         if (img->channel == 1) {
@@ -221,7 +259,8 @@ void XRSLAMRunOneFrame(void) {
     int s = 0;
     const uint8_t *ptr = m->image.data();
     int stride = m->prm.width;
-    xrvio_push_images(m->ctx, &s, &ptr, &stride, &m->image_t, 1, 0);
+    const int rc = xrvio_push_images(m->ctx, &s, &ptr, &stride, &m->image_t, 1, 0);
+    if (rc != XRVIO_OK) std::fprintf(stderr, "XRSLAM: frame at t = %.6f dropped (%d): %s\n", m->image_t, rc, xrvio_last_error());
     m->has_image = false;
 }
 
@@ -229,14 +268,18 @@ void XRSLAMGetResult(XRSLAMResultType result_type, void *result_data) {
     Manager *m = g_mgr;
     if (!m || !result_data) return;
     switch (result_type) {
-    case XRSLAM_RESULT_BODY_POSE: {
+    case XRSLAM_RESULT_BODY_POSE:       // XRSLAMManager::GetResultBodyPose (:155-167): latest pose o imu_to_body
+    case XRSLAM_RESULT_CAMERA_POSE: {   // XRSLAMManager::GetResultCameraPose (:169-181): latest pose o camera_to_body
         xrvio_pose p;
         XRSLAMPose *o = static_cast<XRSLAMPose *>(result_data);
         xrvio_get_pose(m->ctx, 0, &p);
-        for (int k = 0; k < 4; ++k) o->quaternion[k] = p.q[k];
-        for (int k = 0; k < 3; ++k) o->translation[k] = p.p[k];
+        const double *qx = result_type == XRSLAM_RESULT_BODY_POSE ? m->prm.q_bi : m->prm.q_bc;
+        const double *px = result_type == XRSLAM_RESULT_BODY_POSE ? m->prm.p_bi : m->prm.p_bc;
+        compose_pose(p.q, p.p, qx, px, o->quaternion, o->translation);
         o->timestamp = p.valid ? p.t : 0.0;
     } break;
+    case XRSLAM_RESULT_FEATURES:        // XRSLAMManager::GetResultFeatures (:217) has an empty body: the output is left untouched
+        break;
     case XRSLAM_RESULT_STATE:
         *static_cast<XRSLAMState *>(result_data) = xrvio_get_state(m->ctx, 0) == XRVIO_STATE_TRACKING ? XRSLAM_STATE_TRACKING_SUCCESS : XRSLAM_STATE_INITIALIZING;
         break;
