@@ -12,6 +12,7 @@ xrvio_step (front end + localize solve + window BA / marginalisation or sub-wind
 sessions are brought to TRACKING before anything is timed (bootstrap priming is setup, not warm-up).
 `value` is measured with the frames already resident in HBM (device pointers); `e2e` through the same
 C ABI with pinned HOST frames (H2D inside the timed region) and a per-step read-back of every pose.
+The timed region is exactly K steps = K frames per session through the whole path (`ms_per_step` = time / K).
 Every step consumes 64 frames never touched before (19.7 MB of fresh input; the pre-rendered frame
 set is far larger than L2), so no L2 flush is needed: config.l2 = "inputs_larger_than_L2".
 """
@@ -35,7 +36,10 @@ sys.path.insert(0, ROOT)
 
 N_STREAMS = 64
 W_IMG, H_IMG = 640, 480
-PRIME_FRAMES = 40          # frames before the timed region: the sessions bootstrap at frame 36
+# Frames before the warm-up steps.  The sessions bootstrap at frame 36; the timed window starts >= 150 frames (7.5 s of stream
+# time, ~38 window BAs and marginalisations per session) after that, i.e. in steady state: full 10-keyframe windows, full-rank
+# priors, track lengths and landmark counts at their stationary level (frames 45-65 were the young-map transient).
+PRIME_FRAMES = 190
 # algorithmic HBM bytes per kernel family and frame (DESIGN.md "Roofline")
 P_IMG = W_IMG * H_IMG
 ALGO_BYTES_PER_FRAME = {'clahe': 3.0 * P_IMG, 'pyramid': 1.641 * P_IMG, 'gftt': 1.0 * P_IMG, 'klt': 2.656 * P_IMG}
@@ -106,6 +110,40 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
 
 
+def pin_to_gpu_numa_node(local_rank, world):
+    """Binds this rank (and the library threads it will create) to its share of the CPU cores that are local to its GPU.
+    On the 8-GPU boxes GPUs 0-3 and 4-7 hang off different NUMA nodes; an unpinned rank's lane threads and pinned staging
+    buffers end up on the far node half of the time (weak-scaling efficiency 0.65 at N = 8).  The ranks that share
+    a node split its cores evenly.  Returns a description for the JSON line (None if nothing was done)."""
+    if world <= 1 or not hasattr(os, 'sched_setaffinity'):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        n_words = (os.cpu_count() + 63) // 64
+        masks = []
+        for g in range(world):
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(g), n_words)
+            masks.append(frozenset(64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1))
+        mine = masks[local_rank]
+        sharers = [g for g in range(world) if masks[g] == mine]
+        allowed = sorted(mine & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        # keep hyper-thread siblings together: split the sorted list into contiguous shares per sharer, interleaved over the two
+        # halves of the node's list (cores c and c + ncores/2 are siblings on these hosts)
+        k, m = sharers.index(local_rank), len(sharers)
+        half = len(allowed) // 2
+        lo, hi = allowed[:half], allowed[half:]
+        share = lo[k * len(lo) // m:(k + 1) * len(lo) // m] + hi[k * len(hi) // m:(k + 1) * len(hi) // m]
+        if not share:
+            share = allowed
+        os.sched_setaffinity(0, share)
+        return {'cpus': len(share), 'first': share[0], 'last': share[-1], 'numa_sharers': m}
+    except Exception as e:          # pinning is an optimisation, never a reason to fail the run
+        return {'error': str(e)[:80]}
+
+
 def stream_seeds(rank, n_streams=None):
     """Session -> synthetic stream seed; ranks own disjoint seed ranges (seeds = 1000*rank + i)."""
     return [1000 * rank + i for i in range(n_streams or N_STREAMS)]
@@ -156,8 +194,10 @@ def run_cuda_arm(args, rank, world, local_rank):
     from oracle import drive
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    pin = pin_to_gpu_numa_node(local_rank, world)
     # several ranks share the host: give each its share of cores for the library's bookkeeping threads
-    os.environ.setdefault('XRVIO_HOST_THREADS', str(max(8, min(64, (os.cpu_count() or 8) // max(world, 1)))))
+    n_cpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 8)
+    os.environ.setdefault('XRVIO_HOST_THREADS', str(max(8, min(64, n_cpu if pin and 'cpus' in pin else n_cpu // max(world, 1)))))
     K, Wm = args.steps, max(args.warmup, 3)
     n_frames = PRIME_FRAMES + Wm + K + 1
     streams, imus = build_streams(rank, n_frames)
@@ -204,12 +244,10 @@ def run_cuda_arm(args, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
+        # every step processes the frame pushed by the step before it and pushes the next one: K steps = K frames per session
+        # through the whole path and K image pushes inside the timed region
         for k in range(PRIME_FRAMES + Wm, PRIME_FRAMES + Wm + K):
             step(k)
-        # the frame pushed by the last step is processed by the step of the next frame: flush it so that K frames per
-        # session have gone through the whole path inside the timed region
-        ctx.push_imu(*batches[PRIME_FRAMES + Wm + K])
-        ctx.step()
         torch.cuda.synchronize()
         e1.record()
         torch.cuda.synchronize()
@@ -237,6 +275,7 @@ def run_cuda_arm(args, rank, world, local_rank):
     e0s, e1s = r_e2e['stats0'], r_e2e['stats1']
     # frames that went through the whole path inside the timed region (identical on every rank: weak scaling)
     total_frames = int(s1['frames_processed'] - s0['frames_processed']) * world
+    assert total_frames == K * N_STREAMS * world, (total_frames, K)
     value = total_frames / (ms_dev * 1e-3)
     e2e = int(e1s['frames_processed'] - e0s['frames_processed']) * world / (ms_e2e * 1e-3)
     launches = int(s1['kernels_launched'] - s0['kernels_launched'])
@@ -332,7 +371,8 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = min(os.cpu_count() or 1, 64)            # one single-threaded stream per core (at most 64, the workload's stream count)
+    # one single-threaded stream per core, at most the job's stream count (64 per GPU of the launch)
+    cores = min(os.cpu_count() or 1, N_STREAMS * max(world, 1))
     K, Wm = args.steps, max(args.warmup, 3)
     n_timed = max(1, min(K, 20))                     # bounded sample: at most 20 tracked frames per stream
     ctx = mp.get_context('fork')
@@ -350,7 +390,8 @@ def run_reference_arm(args, rank, world):
         'steps': K, 'warmup': Wm, 'ms_per_step': max(secs) / n_timed * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64 back end / u8+f32 front end', 'data': 'synthetic',
         'config': {'workload': '64x640x480_streams', 'streams_per_gpu': N_STREAMS, 'image': [W_IMG, H_IMG], 'cam_hz': 20, 'imu_hz': 200,
-                   'window_keyframes': 10, 'max_detections': 200, 'prime_frames': PRIME_FRAMES},
+                   'window_keyframes': 10, 'max_detections': 200, 'prime_frames': PRIME_FRAMES, 'l2': 'inputs_larger_than_L2',
+                   'parallelism': 'sessions sharded per GPU, no data-path collective'},
         'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                          'sample': '%d streams (one per host core) x %d tracked frames each, restated reference CPU path '
                                    '(cv2 4.13 + numpy), not the original Ceres/Eigen binary' % (cores, n_timed)},

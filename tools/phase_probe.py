@@ -8,7 +8,7 @@ from oracle.synth_torch import TorchRenderer
 from oracle import drive
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 bench.N_STREAMS = S
-PRIME = int(sys.argv[2]) if len(sys.argv) > 2 else 43
+PRIME = int(sys.argv[2]) if len(sys.argv) > 2 else 190
 n_frames = PRIME + 30 + 1
 streams, imus = bench.build_streams(0, n_frames)
 dev = torch.device('cuda', 0)
@@ -48,7 +48,7 @@ capi.lib.xrvio_debug_kprof(arr, 0)
 a = list(arr)
 npb = max(a[31], 1)
 lab = {0: 'J zero', 1: 'J rpe', 2: 'J rot', 3: 'J pre simt', 4: 'J pre coop', 5: 'J marg', 6: 'J reduce', 8: 'C zero/sync', 9: 'C rpe', 10: 'C rot', 11: 'C pre simt', 12: 'C pre coop', 13: 'C marg',
-       14: 'C reduce', 17: 'loop pre-cand', 18: 'D/alpha', 19: 'gauss_newton', 20: 'dogleg', 21: 'cand+ambient', 22: 'post-accept eval etc', 23: 'apply_scaling', 24: 'GN schur', 25: 'GN cholesky', 26: 'GN substitution', 27: 'GN calls', 28: 'GN cholesky failures'}
+       14: 'C reduce', 17: 'loop pre-cand', 18: 'D/alpha', 19: 'gauss_newton', 20: 'dogleg', 21: 'cand+ambient', 22: 'post-accept eval etc', 23: 'apply_scaling', 24: 'GN schur', 25: 'GN cholesky', 26: 'GN substitution', 27: 'GN calls', 28: 'GN cholesky failures', 29: 'GN setup (mu D^2)'}
 print('window problems', npb)
 for i in range(31):
     if a[i]:

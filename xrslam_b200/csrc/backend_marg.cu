@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
     P.flags_g = nullptr;
     P.invd_user = const_cast<double *>(b.inv_depth) + md.lm_off;
     P.rpe = b.rpe; P.rot = nullptr; P.pre = b.pre; P.pre_blocks = b.pre_blocks; P.marg_frames = b.marg_frames;
-    P.M = md.n_lm; P.NPc = 15 * N; P.marg_n = 15 * md.marg_k;
+    P.M = md.n_lm; P.Wp = (P.M + 31) / 32 * 32; P.NPc = 15 * N; P.marg_n = 15 * md.marg_k;
     double *Gm;      // factor rows (global)
     double *Yg;      // n1 x 15
     {

@@ -52,7 +52,7 @@ template <class SM> __device__ double ambient_sq(const Prob &P, SM &s, const dou
 
 // Gauss-Newton step: (Hs + mu D^2) y = gs via Schur complement on the landmark block + Cholesky.
 // Returns false when the factorisation fails (LINEAR_SOLVER_FAILURE).  H is consumed.
-template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu) {
+template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu, KProf &kp) {
     XV_ASSUME_SHARED(&s);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.NPc, M = P.M, na = P.d.n_active;
@@ -61,11 +61,11 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
     for (int l = tid; l < M; l += ST) P.ht_l[l] = P.h_ll[l] + mu * P.D_l[l] * P.D_l[l];
     for (int c = tid; c < n; c += ST) s.bred[c] = s.g[c];
     __syncthreads();
-    if (threadIdx.x == 0 && P.d.marg_k > 0) { s.sc[15] = (double)clock64(); atomicAdd(&g_kprof[27], 1ull); }
+    kp.mark(29); kp.count(27);
     if constexpr (SM::kSharedH) schur_landmarks(P, s, s.bred);
     else schur_landmarks_mma(P, s, s.bred);
     __syncthreads();
-    if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[24], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
+    kp.mark(24);
     // in-place right-looking Cholesky on the packed lower triangle.  The scaled pivot column is mirrored
     // into a contiguous vector (s.du, free at this point) so the trailing update reads it conflict-free;
     // 1/L_jj is kept in s.dw for the substitutions.
@@ -187,11 +187,53 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[25], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
-    if (!s.flag) { if (threadIdx.x == 0 && P.d.marg_k > 0) atomicAdd(&g_kprof[28], 1ull); return false; }
-    // forward / backward substitution (L z = b, L^T y = z) in panels of six columns, two barriers per panel: thread 0
-    // solves the 6x6 triangle of the panel and publishes the six values, then every row outside the panel applies them in
-    // column order -- the same operations in the same order as a column-by-column substitution.
+    kp.mark(25);
+    if (!s.flag) { kp.count(28); return false; }
+    // forward / backward substitution (L z = b, L^T y = z).  Sliding-window instance (H in shared memory, n <= 180): ONE warp
+    // runs both sweeps with the work vector in registers (lane l owns rows l, l + 32, ...): per column the owner lane scales its
+    // entry, broadcasts it with a shuffle and every lane updates its rows -- no CTA barrier inside the sweeps, against two per
+    // panel of six columns when the 6 x 6 triangle was solved by thread 0 alone.  Large instance (H in global memory, n <= 480):
+    // panels of six columns, thread 0 solves the 6 x 6 triangle, every row outside the panel applies the six values.
+    if constexpr (SM::kSharedH) {
+        if (warp == 0) {
+            constexpr int NR = (SM::NPv + 31) / 32;
+            double v[NR];
+#pragma unroll
+            for (int k = 0; k < NR; ++k) { const int i = lane + 32 * k; v[k] = i < n ? s.bred[i] : 0.0; }
+            // forward: z_j = v_j / L_jj ; v_i -= L_ij z_j (i > j)
+            for (int j = 0; j < n; ++j) {
+                const int oj = j >> 5;
+                double mine = 0.0;
+#pragma unroll
+                for (int k = 0; k < NR; ++k) if (k == oj) mine = v[k];
+                const double zj = __shfl_sync(0xffffffffu, mine, j & 31) * idiag[j];
+#pragma unroll
+                for (int k = 0; k < NR; ++k) {
+                    const int i = lane + 32 * k;
+                    if (i == j) v[k] = zj;
+                    else if (i > j && i < n) v[k] -= s.H[hidx(i, j)] * zj;
+                }
+            }
+            // backward: y_j = v_j / L_jj ; v_i -= L_ji y_j (i < j): row j of L is contiguous in the packed triangle
+            for (int j = n - 1; j >= 0; --j) {
+                const int oj = j >> 5;
+                double mine = 0.0;
+#pragma unroll
+                for (int k = 0; k < NR; ++k) if (k == oj) mine = v[k];
+                const double yj = __shfl_sync(0xffffffffu, mine, j & 31) * idiag[j];
+                const double *row = &s.H[hidx(j, 0)];
+#pragma unroll
+                for (int k = 0; k < NR; ++k) {
+                    const int i = lane + 32 * k;
+                    if (i == j) v[k] = yj;
+                    else if (i < j) v[k] -= row[i] * yj;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NR; ++k) { const int i = lane + 32 * k; if (i < n) s.y[i] = v[k]; }
+        }
+        __syncthreads();
+    } else {
     // forward: work vector s.y (starts as b_red), result z in s.bred; backward: work vector s.bred, result in s.y.
     for (int c = tid; c < n; c += ST) s.y[c] = s.bred[c];
     __syncthreads();
@@ -231,7 +273,8 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0 && P.d.marg_k > 0) { long long t = clock64(); atomicAdd(&g_kprof[26], (unsigned long long)(t - (long long)s.sc[15])); s.sc[15] = (double)t; }
+    }
+    kp.mark(26);
     bool ok = true;
     for (int c = tid; c < n; c += ST) ok = ok && isfinite(s.y[c]);
     // back-substitute the landmarks: y_l = (gs_l - w_l . y_p) / ht_l
@@ -239,7 +282,7 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
         double a = P.g_l[l];
         for (int f = 0; f < na; ++f) {
             if (!s.pose_free[f]) continue;
-            for (int k = 0; k < 6; ++k) a -= P.W[(size_t)(f * 6 + k) * M + l] * s.y[15 * f + k];
+            for (int k = 0; k < 6; ++k) a -= P.W[(size_t)(f * 6 + k) * P.Wp + l] * s.y[15 * f + k];
         }
         a /= P.ht_l[l];
         P.y_l[l] = a;
@@ -260,6 +303,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
     P.invd_user = b.inv_depth + P.d.lm_off;
     P.rpe = b.rpe; P.rot = b.rot; P.pre = b.pre; P.pre_blocks = b.pre_blocks; P.marg_frames = b.marg_frames;
     P.M = P.d.n_lm_free;
+    P.Wp = (P.M + 31) / 32 * 32;
     P.NPc = 15 * P.d.n_active;
     P.marg_n = 15 * P.d.marg_k;
     {
@@ -300,7 +344,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
     nfree += P.M;
 
     KProf kp; kp.start(P.d.marg_k > 0);
-    if (kp.on) atomicAdd(&g_kprof[31], 1ull);
+    kp.count(31);
     // ---- iteration zero ----
     double x_cost = evaluate(P, s, s.xs, P.inv_x, rg, true, true, &kp);
     if (nfree == 0) {
@@ -320,19 +364,19 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
     __syncthreads();
 
     auto apply_scaling = [&]() {
-        for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) {
-            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-            while (i * (i + 1) / 2 > e) --i;
-            while ((i + 1) * (i + 2) / 2 <= e) ++i;
-            const int j = e - i * (i + 1) / 2;
-            if (s.col_free[i] && s.col_free[j]) s.H[e] *= s.scale[i] * s.scale[j];
+        for (int i = tid >> 5; i < P.NPc; i += NW) {               // one warp per row of the packed triangle (no index decode)
+            if (!s.col_free[i]) continue;
+            const double si = s.scale[i];
+            const int r0 = i * (i + 1) / 2;
+            for (int j = tid & 31; j <= i; j += 32)
+                if (s.col_free[j]) s.H[r0 + j] *= si * s.scale[j];
         }
         for (int c = tid; c < P.NPc; c += ST) s.g[c] *= s.scale[c];
         for (int l = tid; l < P.M; l += ST) { const double sl = P.sc_l[l]; P.h_ll[l] *= sl * sl; P.g_l[l] *= sl; }
-        for (int e = tid; e < P.d.n_active * 6 * P.M; e += ST) {
-            const int l = e % P.M, ck = e / P.M;
-            const int f = ck / 6, k = ck % 6;
-            P.W[(size_t)ck * P.M + l] *= P.sc_l[l] * s.scale[15 * f + k];
+        for (int ck = tid >> 5; ck < P.d.n_active * 6; ck += NW) {          // one warp per row of W
+            const double sck = s.scale[15 * (ck / 6) + ck % 6];
+            double *wr = P.W + (size_t)ck * P.Wp;
+            for (int l = tid & 31; l < P.M; l += 32) wr[l] *= P.sc_l[l] * sck;
         }
         __syncthreads();
         for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) P.Hcopy[e] = s.H[e];
@@ -384,19 +428,21 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
             for (int c = tid; c < P.NPc; c += ST) { const double t = s.g[c] / s.D[c]; a += t * t; s.bred[c] = s.g[c] / (s.D[c] * s.D[c]); }
             for (int l = tid; l < P.M; l += ST) { const double t = P.g_l[l] / P.D_l[l]; a += t * t; }
             gnorm2 = block_sum(a, s);
-            for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) {
-                int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-                while (i * (i + 1) / 2 > e) --i;
-                while ((i + 1) * (i + 2) / 2 <= e) ++i;
-                const int j = e - i * (i + 1) / 2;
-                if (s.col_free[i] && s.col_free[j]) q += (i == j ? 1.0 : 2.0) * s.bred[i] * s.H[e] * s.bred[j];
+            for (int i = tid >> 5; i < P.NPc; i += NW) {           // v^T Hs v over the packed triangle, one warp per row
+                if (!s.col_free[i]) continue;
+                const double vi = s.bred[i];
+                const int r0 = i * (i + 1) / 2;
+                double qr = 0.0;
+                for (int j = tid & 31; j <= i; j += 32)
+                    if (s.col_free[j]) qr += (i == j ? 1.0 : 2.0) * s.H[r0 + j] * s.bred[j];
+                q += vi * qr;
             }
             for (int l = tid; l < P.M; l += ST) {
                 const double vl = P.g_l[l] / (P.D_l[l] * P.D_l[l]);
                 double wv = 0.0;
                 for (int f = 0; f < P.d.n_active; ++f)
                     if (s.pose_free[f])
-                        for (int k = 0; k < 6; ++k) wv += P.W[(size_t)(f * 6 + k) * P.M + l] * s.bred[15 * f + k];
+                        for (int k = 0; k < 6; ++k) wv += P.W[(size_t)(f * 6 + k) * P.Wp + l] * s.bred[15 * f + k];
                 q += 2.0 * vl * wv + P.h_ll[l] * vl * vl;
             }
             uHu = block_sum(q, s);
@@ -405,8 +451,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
             solver_failed = true;
             while (mu < kMaxMu) {
                 kp.mark(18);
-                const bool gn_ok = gauss_newton(P, s, mu);
-                kp.mark(19);
+                const bool gn_ok = gauss_newton(P, s, mu, kp);
                 if (gn_ok) { solver_failed = false; break; }
                 mu *= kMuInc;
                 for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) s.H[e] = P.Hcopy[e];
@@ -539,8 +584,8 @@ size_t solve_large_scratch_doubles(int n_active, int n_lm_free, int n_pre, int m
 void solve_large(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
     if (n_problems <= 0) return;
     static std::atomic<unsigned long long> attr_done{0};
-    xv::ensure_dynamic_smem(solve_large_kernel, (int)sizeof(SmemL), attr_done);
-    solve_large_kernel<<<n_problems, ST, sizeof(SmemL), st>>>(b, rig);
+    xv::ensure_dynamic_smem(solve_large_kernel, (int)kSolveLargeSmem, attr_done);
+    solve_large_kernel<<<n_problems, ST, kSolveLargeSmem, st>>>(b, rig);
 }
 
 void solve(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {

@@ -141,7 +141,8 @@ int xrvio_op_klt(const uint8_t *prev_img, const uint8_t *next_img, int n, int w,
     CK(cudaMemcpy(d_np.p, next_pts, pb, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_cnt.p, npts, n * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemset(d_st.p, 0, (size_t)n * xvfe::kMaxPts));
-    xvfe::klt_track(d_p.as<uint8_t>(), d_n.as<uint8_t>(), nullptr, nullptr, n, L, d_pp.as<float>(), d_np.as<float>(), d_cnt.as<int>(), d_st.as<uint8_t>(), 0);
+    const xvfe::KltMapSet mp = xvfe::klt_make_maps(d_p.as<uint8_t>(), n, L), mn = xvfe::klt_make_maps(d_n.as<uint8_t>(), n, L);
+    xvfe::klt_track(d_p.as<uint8_t>(), d_n.as<uint8_t>(), nullptr, nullptr, n, L, d_pp.as<float>(), d_np.as<float>(), d_cnt.as<int>(), d_st.as<uint8_t>(), 0, &mp, &mn);
     CK(cudaGetLastError());
     CK(cudaMemcpy(next_pts, d_np.p, pb, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(status, d_st.p, (size_t)n * xvfe::kMaxPts, cudaMemcpyDeviceToHost));

@@ -200,6 +200,7 @@ struct Lane {
     uint8_t *d_raw = nullptr;          // S * kImgQueue * w*h
     uint8_t *d_pyr = nullptr;          // S * kPyrSlots * L.total
     uint8_t *d_lut = nullptr;
+    xvfe::KltMapSet klt_maps{};        // TMA tensor maps over d_pyr, one pair per pyramid level
     uint8_t *d_und = nullptr;          // S * w*h undistorted images of the round (only with prm.distortion_model != 0)
     int2 *d_und_map = nullptr;         // w*h source positions in 1/32 px
     unsigned long long *d_cand = nullptr; int *d_cand_count = nullptr; unsigned *d_maxval = nullptr;
@@ -617,6 +618,7 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
     CKC(cudaMalloc((void **)&c->d_raw, (size_t)S * kImgQueue * P));
     CKC(cudaMalloc((void **)&c->d_pyr, (size_t)S * kPyrSlots * c->L.total));
     CKC(cudaMalloc((void **)&c->d_lut, (size_t)S * p->clahe_width * p->clahe_height * 256));
+    c->klt_maps = xvfe::klt_make_maps(c->d_pyr, S * kPyrSlots, c->L);
     if (p->distortion_model != XRVIO_DISTORTION_NONE) {
         if (p->distortion_model != XRVIO_DISTORTION_RADTAN && p->distortion_model != XRVIO_DISTORTION_EQUIDISTANT) { xrvio_set_error("xrvio_create: unknown distortion_model"); return XRVIO_ERR_ARG; }
         CKC(cudaMalloc((void **)&c->d_und, (size_t)S * P));

@@ -3,8 +3,13 @@
 // FMA-contracted in its SSE3 baseline build.
 #include "frontend.cuh"
 #include "launch_attr.cuh"
+#ifndef CUEMU
+#include <cuda.h>                 // CUtensorMap, cuTensorMapEncodeTiled (resolved at run time through cudaGetDriverEntryPoint)
+#endif
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 namespace xvfe {
 
@@ -510,15 +515,56 @@ constexpr int RAWP = WIN + 3;     // 24: + 1 px ring for the Scharr stencil
 constexpr int KLT_WARPS = 4;
 
 constexpr int JREG = 32;          // side of the staged search region (window 22 + 10 px of slack)
-struct KltSmem {
-    union {
-        uint8_t raw[RAWP][RAWP + 4];  // level image around the template window (reflect-101 border)
+constexpr int RAWPITCH = 32;      // row pitch of the staged template neighbourhood = inner box of its TMA tile (16-byte multiple)
+struct alignas(128) KltSmem {
+    union {                           // both are destinations of TMA tile loads: 128-byte aligned, pitch = box width
+        uint8_t raw[RAWP][RAWPITCH];  // level image around the template window (reflect-101 border)
         uint8_t J[JREG][JREG];        // search region in the other image (staged once per level, re-staged on exit)
     };
     short dx[WINP][WINP];             // Scharr derivatives at the 22x22 positions (0 outside the image)
     short dy[WINP][WINP];
     short I[WIN * WIN];               // template patch  (<< 5)
     short Ix[WIN * WIN], Iy[WIN * WIN];
+    unsigned long long bar;           // mbarrier of this warp's TMA loads
+};
+
+// ---- TMA staging (north_star: "image patches ... staged through TMA into shared memory") --------------------------------
+// One tensor map per pyramid level over the whole pyramid buffer: dims (x = level width, y = level height, z = pyramid
+// index), u8, box 32 x 24 (template neighbourhood) or 32 x 32 (search region).  A tile that lies completely inside the level
+// is fetched by ONE cp.async.bulk.tensor issued by lane 0 and awaited on the warp's mbarrier, instead of 18-32 predicated
+// byte loads per lane with reflect-101 index arithmetic; tiles that touch the border keep the scalar path (TMA can only
+// zero-fill outside the tensor, OpenCV reflects).  Levels whose width / offset / pyramid stride is not a multiple of 16
+// bytes (e.g. 94 x 60 of a 752 x 480 image) have no map and always take the scalar path.
+#ifndef CUEMU
+struct KltMaps {
+    CUtensorMap tmpl[kPyrLevels];     // box 32 x 24
+    CUtensorMap srch[kPyrLevels];     // box 32 x 32
+    unsigned ok;                      // bit l: level l has maps
+};
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// lane 0: arm the barrier with the tile's byte count and issue the tile load (coordinates x, y, pyramid index)
+__device__ __forceinline__ void tma_tile_3d(void *dst, const CUtensorMap *map, unsigned long long *bar, int x, int y, int z, unsigned bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the warp's earlier generic-proxy accesses to dst come first
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#else
+struct KltMaps { unsigned ok; };
+#endif
+// what one lk_track_point call needs to use the maps: which pyramid (z) each image is, and the warp's barrier phase
+struct KltTma {
+    const KltMaps *mapsI, *mapsJ;     // maps of the buffers holding the template image / the searched image (null: scalar path)
+    int zI, zJ;
+    unsigned phase;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -529,7 +575,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // One LK run for one point through all levels.  Returns status; out = tracked point (level 0).
 // Lane l owns window pixels i = l + 32 k (k < 14); their (y, x) are computed once (no div/mod in the loops).
 __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *__restrict__ pyrJ, const PyrLayout &L,
-                               float px, float py, float gx, float gy, float &ox, float &oy, KltSmem &sm) {
+                               float px, float py, float gx, float gy, float &ox, float &oy, KltSmem &sm, KltTma &tma) {
     const int lane = threadIdx.x & 31;
     constexpr int NPX = (WIN * WIN + 31) / 32;      // 14
     int pxy[NPX];                                   // y << 8 | x, or -1 beyond the 441 pixels
@@ -563,7 +609,16 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
         int iw11 = 16384 - iw00 - iw01 - iw10;
         // stage the raw template neighbourhood (24 x 24): loads first, stores after, so the loads overlap
         __syncwarp();
-        {
+        bool tile_done = false;
+#ifndef CUEMU
+        if (tma.mapsI != nullptr && ((tma.mapsI->ok >> level) & 1u) && ipx >= 1 && ipx + RAWP - 2 < cols && ipy >= 1 && ipy + RAWP - 2 < rows) {
+            if (lane == 0) tma_tile_3d(&sm.raw[0][0], &tma.mapsI->tmpl[level], &sm.bar, ipx - 1, ipy - 1, tma.zI, RAWP * RAWPITCH);
+            mbar_wait(&sm.bar, tma.phase);
+            tma.phase ^= 1u;
+            tile_done = true;
+        }
+#endif
+        if (!tile_done) {
             constexpr int NR = (RAWP * RAWP + 31) / 32;     // 18
             uint8_t v[NR];
 #pragma unroll
@@ -648,13 +703,24 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
             if (!staged || inx < rox || inx > rox + JREG - WINP || iny < roy || iny > roy + JREG - WINP) {
                 rox = inx - (JREG - WINP) / 2; roy = iny - (JREG - WINP) / 2;
                 __syncwarp();
-                // lane = column, 32 rows: 32 independent loads per lane
-                uint8_t v[JREG];
-                const int cxg = reflect1(rox + lane, cols);
+                bool region_done = false;
+#ifndef CUEMU
+                if (tma.mapsJ != nullptr && ((tma.mapsJ->ok >> level) & 1u) && rox >= 0 && rox + JREG <= cols && roy >= 0 && roy + JREG <= rows) {
+                    if (lane == 0) tma_tile_3d(&sm.J[0][0], &tma.mapsJ->srch[level], &sm.bar, rox, roy, tma.zJ, JREG * JREG);
+                    mbar_wait(&sm.bar, tma.phase);
+                    tma.phase ^= 1u;
+                    region_done = true;
+                }
+#endif
+                if (!region_done) {
+                    // lane = column, 32 rows: 32 independent loads per lane
+                    uint8_t v[JREG];
+                    const int cxg = reflect1(rox + lane, cols);
 #pragma unroll
-                for (int r = 0; r < JREG; ++r) v[r] = J[(size_t)reflect1(roy + r, rows) * cols + cxg];
+                    for (int r = 0; r < JREG; ++r) v[r] = J[(size_t)reflect1(roy + r, rows) * cols + cxg];
 #pragma unroll
-                for (int r = 0; r < JREG; ++r) sm.J[r][lane] = v[r];
+                    for (int r = 0; r < JREG; ++r) sm.J[r][lane] = v[r];
+                }
                 __syncwarp();
                 staged = true;
             }
@@ -685,6 +751,11 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
     return status;
 }
 
+#ifndef CUEMU
+#define XV_GRID_CONSTANT __grid_constant__
+#else
+#define XV_GRID_CONSTANT
+#endif
 __global__ void __launch_bounds__(32 * KLT_WARPS) klt_kernel(const uint8_t *__restrict__ prev_pyr,
                                                               const uint8_t *__restrict__ next_pyr,
                                                               const int *__restrict__ pidx, const int *__restrict__ nidx,
@@ -692,19 +763,29 @@ __global__ void __launch_bounds__(32 * KLT_WARPS) klt_kernel(const uint8_t *__re
                                                               const float *__restrict__ prev_pts,
                                                               float *__restrict__ next_pts,
                                                               const int *__restrict__ npts,
-                                                              uint8_t *__restrict__ status) {
+                                                              uint8_t *__restrict__ status,
+                                                              const XV_GRID_CONSTANT KltMaps maps_prev,
+                                                              const XV_GRID_CONSTANT KltMaps maps_next) {
     __shared__ KltSmem sm[KLT_WARPS];
     const int img = blockIdx.y;
     const int warp = threadIdx.x >> 5;
     const int pt = blockIdx.x * KLT_WARPS + warp;
     if (pt >= npts[img]) return;
-    const uint8_t *P = prev_pyr + (size_t)(pidx ? pidx[img] : img) * L.total;
-    const uint8_t *N = next_pyr + (size_t)(nidx ? nidx[img] : img) * L.total;
+    const int zp = pidx ? pidx[img] : img, zn = nidx ? nidx[img] : img;
+    const uint8_t *P = prev_pyr + (size_t)zp * L.total;
+    const uint8_t *N = next_pyr + (size_t)zn * L.total;
     const size_t o = ((size_t)img * kMaxPts + pt) * 2;
     const float px = prev_pts[o], py = prev_pts[o + 1];
     const float gx = next_pts[o], gy = next_pts[o + 1];
+    KltTma tf{maps_prev.ok ? &maps_prev : nullptr, maps_next.ok ? &maps_next : nullptr, zp, zn, 0u};
+#ifndef CUEMU
+    if (maps_prev.ok | maps_next.ok) {       // the barrier belongs to this warp alone: no CTA-wide synchronisation needed
+        if ((threadIdx.x & 31) == 0) mbar_init(&sm[warp].bar, 1);
+        __syncwarp();
+    }
+#endif
     float qx, qy;
-    bool st = lk_track_point(P, N, L, px, py, gx, gy, qx, qy, sm[warp]);
+    bool st = lk_track_point(P, N, L, px, py, gx, gy, qx, qy, sm[warp], tf);
     const int cols = L.w[0], rows = L.h[0];
     // reference gates, opencv_image.cpp:99-113
     if (qx < 20.f || qx >= (float)(cols - 20) || qy < 20.f || qy >= (float)(rows - 20)) st = false;
@@ -714,7 +795,8 @@ __global__ void __launch_bounds__(32 * KLT_WARPS) klt_kernel(const uint8_t *__re
     }
     if (st) {
         float bx, by;
-        bool stb = lk_track_point(N, P, L, qx, qy, px, py, bx, by, sm[warp]);
+        KltTma tb{tf.mapsJ, tf.mapsI, zn, zp, tf.phase};
+        bool stb = lk_track_point(N, P, L, qx, qy, px, py, bx, by, sm[warp], tb);
         double ex = (double)(px - bx), ey = (double)(py - by);
         if (!stb || sqrt(ex * ex + ey * ey) > 0.5) st = false;
     }
@@ -724,11 +806,60 @@ __global__ void __launch_bounds__(32 * KLT_WARPS) klt_kernel(const uint8_t *__re
     }
 }
 
+// Tensor maps over a pyramid buffer of n_pyramids pyramids (see KltMaps).  ok == 0 when the driver entry point is missing or
+// the layout is not 16-byte regular: klt_track then runs the scalar staging path for every tile.
+KltMapSet klt_make_maps(const uint8_t *pyr, int n_pyramids, const PyrLayout &L) {
+    KltMapSet out;
+    std::memset(&out, 0, sizeof(out));
+#ifndef CUEMU
+    static_assert(sizeof(KltMaps) <= sizeof(out.bytes), "KltMapSet too small");
+    KltMaps m;
+    std::memset(&m, 0, sizeof(m));
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) fn = nullptr;
+        return (EncodeFn)fn;
+    }();
+    if (encode != nullptr && n_pyramids > 0 && L.total % 16 == 0 && ((uintptr_t)pyr % 16) == 0) {
+        for (int l = 0; l < kPyrLevels; ++l) {
+            if (L.w[l] % 16 != 0 || L.off[l] % 16 != 0 || L.w[l] < JREG || L.h[l] < JREG) continue;
+            const cuuint64_t dims[3] = {(cuuint64_t)L.w[l], (cuuint64_t)L.h[l], (cuuint64_t)n_pyramids};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.w[l], (cuuint64_t)L.total};       // bytes, dims 1 and 2
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const cuuint32_t box_t[3] = {RAWPITCH, RAWP, 1}, box_s[3] = {JREG, JREG, 1};
+            void *base = (void *)(pyr + L.off[l]);
+            if (encode(&m.tmpl[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_t, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) continue;
+            if (encode(&m.srch[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_s, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) continue;
+            m.ok |= 1u << l;
+        }
+    }
+    if (const char *e = std::getenv("XRVIO_KLT_TMA")) if (e[0] == '0') m.ok = 0;       // A/B switch for profiling
+    std::memcpy(out.bytes, &m, sizeof(m));
+    out.levels = m.ok;
+#else
+    (void)pyr; (void)n_pyramids; (void)L;
+#endif
+    return out;
+}
+
 void klt_track(const uint8_t *prev_pyr, const uint8_t *next_pyr, const int *prev_idx, const int *next_idx, int n,
                const PyrLayout &L, const float *prev_pts,
-               float *next_pts, const int *npts, uint8_t *status, cudaStream_t st) {
+               float *next_pts, const int *npts, uint8_t *status, cudaStream_t st, const KltMapSet *maps_prev, const KltMapSet *maps_next) {
     dim3 grid(kMaxPts / KLT_WARPS, n);
-    klt_kernel<<<grid, 32 * KLT_WARPS, 0, st>>>(prev_pyr, next_pyr, prev_idx, next_idx, L, prev_pts, next_pts, npts, status);
+    KltMaps mp, mn;
+    std::memset(&mp, 0, sizeof(mp)); std::memset(&mn, 0, sizeof(mn));
+#ifndef CUEMU
+    if (maps_prev && maps_prev->levels) std::memcpy(&mp, maps_prev->bytes, sizeof(mp));
+    if (maps_next && maps_next->levels) std::memcpy(&mn, maps_next->bytes, sizeof(mn));
+#else
+    (void)maps_prev; (void)maps_next;
+#endif
+    klt_kernel<<<grid, 32 * KLT_WARPS, 0, st>>>(prev_pyr, next_pyr, prev_idx, next_idx, L, prev_pts, next_pts, npts, status, mp, mn);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -48,9 +48,14 @@ void gftt_harris(const uint8_t *img, const int *idx, size_t img_stride, int n, i
 // ---- K4: pyramidal LK forward + gates + backward + 0.5 px check (opencv_image.cpp:75-154).
 // prev_pyr / next_pyr: n pyramids.  pts: n * kMaxPts * 2 floats.  npts: n ints.
 // next_pts in: initial guess (gyro prediction); out: tracked position.  status out: n * kMaxPts bytes.
+// maps_prev / maps_next: TMA tensor maps of the two pyramid buffers (klt_make_maps; built once per buffer), null or
+// levels == 0: every tile is staged with ordinary loads.  Inner tiles are fetched by cp.async.bulk.tensor (frontend.cu).
+struct alignas(64) KltMapSet { unsigned char bytes[8 * 128 + 64]; unsigned levels; };
+KltMapSet klt_make_maps(const uint8_t *pyr, int n_pyramids, const PyrLayout &L);
 void klt_track(const uint8_t *prev_pyr, const uint8_t *next_pyr, const int *prev_idx, const int *next_idx, int n,
                const PyrLayout &L, const float *prev_pts,
-               float *next_pts, const int *npts, uint8_t *status, cudaStream_t st);
+               float *next_pts, const int *npts, uint8_t *status, cudaStream_t st, const KltMapSet *maps_prev = nullptr,
+               const KltMapSet *maps_next = nullptr);
 // ---- K5: Poisson-disk filter.  For each of n lists: the first n_preset points are pre-seeded, the
 // rest are tested in order; keep[i] = 1 if accepted.  mode 0: insert_points semantics (detect);
 // mode 1: permit+preset with an extra per-point veto flag (track).  pts: n * kMaxPts * 2 doubles.

@@ -162,7 +162,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         const int *d_idx_prev = g.put(B.idx_prev.h, (size_t)n);
         CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));
         { ProfScope ps(c, FAM_KLT, 1);
-          xvfe::klt_track(c->d_pyr, c->d_pyr, d_idx_prev, B.idx_next.d, n, c->L, d_prev, d_next, d_n, d_status, c->st); }
+          xvfe::klt_track(c->d_pyr, c->d_pyr, d_idx_prev, B.idx_next.d, n, c->L, d_prev, d_next, d_n, d_status, c->st, &c->klt_maps, &c->klt_maps); }
         c->stats.kernels_launched += 1;
         CKC(cudaMemcpyAsync(g.h, g.d, out_bytes, cudaMemcpyDeviceToHost, c->st));
         CKC(cudaStreamSynchronize(c->st));

@@ -24,13 +24,25 @@ constexpr double kFuncTol = 1e-6, kGradTol = 1e-10, kParamTol = 1e-8;
 constexpr double kMinDiag = 1e-6, kMaxDiag = 1e32, kMinMu = 1e-8, kMaxMu = 1.0, kMuInc = 10.0;
 constexpr int kMaxInvalid = 5;
 
-// in-kernel section timing (clock64 of thread 0 of window problems), read back through xrvio_debug_kprof
+// in-kernel section timing (clock64 of thread 0 of window problems), read back through xrvio_debug_kprof.  A diagnostic:
+// compiled in only with -DXRVIO_KPROF (XRVIO_KPROF=1 python xrslam_b200/build.py --force; tools/phase_probe.py needs that
+// build), the product kernel carries neither the clock reads nor the atomics.
 __device__ unsigned long long g_kprof[32];
+#ifdef XRVIO_KPROF
 struct KProf {
     long long last; bool on;
     __device__ void start(bool enable) { on = enable && threadIdx.x == 0; if (on) last = clock64(); }
     __device__ void mark(int i) { if (on) { long long t = clock64(); atomicAdd(&g_kprof[i], (unsigned long long)(t - last)); last = t; } }
+    __device__ void count(int i) { if (on) atomicAdd(&g_kprof[i], 1ull); }
 };
+#else
+struct KProf {
+    static constexpr bool on = false;
+    __device__ __forceinline__ void start(bool) {}
+    __device__ __forceinline__ void mark(int) {}
+    __device__ __forceinline__ void count(int) {}
+};
+#endif
 
 // Address-space facts the compiler cannot see once a function is not inlined into the kernel (the large-window instance):
 // without them every access through `s` or H becomes a generic LD.E / ST.E / CAS-loop atomic.
@@ -104,13 +116,24 @@ template <class SM> __device__ __forceinline__ double block_max(double v, SM &s)
     return t;
 }
 
-// segmented suffix sum over lanes with sorted (contiguous) keys; segment heads end up with the sum
-__device__ __forceinline__ double seg_sum(double v, int key, int lane) {
+// Segmented suffix sum over lanes with sorted (contiguous) keys; segment heads end up with the sum.  Which partner values a lane
+// takes depends on the keys alone, so the five key comparisons are done once per batch of observations (seg_mask) and every
+// one of the ~90 sums of the batch is five value shuffles with predicated adds.
+__device__ __forceinline__ unsigned seg_mask(int key, int lane) {
+    unsigned m = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double t = __shfl_down_sync(0xffffffffu, v, o);
-        int k = __shfl_down_sync(0xffffffffu, key, o);
-        if (lane + o < 32 && k == key) v += t;
+    for (int b = 0; b < 5; ++b) {
+        const int o = 1 << b;
+        const int k = __shfl_down_sync(0xffffffffu, key, o);
+        if (lane + o < 32 && k == key) m |= 1u << b;
+    }
+    return m;
+}
+__device__ __forceinline__ double seg_sum(double v, unsigned take) {
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const double t = __shfl_down_sync(0xffffffffu, v, 1 << b);
+        if ((take >> b) & 1u) v += t;
     }
     return v;
 }
@@ -132,6 +155,8 @@ struct Prob {
     // scratch (global)
     double *inv_x, *inv_c, *h_ll, *g_l, *sc_l, *D_l, *y_l, *ht_l, *W, *Hcopy, *pre_s, *m_dx, *m_r, *m_v, *m_T, *du_l, *dw_l;
     int M, NPc;                    // free landmarks, pose/motion columns = 15 * n_active
+    int Wp;                        // row pitch of W in doubles: M rounded up to 32, so that every row (and every 32-landmark tile of
+                                   // it) starts on a 256-byte boundary -- what the bulk-copy staging of solve_large.cuh needs
 };
 
 // One-time per-problem precomputation: tangent bases of all reprojection observations.
@@ -227,7 +252,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
         for (int i = tid; i < SM::HP; i += ST) s.H[i] = 0.0;
         for (int i = tid; i < SM::NPv; i += ST) s.g[i] = 0.0;
         for (int i = tid; i < M; i += ST) { P.h_ll[i] = 0.0; P.g_l[i] = 0.0; }
-        const int nw = P.d.n_active * 6 * M;
+        const int nw = P.d.n_active * 6 * P.Wp;          // including the padding columns: they enter the tensor-pipe tiles
         for (int i = tid; i < nw; i += ST) P.W[i] = 0.0;
     }
     __syncthreads();
@@ -276,16 +301,17 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
             const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);   // unconditional: every lane must take part
             const bool head = (lane == 0) || (key_prev != key);
             const bool act = valid && tf;
+            const unsigned take = seg_mask(key, lane);
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
 #pragma unroll
                 for (int j = 0; j <= i; ++j) {
                     double v = act ? (e.Jt[i] * e.Jt[j] + e.Jt[6 + i] * e.Jt[6 + j]) : 0.0;
-                    v = seg_sum(v, key, lane);
+                    v = seg_sum(v, take);
                     if (act && head) atomicAdd(&s.H[hidx(15 * ts + i, 15 * ts + j)], v);
                 }
                 double gv = act ? (e.Jt[i] * e.r[0] + e.Jt[6 + i] * e.r[1]) : 0.0;
-                gv = seg_sum(gv, key, lane);
+                gv = seg_sum(gv, take);
                 if (act && head) atomicAdd(&s.g[15 * ts + i], gv);
             }
         }
@@ -296,13 +322,14 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
             const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);   // unconditional: every lane must take part
             const bool head = (lane == 0) || (key_prev != key);
             const bool act_tr = valid && tf && rf, act_rr = valid && rf;
+            const unsigned take = fast ? 0u : seg_mask(key, lane);
             if (!fast) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
                     double v = act_tr ? (e.Jt[i] * e.Jr[j] + e.Jt[6 + i] * e.Jr[6 + j]) : 0.0;
-                    v = seg_sum(v, key, lane);
+                    v = seg_sum(v, take);
                     if (act_tr && head) {
                         const int a = 15 * ts + i, b = 15 * rs + j;
                         atomicAdd(&s.H[a > b ? hidx(a, b) : hidx(b, a)], v);
@@ -311,11 +338,11 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
 #pragma unroll
                 for (int j = 0; j <= i; ++j) {
                     double v = act_rr ? (e.Jr[i] * e.Jr[j] + e.Jr[6 + i] * e.Jr[6 + j]) : 0.0;
-                    v = seg_sum(v, key, lane);
+                    v = seg_sum(v, take);
                     if (act_rr && head) atomicAdd(&s.H[hidx(15 * rs + i, 15 * rs + j)], v);
                 }
                 double gv = act_rr ? (e.Jr[i] * e.r[0] + e.Jr[6 + i] * e.r[1]) : 0.0;
-                gv = seg_sum(gv, key, lane);
+                gv = seg_sum(gv, take);
                 if (act_rr && head) atomicAdd(&s.g[15 * rs + i], gv);
             }
             }
@@ -324,9 +351,9 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
                 atomicAdd(&P.h_ll[lm], e.Jl[0] * e.Jl[0] + e.Jl[1] * e.Jl[1]);
                 atomicAdd(&P.g_l[lm], e.Jl[0] * e.r[0] + e.Jl[1] * e.r[1]);
                 if (tf)
-                    for (int k = 0; k < 6; ++k) P.W[(size_t)(ts * 6 + k) * M + lm] = e.Jl[0] * e.Jt[k] + e.Jl[1] * e.Jt[6 + k];
+                    for (int k = 0; k < 6; ++k) P.W[(size_t)(ts * 6 + k) * P.Wp + lm] = e.Jl[0] * e.Jt[k] + e.Jl[1] * e.Jt[6 + k];
                 if (rf)
-                    for (int k = 0; k < 6; ++k) atomicAdd(&P.W[(size_t)(rs * 6 + k) * M + lm], e.Jl[0] * e.Jr[k] + e.Jl[1] * e.Jr[6 + k]);
+                    for (int k = 0; k < 6; ++k) atomicAdd(&P.W[(size_t)(rs * 6 + k) * P.Wp + lm], e.Jl[0] * e.Jr[k] + e.Jl[1] * e.Jr[6 + k]);
             }
         }
     }
@@ -558,7 +585,7 @@ template <class SM> static __device__ void schur_landmarks(const Prob &P, SM &s,
                 if (!isfinite(ih)) ih = 0.0;
                 double wa[6], wb[6];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) { wa[k] = P.W[(size_t)(a * 6 + k) * M + l]; wb[k] = P.W[(size_t)(b * 6 + k) * M + l] * ih; }
+                for (int k = 0; k < 6; ++k) { wa[k] = P.W[(size_t)(a * 6 + k) * P.Wp + l]; wb[k] = P.W[(size_t)(b * 6 + k) * P.Wp + l] * ih; }
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -583,7 +610,7 @@ template <class SM> static __device__ void schur_landmarks(const Prob &P, SM &s,
             const int a = c / 6, k = c % 6;
             if (!s.pose_free[a]) continue;
             double v = 0.0;
-            for (int l = lane; l < M; l += 32) { double ih = 1.0 / P.ht_l[l]; if (!isfinite(ih)) ih = 0.0; v += P.W[(size_t)c * M + l] * P.g_l[l] * ih; }
+            for (int l = lane; l < M; l += 32) { double ih = 1.0 / P.ht_l[l]; if (!isfinite(ih)) ih = 0.0; v += P.W[(size_t)c * P.Wp + l] * P.g_l[l] * ih; }
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) rhs[15 * a + k] -= v;
         }

@@ -34,76 +34,156 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 #endif
 }
 
-// Same contract as schur_landmarks() (solve_core.cuh).  The 6 * n_active pose rows of W (row r = 6 * frame + k, landmarks
-// fastest) are cut into 16 x 16 blocks of the lower triangle, one warp per block and four m8n8k4 accumulators per warp;
-// the contraction runs over the landmarks four at a time.  Every output element is owned by exactly one lane.
+// ---- W tiles through the bulk-copy engine (north_star: "Hessian blocks staged through TMA into shared memory") ----------
+// The Schur complement reads every row of W (6 * n_active rows, one double per landmark) once per 16 x 16 output block that
+// touches it -- 12 times for a 30-keyframe window when the fragments come straight from L2.  Instead the CTA streams W through
+// shared memory in tiles of 32 landmarks: one cp.async.bulk of 256 bytes per row (plus one for the 32 values 1 / ht_l),
+// all signalling one mbarrier per buffer, double buffered so the copy of tile k + 1 runs under the tensor-pipe work on tile k.
+// Rows are padded to 36 doubles in shared memory: the four row groups a half-warp reads in one fragment load then fall
+// into distinct banks.  A warp carries at most three output blocks (24 accumulator registers), so windows with more than
+// 48 blocks take two passes over the tiles: every W element leaves L2 at most twice.
+constexpr int WT_L = 32;                           // landmarks per tile
+constexpr int WT_PITCH = 36;                       // doubles per staged row
+constexpr int WT_ROWS = 6 * kMaxActiveLarge;       // 192
+constexpr int WT_BLOCKS = 3;                       // output blocks per warp and pass
+struct alignas(128) WStage {
+    double w[2][WT_ROWS][WT_PITCH];
+    double ih[2][WT_L];
+    unsigned long long bar[2];
+};
+constexpr size_t kSmemLBytes = (sizeof(SmemL) + 127) / 128 * 128;      // WStage follows SmemL in the dynamic shared memory
+constexpr size_t kSolveLargeSmem = kSmemLBytes + sizeof(WStage);
+
+#ifndef CUEMU
+__device__ __forceinline__ unsigned xv_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void xv_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(xv_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void xv_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xv_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xv_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(xv_smem_u32(dst)), "l"(src), "r"(bytes), "r"(xv_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void xv_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 ::"r"(xv_smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
+// warp 0: start the copy of the tile of landmarks [l0, l0 + 32) into buffer `buf`
+__device__ __forceinline__ void wstage_issue(WStage &ws, int buf, const double *W, int Wp, const double *ihv, int R, int l0, int lane) {
+#ifndef CUEMU
+    if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        xv_mbar_expect_tx(&ws.bar[buf], (unsigned)((R + 1) * WT_L * sizeof(double)));
+    }
+    __syncwarp();
+    for (int r = lane; r < R; r += 32) xv_bulk_g2s(&ws.w[buf][r][0], W + (size_t)r * Wp + l0, WT_L * sizeof(double), &ws.bar[buf]);
+    if (lane == 0) xv_bulk_g2s(&ws.ih[buf][0], ihv + l0, WT_L * sizeof(double), &ws.bar[buf]);
+#else
+    for (int r = lane; r < R; r += 32)
+        for (int k = 0; k < WT_L; ++k) ws.w[buf][r][k] = W[(size_t)r * Wp + l0 + k];
+    ws.ih[buf][lane] = ihv[l0 + lane];
+#endif
+}
+
+// Same contract as schur_landmarks() (solve_core.cuh).  The 6 * n_active pose rows of W are cut into 16 x 16 blocks of the
+// lower triangle, four m8n8k4 accumulators per block; the contraction runs over the landmarks four at a time on the
+// FP64 tensor pipe, operands from the staged tiles.  Every output element is owned by exactly one lane.
 template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM &s, double *rhs) {
     XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(rhs);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int M = P.M, na = P.d.n_active;
+    const int M = P.M, na = P.d.n_active, Wp = P.Wp;
     if (M <= 0) return;
+    WStage &ws = *reinterpret_cast<WStage *>(reinterpret_cast<unsigned char *>(&s) + kSmemLBytes);
+    XV_ASSUME_SHARED(&ws);
     const int R = 6 * na;
     const int nb = (R + 15) / 16;
+    const int nblk = nb * (nb + 1) / 2;
     const int g = lane >> 2, t = lane & 3;
-    // 1 / ht_l once per landmark (non-finite -> 0: the landmark is skipped, marginalization_factor.h:384-386); y_l is free
-    // until the back-substitution at the end of gauss_newton()
+    // 1 / ht_l once per landmark (non-finite -> 0: the landmark is skipped, marginalization_factor.h:384-386), 0 in the padding
+    // columns; y_l is free until the back-substitution at the end of gauss_newton()
     double *ihv = P.y_l;
-    for (int l = tid; l < M; l += ST) { double ih = 1.0 / P.ht_l[l]; if (!isfinite(ih)) ih = 0.0; ihv[l] = ih; }
+    for (int l = tid; l < Wp; l += ST) { double ih = l < M ? 1.0 / P.ht_l[l] : 0.0; if (!isfinite(ih)) ih = 0.0; ihv[l] = ih; }
+#ifndef CUEMU
+    if (tid == 0) { xv_mbar_init(&ws.bar[0], 1); xv_mbar_init(&ws.bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#endif
     __syncthreads();
-    for (int blk = warp; blk < nb * (nb + 1) / 2; blk += NW) {
-        int bi = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
-        while (bi * (bi + 1) / 2 > blk) --bi;
-        while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
-        const int bj = blk - bi * (bi + 1) / 2;        // bi >= bj
-        double acc[2][2][2];
+    const int T = Wp / WT_L;
+    unsigned uses0 = 0, uses1 = 0;                     // completed phases per buffer (parity of the next wait)
+    for (int pass = 0; pass * NW * WT_BLOCKS < nblk; ++pass) {
+        int bi[WT_BLOCKS], bj[WT_BLOCKS];
+        double acc[WT_BLOCKS][2][2][2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) (&acc[0][0][0])[i] = 0.0;
-        const int ra0 = bi * 16 + g, ra1 = ra0 + 8;      // rows of the two A fragments
-        const int cb0 = bj * 16 + g, cb1 = cb0 + 8;      // columns of the two B fragments
-        const double *wa0 = P.W + (size_t)ra0 * M, *wa1 = P.W + (size_t)ra1 * M;
-        const double *wb0 = P.W + (size_t)cb0 * M, *wb1 = P.W + (size_t)cb1 * M;
-        // four k-steps per pass: the 16 fragment loads (L2 latency) are issued before the 16 tensor-pipe instructions
-        for (int l0 = 0; l0 < M; l0 += 16) {
-            double a0[4], a1[4], b0[4], b1[4];
+        for (int q = 0; q < WT_BLOCKS; ++q) {
+            const int blk = warp + NW * (WT_BLOCKS * pass + q);
+            int i = -1, j = -1;
+            if (blk < nblk) {
+                i = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
+                while (i * (i + 1) / 2 > blk) --i;
+                while ((i + 1) * (i + 2) / 2 <= blk) ++i;
+                j = blk - i * (i + 1) / 2;             // i >= j
+            }
+            bi[q] = i; bj[q] = j;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int l = l0 + 4 * u + t;
-                a0[u] = a1[u] = b0[u] = b1[u] = 0.0;
-                if (l < M) {
-                    const double ih = ihv[l];
-                    if (ra0 < R) a0[u] = wa0[l];
-                    if (ra1 < R) a1[u] = wa1[l];
-                    if (cb0 < R) b0[u] = wb0[l] * ih;
-                    if (cb1 < R) b1[u] = wb1[l] * ih;
+            for (int e = 0; e < 8; ++e) (&acc[q][0][0][0])[e] = 0.0;
+        }
+        if (warp == 0) wstage_issue(ws, 0, P.W, Wp, ihv, R, 0, lane);
+        for (int k = 0; k < T; ++k) {
+            const int buf = k & 1;
+            if (warp == 0 && k + 1 < T) wstage_issue(ws, buf ^ 1, P.W, Wp, ihv, R, (k + 1) * WT_L, lane);     // its readers passed the barrier below
+#ifndef CUEMU
+            xv_mbar_wait(&ws.bar[buf], (buf ? uses1 : uses0) & 1u);
+#else
+            __syncthreads();
+#endif
+            if (buf) ++uses1; else ++uses0;
+            const double(*wt)[WT_PITCH] = ws.w[buf];
+            const double *iht = ws.ih[buf];
+#pragma unroll
+            for (int q = 0; q < WT_BLOCKS; ++q) {
+                if (bi[q] < 0) continue;                // warp-uniform
+                const int ra0 = bi[q] * 16 + g, ra1 = ra0 + 8;      // rows of the two A fragments
+                const int cb0 = bj[q] * 16 + g, cb1 = cb0 + 8;      // columns of the two B fragments
+#pragma unroll
+                for (int u = 0; u < WT_L / 4; ++u) {
+                    const int l = 4 * u + t;
+                    const double ih = iht[l];
+                    const double a0 = ra0 < R ? wt[ra0][l] : 0.0, a1 = ra1 < R ? wt[ra1][l] : 0.0;
+                    const double b0 = cb0 < R ? wt[cb0][l] * ih : 0.0, b1 = cb1 < R ? wt[cb1][l] * ih : 0.0;
+                    dmma_m8n8k4(acc[q][0][0][0], acc[q][0][0][1], a0, b0);
+                    dmma_m8n8k4(acc[q][0][1][0], acc[q][0][1][1], a0, b1);
+                    dmma_m8n8k4(acc[q][1][0][0], acc[q][1][0][1], a1, b0);
+                    dmma_m8n8k4(acc[q][1][1][0], acc[q][1][1][1], a1, b1);
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                dmma_m8n8k4(acc[0][0][0], acc[0][0][1], a0[u], b0[u]);
-                dmma_m8n8k4(acc[0][1][0], acc[0][1][1], a0[u], b1[u]);
-                dmma_m8n8k4(acc[1][0][0], acc[1][0][1], a1[u], b0[u]);
-                dmma_m8n8k4(acc[1][1][0], acc[1][1][1], a1[u], b1[u]);
-            }
+            __syncthreads();                            // buffer `buf` may be refilled (tile k + 2) from the next iteration on
         }
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
+        for (int q = 0; q < WT_BLOCKS; ++q) {
+            if (bi[q] < 0) continue;
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc)
+            for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int r = bi * 16 + rr * 8 + g, c = bj * 16 + cc * 8 + 2 * t + i;
-                    if (r >= R || c > r) continue;
-                    const int fa = r / 6, fb = c / 6;
-                    if (!s.pose_free[fa] || !s.pose_free[fb]) continue;
-                    s.H[hidx(15 * fa + r % 6, 15 * fb + c % 6)] -= acc[rr][cc][i];
-                }
+                for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int r = bi[q] * 16 + rr * 8 + g, c = bj[q] * 16 + cc * 8 + 2 * t + i;
+                        if (r >= R || c > r) continue;
+                        const int fa = r / 6, fb = c / 6;
+                        if (!s.pose_free[fa] || !s.pose_free[fb]) continue;
+                        s.H[hidx(15 * fa + r % 6, 15 * fb + c % 6)] -= acc[q][rr][cc][i];
+                    }
+        }
     }
     // b_red = gs_p - sum_l w_l gs_l / ht_l
     for (int c = warp; c < R; c += NW) {
         const int a = c / 6, k = c % 6;
         if (!s.pose_free[a]) continue;
         double v = 0.0;
-        for (int l = lane; l < M; l += 32) v += P.W[(size_t)c * M + l] * P.g_l[l] * ihv[l];
+        for (int l = lane; l < M; l += 32) v += P.W[(size_t)c * Wp + l] * P.g_l[l] * ihv[l];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) rhs[15 * a + k] -= v;
     }
