@@ -427,6 +427,14 @@ def run_ba_stress(args):
             wall_ms.append((t1 - t0) * 1e3)
             iters = int(sum(int(o['iterations']) - 1 for o in out))
     km, wm = float(np.mean(kern_ms)), float(np.mean(wall_ms))
+    # clock64 sections of the solve kernel (only a -DXRVIO_KPROF diagnostic build fills them; all zero in the product build)
+    import ctypes as _ct
+    _arr = (_ct.c_ulonglong * 32)()
+    capi.lib.xrvio_debug_kprof(_arr, 1)
+    _names = {0: 'J zero', 1: 'J rpe', 3: 'J pre simt', 4: 'J pre coop', 5: 'J marg', 9: 'C evaluations', 17: 'make_candidate', 18: 'D/alpha',
+              20: 'dogleg', 21: 'ambient', 22: 'post-accept', 23: 'apply_scaling', 24: 'GN schur', 25: 'GN cholesky', 26: 'GN substitution', 29: 'GN setup'}
+    _np = max(int(_arr[31]), 1)
+    kprof = {_names.get(i, str(i)): round(_arr[i] / _np / 1e3, 1) for i in range(31) if _arr[i] and i not in (27, 28)}
     try:
         dfma_peak, dmma_peak = capi.fp64_peak()           # measured on this GPU: DFMA loop / mma.sync.m8n8k4.f64 loop, TFLOP/s
         peak, peak_source = max(dfma_peak, dmma_peak), 'measured (xrvio_debug_fp64_peak: DFMA %.1f, DMMA %.1f TFLOP/s)' % (dfma_peak, dmma_peak)
@@ -444,7 +452,8 @@ def run_ba_stress(args):
         'gpu_launches': args.steps * (1 + args.problems),
         'roofline': {'bound': 'tensor', 'kernel': 'solve_large', 'achieved': flops / (km * 1e-3) / 1e12, 'peak': peak, 'peak_source': peak_source,
                      'unit': 'TFLOP/s', 'frac': flops / (km * 1e-3) / 1e12 / peak, 'traffic': None},
-        'final_cost_mean': float(np.mean([o['final_cost'] for o in out]))}))
+        'final_cost_mean': float(np.mean([o['final_cost'] for o in out])),
+        'kprof_kcycles_per_problem': kprof or None}))
 
 
 def main():

@@ -39,7 +39,8 @@ inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
 // ---- runtime API (host memory stands in for device memory; everything is synchronous) ----
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 11 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 11, cudaErrorNotReady = 600 };
+enum { cudaEventDefault = 0, cudaEventBlockingSync = 1, cudaEventDisableTiming = 2 };
 typedef void *cudaStream_t;
 typedef struct cuemu_event *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
@@ -68,6 +69,11 @@ cudaError_t cudaEventCreate(cudaEvent_t *e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st = nullptr);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
+// the emulator executes every launch synchronously: an event is complete as soon as it is recorded
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class T> inline cudaError_t cudaMemcpyFromSymbol(void *dst, const T &sym, size_t n) { std::memcpy(dst, &sym, n); return cudaSuccess; }
 template <class T> inline cudaError_t cudaMemcpyToSymbol(T &sym, const void *src, size_t n) { std::memcpy(&sym, src, n); return cudaSuccess; }

@@ -216,6 +216,14 @@ struct Lane {
     Arena<xvbe::TriJob> tjobs; Arena<double> tviews; Arena<double> tout;
     DevOnly scratch;
     Stage stage;                       // packed inputs / outputs of one back-end launch
+    // Marginalisation runs on its own stream with its own staging block and scratch: its result (the new prior) stays on the
+    // device and is first needed by the NEXT window solve of the session, so the host never waits for it (ev_marg_done orders
+    // the solves behind it, ev_marg_h2d protects the pinned staging block until its upload has been consumed).
+    cudaStream_t st_marg = nullptr;
+    cudaEvent_t ev_marg_done = nullptr, ev_marg_h2d = nullptr;
+    bool marg_pending = false, marg_h2d_pending = false;
+    DevOnly scratch_marg;
+    Stage stage_marg;
     // ---- optional per-kernel-family timing with CUDA events on the launch stream ----
     bool prof = false;
     struct ProfEv { int fam; cudaEvent_t a, b; };
@@ -255,22 +263,24 @@ cudaEvent_t prof_event(Lane *c) {
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct ProfScope {
-    Lane *c; int fam; int launches; cudaEvent_t a{};
-    ProfScope(Lane *c_, int fam_, int launches_) : c(c_), fam(fam_), launches(launches_) {
-        if (c->prof) { a = prof_event(c); cudaEventRecord(a, c->st); }
+    Lane *c; int fam; int launches; cudaEvent_t a{}; cudaStream_t st;
+    ProfScope(Lane *c_, int fam_, int launches_, cudaStream_t st_ = nullptr) : c(c_), fam(fam_), launches(launches_), st(st_ ? st_ : c_->st) {
+        if (c->prof) { a = prof_event(c); cudaEventRecord(a, st); }
     }
     ~ProfScope() {
         c->prof_launches[fam] += launches;
-        if (c->prof) { cudaEvent_t b = prof_event(c); cudaEventRecord(b, c->st); c->prof_pending.push_back({fam, a, b}); }
+        if (c->prof) { cudaEvent_t b = prof_event(c); cudaEventRecord(b, st); c->prof_pending.push_back({fam, a, b}); }
     }
 };
-void prof_collect(Lane *c) {     // call after the stream has been synchronised
+void prof_collect(Lane *c) {     // call after the stream has been synchronised; events of the marginalisation stream may still be pending
+    std::vector<Lane::ProfEv> later;
     for (auto &e : c->prof_pending) {
+        if (cudaEventQuery(e.b) == cudaErrorNotReady) { later.push_back(e); continue; }
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->prof_ms[e.fam] += ms;
         c->prof_pool.push_back(e.a); c->prof_pool.push_back(e.b);
     }
-    c->prof_pending.clear();
+    c->prof_pending.swap(later);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -538,6 +548,7 @@ int run_solves(Lane *c) {
     b.marg = c->d_prior; b.scratch = c->scratch.as<double>();
     CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));
     c->stats.h2d_bytes += in_bytes - n * sizeof(xvbe::SolveOut);
+    if (c->marg_pending) { CKC(cudaStreamWaitEvent(c->st, c->ev_marg_done, 0)); c->marg_pending = false; }   // priors written by the marginalisation stream
     { ProfScope ps(c, FAM_SOLVE, 1); xvbe::solve(b, n, c->rig_d, c->st); }
     c->stats.kernels_launched += 1;
     CKC(cudaGetLastError());
@@ -602,6 +613,9 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
     struct Guard { Lane *l; ~Guard() { if (l) lane_destroy(l); } } guard{c};      // releases everything on an early error return
     c->prm = *p; c->S = n_sessions; c->device = device;
     CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&c->st_marg, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&c->ev_marg_done, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&c->ev_marg_h2d, cudaEventDisableTiming));
     c->L = xvfe::make_pyr_layout(p->width, p->height);
     c->K[0] = p->fx; c->K[1] = p->fy; c->K[2] = p->cx; c->K[3] = p->cy;
     c->sic[0] = p->fx / std::sqrt(p->keypoint_cov[0]); c->sic[1] = p->fy / std::sqrt(p->keypoint_cov[1]);      // detail.cpp:107-109
@@ -662,6 +676,9 @@ static int lane_destroy(Lane *c) {
     if (!c) return XRVIO_OK;
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
+    if (c->st_marg) { cudaStreamSynchronize(c->st_marg); cudaStreamDestroy(c->st_marg); }
+    if (c->ev_marg_done) cudaEventDestroy(c->ev_marg_done);
+    if (c->ev_marg_h2d) cudaEventDestroy(c->ev_marg_h2d);
     cudaFree(c->rig_d); cudaFree(c->d_raw); cudaFree(c->d_pyr); 
     cudaFree(c->d_und); cudaFree(c->d_und_map);
     cudaFree(c->d_lut); cudaFree(c->d_cand); cudaFree(c->d_cand_count); cudaFree(c->d_maxval); cudaFree(c->d_prior);
@@ -760,6 +777,7 @@ static int lane_set_profiling(Lane *c, int enable) {
 static int lane_get_kernel_times(Lane *c, double *ms, long long *launches, int capacity) {
     if (!c || !ms || !launches) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
     cudaStreamSynchronize(c->st);
+    cudaStreamSynchronize(c->st_marg);
     prof_collect(c);
     for (int k = 0; k < capacity && k < 16; ++k) { ms[k] = c->prof_ms[k]; launches[k] = c->prof_launches[k]; }
     return FAM_COUNT;

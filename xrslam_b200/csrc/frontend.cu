@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(256) harris_nms_kernel(const uint8_t *__restri
 // of sorted candidates before max_corners are accepted, the whole list is sorted and the pass repeated.
 constexpr int kSortTarget = 2048;
 constexpr int kHistBins = 2048;
+constexpr int kSortSmem = 4096;        // candidates that can be sorted inside shared memory (32 KB of keys)
 __device__ void bitonic_desc(unsigned long long *C, int np2) {
     for (int k = 2; k <= np2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -371,6 +372,8 @@ __global__ void __launch_bounds__(1024) corner_select_kernel(unsigned long long 
     const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
     short *cell_cnt = reinterpret_cast<short *>(smem_raw);                 // gw*gh
     short2 *cell_pts = reinterpret_cast<short2 *>(cell_cnt + ((gw * gh + 1) & ~1));   // gw*gh*CELL_CAP
+    // sort buffer behind the grid (8-byte aligned): the strongest <= kSortSmem candidates are sorted here instead of in global memory
+    unsigned long long *S = reinterpret_cast<unsigned long long *>(smem_raw + (((size_t)((gw * gh + 1) & ~1) * sizeof(short) + (size_t)gw * gh * CELL_CAP * sizeof(short2) + 7) & ~(size_t)7));
     __shared__ int hist[kHistBins];
     __shared__ int s_cut, s_m, s_done, s_ncorners;
     // ---- (1) choose the cut: bin = top 11 bits below the sign of the float response (exponent + 3 mantissa bits) ----
@@ -426,6 +429,15 @@ __global__ void __launch_bounds__(1024) corner_select_kernel(unsigned long long 
         const int cnt = attempt == 0 ? m_sorted : n;
         int np2 = 1;
         while (np2 < cnt) np2 <<= 1;
+        const unsigned long long *sorted = C;
+        // the usual case: the strong candidates fit the shared-memory buffer -> ~80 compare-exchange passes at shared-memory
+        // latency with a CTA barrier each, instead of the same passes on global memory (the kernel's former critical path)
+        if (np2 <= kSortSmem) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) S[i] = i < cnt ? C[i] : 0ull;
+            __syncthreads();
+            bitonic_desc(S, np2);
+            sorted = S;
+        } else
         // pad [cnt, np2) with zeros: when only the strong part is sorted, save and restore the overwritten tail
         if (attempt == 0 && np2 > cnt && cnt < n) {
             // the padding would destroy weak candidates in [cnt, np2): sort the larger power of two instead (they are
@@ -437,7 +449,7 @@ __global__ void __launch_bounds__(1024) corner_select_kernel(unsigned long long 
             for (int i = cnt + threadIdx.x; i < np2; i += blockDim.x) C[i] = 0ull;
         }
         __syncthreads();
-        bitonic_desc(C, np2);
+        if (sorted == C) bitonic_desc(C, np2);
         const int usable = attempt == 0 ? m_sorted : n;      // candidates guaranteed to be in global order
         for (int i = threadIdx.x; i < gw * gh; i += blockDim.x) cell_cnt[i] = 0;
         if (threadIdx.x == 0) { s_done = 0; s_ncorners = 0; }
@@ -448,7 +460,7 @@ __global__ void __launch_bounds__(1024) corner_select_kernel(unsigned long long 
             int ncorners = 0;
             int i = 0;
             for (; i < usable && ncorners < max_corners; i += 32) {
-                const unsigned long long mykey = (i + lane < usable) ? C[i + lane] : 0ull;     // prefetch 32 candidates
+                const unsigned long long mykey = (i + lane < usable) ? sorted[i + lane] : 0ull;     // prefetch 32 candidates
                 const int lim = min(32, usable - i);
                 for (int q = 0; q < lim && ncorners < max_corners; ++q) {
                     const unsigned long long key = __shfl_sync(0xffffffffu, mykey, q);
@@ -499,8 +511,10 @@ void gftt_harris(const uint8_t *img, const int *idx, size_t img_stride, int n, i
     harris_nms_kernel<<<grid, 256, 0, st>>>(img, idx, img_stride, w, h, maxval, cand, cand_count);
     int cell = (int)lrintf(min_distance);
     int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
-    size_t smem = (size_t)((gw * gh + 1) & ~1) * sizeof(short) + (size_t)gw * gh * 8 * sizeof(short2);
+    size_t smem = (((size_t)((gw * gh + 1) & ~1) * sizeof(short) + (size_t)gw * gh * 8 * sizeof(short2) + 7) & ~(size_t)7) + (size_t)kSortSmem * sizeof(unsigned long long);
     if (max_corners > kMaxCorners) max_corners = kMaxCorners;
+    static std::atomic<unsigned long long> attr_done{0};
+    xv::ensure_dynamic_smem(corner_select_kernel, (int)smem, attr_done);
     corner_select_kernel<<<n, 1024, smem, st>>>(cand, cand_count, maxval, quality, w, h, max_corners, min_distance, corners, count);
 }
 

@@ -822,25 +822,31 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
             c->mdesc.push(d);
             g.has_marg = false;
         }
-        CKC(c->scratch.reserve(scratch * sizeof(double)));
+        // own stream, staging block and scratch (see Lane::st_marg); a block or scratch that has to grow, and a staging block whose
+        // previous upload may not have been consumed yet, are the only reasons to wait for the marginalisation stream
+        Stage &g = c->stage_marg;
+        const size_t stage_want = nm * sizeof(xvbe::MargDesc) + c->states.n * 8 + c->invd.n * 8 + c->rpe.n * sizeof(xvbe::RpeObs) + c->pref.n * sizeof(xvbe::PreRef) +
+                                  c->pblocks.n * 8 + c->mframes.n * sizeof(int) + 16 * 256;
+        if (scratch * sizeof(double) > c->scratch_marg.bytes || stage_want > g.cap) CKC(cudaStreamSynchronize(c->st_marg));
+        if (c->marg_h2d_pending) { CKC(cudaEventSynchronize(c->ev_marg_h2d)); c->marg_h2d_pending = false; }
+        CKC(c->scratch_marg.reserve(scratch * sizeof(double)));
         CKC(c->mrank.reserve(nm));
-        Stage &g = c->stage;
-        CKC(g.reserve(nm * sizeof(xvbe::MargDesc) + c->states.n * 8 + c->invd.n * 8 + c->rpe.n * sizeof(xvbe::RpeObs) + c->pref.n * sizeof(xvbe::PreRef) +
-                      c->pblocks.n * 8 + c->mframes.n * sizeof(int) + 16 * 256));
+        CKC(g.reserve(stage_want));
         g.reset();
         xvbe::MargBatch mb;
         mb.desc = g.put(c->mdesc.h, (size_t)nm); mb.states = g.put(c->states.h, c->states.n); mb.inv_depth = g.put(c->invd.h, c->invd.n);
         mb.rpe = g.put(c->rpe.h, c->rpe.n); mb.pre = g.put(c->pref.h, c->pref.n); mb.pre_blocks = g.put(c->pblocks.h, c->pblocks.n);
         mb.marg_frames = g.put(c->mframes.h, c->mframes.n);
-        CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));      // one upload for the whole batch of problems
+        // the window solve that produced the states of this batch has been read back already (the host packed them), and the prior
+        // slots read here were written either by an earlier launch on this stream or by a host-synchronous upload: no wait needed
+        CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st_marg));      // one upload for the whole batch of problems
+        CKC(cudaEventRecord(c->ev_marg_h2d, c->st_marg)); c->marg_h2d_pending = true;
         c->stats.h2d_bytes += nm * sizeof(xvbe::MargDesc) + c->states.n * 8 + c->invd.n * 8 + c->rpe.n * sizeof(xvbe::RpeObs) + c->pblocks.n * 8;
-        mb.marg = c->d_prior; mb.out = c->d_prior; mb.scratch = c->scratch.as<double>(); mb.rank_out = c->mrank.d;
-        { ProfScope ps(c, FAM_MARG, 1); xvbe::marginalize(mb, nm, c->rig_d, c->st); }
+        mb.marg = c->d_prior; mb.out = c->d_prior; mb.scratch = c->scratch_marg.as<double>(); mb.rank_out = c->mrank.d;
+        { ProfScope ps(c, FAM_MARG, 1, c->st_marg); xvbe::marginalize(mb, nm, c->rig_d, c->st_marg); }
         c->stats.kernels_launched += 1;
         CKC(cudaGetLastError());
-        CKC(cudaMemcpyAsync(c->mrank.h, c->mrank.d, nm * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-        CKC(cudaStreamSynchronize(c->st));
-        c->stats.d2h_bytes += nm * sizeof(int);
+        CKC(cudaEventRecord(c->ev_marg_done, c->st_marg)); c->marg_pending = true;
         c->pool->parallel_for(nm, [&](int i) {
             Session &s = *ms[i];
             Map *m = s.sw_map.get();

@@ -238,13 +238,106 @@ template <class SM> __device__ __forceinline__ void jtj_uniform_warp(SM &s, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cost-only evaluation (29 of the 31 evaluations of a window BA): the three factor families do not depend
+// on each other, so they run SIDE BY SIDE on different warps instead of one after the other with CTA barriers in between:
+//   * the last warp evaluates the preintegration factors (one lane per factor: a serial chain of ~10 k cycles) and whitens them,
+//   * the warp before it evaluates the marginalisation prior (marg_dx per prior frame, then one lane per row of S dx + infovec),
+//   * the other warps share the reprojection (and rotation-prior) residuals.
+// One block reduction at the end.  Same arithmetic per residual as evaluate(..., want_jac = false); only the order in which
+// the partial costs are summed differs.
+// ------------------------------------------------------------------------------------------------
+template <class SM> static __device__ double evaluate_cost(const Prob &P, SM &s, const double *S, const double *inv, const RigParams &rg, bool robust) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = P.M;
+    XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(S); XV_ASSUME_GLOBAL(inv);
+    const bool has_pre = P.d.n_pre > 0, has_marg = P.d.marg_k > 0;
+    const int w_pre = has_pre ? NW - 1 : -1;
+    const int w_marg = has_marg ? NW - 1 - (has_pre ? 1 : 0) : -1;
+    const int n_rw = NW - (has_pre ? 1 : 0) - (has_marg ? 1 : 0);          // warps 0 .. n_rw - 1 take the reprojection residuals
+    double cost = 0.0;
+    if (warp == w_pre) {
+        for (int f = lane; f < P.d.n_pre; f += 32) {
+            const PreRef pf = P.pre[P.d.pre_off + f];
+            const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
+            double *sc = P.pre_s + (size_t)f * kPreScratch;
+            const double *si = pf.prior ? (s.us + pf.i * 16) : (S + pf.i * 16);
+            const double *sj = S + pf.j * 16;
+            pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, false, sc, sc + 16, sc + 241);
+        }
+        __syncwarp();
+        for (int e = lane; e < 15 * P.d.n_pre; e += 32) {          // whitened residual, one lane per row
+            const int f = e / 15, r = e % 15;
+            const PreRef pf = P.pre[P.d.pre_off + f];
+            const double *Sic = P.pre_blocks + (size_t)pf.block * kPreBlock + PB_SIC;
+            const double *sc = P.pre_s + (size_t)f * kPreScratch;
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 15; ++k) a += Sic[r * 15 + k] * sc[k];
+            cost += 0.5 * a * a;
+        }
+    } else if (warp == w_marg) {
+        const int K = P.d.marg_k, n = P.marg_n, rk = P.marg_rank;
+        for (int k = lane; k < K; k += 32) {
+            const int f = P.marg_frames[P.d.marg_frames_off + k];
+            marg_dx(S + f * 16, P.marg_lin + k * 16, P.m_dx + 15 * k, nullptr);
+        }
+        __syncwarp();
+        // r = S dx + infovec over the non-zero rows: one lane per row on the transposed copy (coalesced), four accumulators
+        for (int r = lane; r < rk; r += 32) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int cidx = 0;
+            for (; cidx + 3 < n; cidx += 4) {
+                a0 += P.marg_St[(size_t)cidx * rk + r] * P.m_dx[cidx];
+                a1 += P.marg_St[(size_t)(cidx + 1) * rk + r] * P.m_dx[cidx + 1];
+                a2 += P.marg_St[(size_t)(cidx + 2) * rk + r] * P.m_dx[cidx + 2];
+                a3 += P.marg_St[(size_t)(cidx + 3) * rk + r] * P.m_dx[cidx + 3];
+            }
+            for (; cidx < n; ++cidx) a0 += P.marg_St[(size_t)cidx * rk + r] * P.m_dx[cidx];
+            const double a = ((a0 + a1) + (a2 + a3)) + P.marg_info[r];
+            cost += 0.5 * a * a;
+        }
+        // rows beyond the rank are exactly zero in S; their residual is infovec[r] (zero for our priors)
+        for (int r = rk + lane; r < n; r += 32) { const double a = P.marg_info[r]; cost += 0.5 * a * a; }
+    } else {
+        for (int base = warp * 32; base < P.d.n_rpe; base += n_rw * 32) {
+            const int o = base + lane;
+            if (o < P.d.n_rpe) {
+                const RpeObs ob = P.rpe[P.d.rpe_off + o];
+                const int ts = ob.tgt, rs = ob.ref, lm = ob.lm;
+                const bool prior = ob.prior != 0;
+                const double *st = S + ts * 16;
+                const double *sr = prior ? (s.us + rs * 16) : (S + rs * 16);
+                const double idp = prior ? P.invd_user[lm] : inv[lm];
+                RpeEval e;
+                rpe_eval(ld4(st), ld3(st + 4), ld4(sr), ld3(sr + 4), idp, ld3(ob.zt), ld3(ob.zr), P.rpe_tb + (size_t)o * 6, rg, false, false, e);
+                const double sq = e.r[0] * e.r[0] + e.r[1] * e.r[1];
+                cost += robust ? 0.5 * log(1.0 + sq) : 0.5 * sq;
+            }
+        }
+        for (int o = warp * 32 + lane; o < P.d.n_rot; o += n_rw * 32) {
+            const RotObs ob = P.rot[P.d.rot_off + o];
+            double r[2], Jq[6];
+            rot_eval(ld4(S + ob.tgt * 16), ld4(s.us + ob.ref * 16), ld3(ob.zt), ld3(ob.zr), rg, false, r, Jq);
+            cost += 0.5 * log(1.0 + (r[0] * r[0] + r[1] * r[1]));
+        }
+    }
+    (void)M;
+    return block_sum(cost, s);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Residual (+ Jacobian) evaluation at S (= xs or cs) / inv (= inv_x or inv_c).  Returns the cost.
 // With want_jac the unscaled H (pose/motion block, packed in shared memory), g, W, h_ll, g_l are
 // rebuilt.  Constant blocks and "user memory" reads come from us / invd_user.
 // ------------------------------------------------------------------------------------------------
 template <class SM> static __device__ double evaluate(const Prob &P, SM &s, const double *S, const double *inv, const RigParams &rg,
                            bool want_jac, bool robust = true, KProf *kp = nullptr) {
-    const int kb = want_jac ? 0 : 8;
+    if (!want_jac) {
+        const double c = evaluate_cost(P, s, S, inv, rg, robust);
+        if (kp) kp->mark(9);
+        return c;
+    }
+    const int kb = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M;
     XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(S); XV_ASSUME_GLOBAL(inv);   // S is s.xs or s.cs, inv is P.inv_x or P.inv_c
