@@ -240,7 +240,10 @@ def test_window_solves_hit_the_iteration_limit(xrvio):
     st = ctx.stats()
     # the first window solve of a session is the bootstrap BA (counted in window_solves, not a refine_window)
     refine = int(st['window_solves']) - len(streams)
-    assert refine >= 12
-    assert int(st['window_at_limit']) == refine
+    # the oracle on the same 3 x 60 frames (tests/test_oracle.py runs the first 48): 15 refine_window solves, every one of them
+    # 30 iterations long; 13 end as "max iterations", 2 (stream 7) at the same 30th iteration because the radius, halved 29
+    # times, has pushed the step below the parameter tolerance
+    assert refine == 15
     assert int(st['window_iterations']) == 30 * refine
+    assert int(st['window_at_limit']) == 13
     ctx.close()

@@ -281,7 +281,9 @@ def test_window_ba_runs_to_the_iteration_limit():
         wins = [s for k, s in rec if k == 'window']
         assert len(wins) >= 2, (seed, [k for k, _ in rec])
         for s in wins:
-            assert s.termination == 'max iterations' and len(s.iterations) == 31, (seed, s.termination, len(s.iterations))
+            # (over longer runs a few solves end at the same 30th iteration as "parameter tolerance": the radius has been
+            # halved 29 times by then -- tests/test_gpu_pipeline.py counts both kinds on 60 frames)
+            assert s.termination in ('max iterations', 'parameter tolerance') and len(s.iterations) == 31, (seed, s.termination, len(s.iterations))
             ok = [it['iteration'] for it in s.iterations if it['successful']]
             assert ok[0] == 0 and len(ok) >= 2 and max(ok) <= 3, (seed, ok)       # accepted steps only at the very start
             tail = s.iterations[max(ok) + 1:]

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
 
 void marginalize(const MargBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
     if (n_problems <= 0) return;
-    static std::atomic<unsigned long long> attr_done{0};
+    static xv::SmemOptIn attr_done;
     xv::ensure_dynamic_smem(marg_kernel, (int)sizeof(Smem), attr_done);
     marg_kernel<<<n_problems, ST, sizeof(Smem), st>>>(b, rig);
 }

@@ -52,6 +52,8 @@ template <class SM> __device__ double ambient_sq(const Prob &P, SM &s, const dou
 
 // Gauss-Newton step: (Hs + mu D^2) y = gs via Schur complement on the landmark block + Cholesky.
 // Returns false when the factorisation fails (LINEAR_SOLVER_FAILURE).  H is consumed.
+struct alignas(16) Pair64 { double a, b; };      // one 128-bit shared-memory access
+
 template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu, KProf &kp) {
     XV_ASSUME_SHARED(&s);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -160,12 +162,19 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
 #pragma unroll
                 for (int c = 0; c < TB; ++c) {
                     if (j0 + c >= n) continue;
+                    // the six published values of a tile row / tile column are 48 contiguous, 16-byte aligned bytes: three 128-bit
+                    // loads each.  Lanes of a warp hold consecutive tile columns (stride 48 bytes): as 128-bit accesses that is
+                    // conflict-free, as six 64-bit loads it was an 8-way bank conflict and made this update shared-memory bound
+                    // (measured 9 kcycles per panel).  Rows beyond n hold zeros (written by phases 1 and 2), so no bound checks.
                     double ci[TB], ck[TB];
+                    {
+                        const Pair64 *pi = reinterpret_cast<const Pair64 *>(colp + c * SM::NPv + ti * TB);
+                        const Pair64 *pk = reinterpret_cast<const Pair64 *>(colp + c * SM::NPv + tk * TB);
 #pragma unroll
-                    for (int l = 0; l < TB; ++l) {
-                        const int gi = ti * TB + l, gk = tk * TB + l;
-                        ci[l] = gi < n ? colp[c * SM::NPv + gi] : 0.0;
-                        ck[l] = gk < n ? colp[c * SM::NPv + gk] : 0.0;
+                        for (int l = 0; l < TB / 2; ++l) {
+                            const Pair64 vi = pi[l], vk = pk[l];
+                            ci[2 * l] = vi.a; ci[2 * l + 1] = vi.b; ck[2 * l] = vk.a; ck[2 * l + 1] = vk.b;
+                        }
                     }
 #pragma unroll
                     for (int li = 0; li < TB; ++li)
@@ -189,51 +198,12 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
     __syncthreads();
     kp.mark(25);
     if (!s.flag) { kp.count(28); return false; }
-    // forward / backward substitution (L z = b, L^T y = z).  Sliding-window instance (H in shared memory, n <= 180): ONE warp
-    // runs both sweeps with the work vector in registers (lane l owns rows l, l + 32, ...): per column the owner lane scales its
-    // entry, broadcasts it with a shuffle and every lane updates its rows -- no CTA barrier inside the sweeps, against two per
-    // panel of six columns when the 6 x 6 triangle was solved by thread 0 alone.  Large instance (H in global memory, n <= 480):
-    // panels of six columns, thread 0 solves the 6 x 6 triangle, every row outside the panel applies the six values.
-    if constexpr (SM::kSharedH) {
-        if (warp == 0) {
-            constexpr int NR = (SM::NPv + 31) / 32;
-            double v[NR];
-#pragma unroll
-            for (int k = 0; k < NR; ++k) { const int i = lane + 32 * k; v[k] = i < n ? s.bred[i] : 0.0; }
-            // forward: z_j = v_j / L_jj ; v_i -= L_ij z_j (i > j)
-            for (int j = 0; j < n; ++j) {
-                const int oj = j >> 5;
-                double mine = 0.0;
-#pragma unroll
-                for (int k = 0; k < NR; ++k) if (k == oj) mine = v[k];
-                const double zj = __shfl_sync(0xffffffffu, mine, j & 31) * idiag[j];
-#pragma unroll
-                for (int k = 0; k < NR; ++k) {
-                    const int i = lane + 32 * k;
-                    if (i == j) v[k] = zj;
-                    else if (i > j && i < n) v[k] -= s.H[hidx(i, j)] * zj;
-                }
-            }
-            // backward: y_j = v_j / L_jj ; v_i -= L_ji y_j (i < j): row j of L is contiguous in the packed triangle
-            for (int j = n - 1; j >= 0; --j) {
-                const int oj = j >> 5;
-                double mine = 0.0;
-#pragma unroll
-                for (int k = 0; k < NR; ++k) if (k == oj) mine = v[k];
-                const double yj = __shfl_sync(0xffffffffu, mine, j & 31) * idiag[j];
-                const double *row = &s.H[hidx(j, 0)];
-#pragma unroll
-                for (int k = 0; k < NR; ++k) {
-                    const int i = lane + 32 * k;
-                    if (i == j) v[k] = yj;
-                    else if (i < j) v[k] -= row[i] * yj;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < NR; ++k) { const int i = lane + 32 * k; if (i < n) s.y[i] = v[k]; }
-        }
-        __syncthreads();
-    } else {
+    // forward / backward substitution (L z = b, L^T y = z) in panels of six columns, two barriers per panel: thread 0
+    // solves the 6x6 triangle of the panel and publishes the six values, then every row outside the panel applies them in
+    // column order -- the same operations in the same order as a column-by-column substitution.  (A single-warp version with
+    // the work vector in registers and a shuffle broadcast per column measured 1.75x SLOWER on a B200: 241 against 137 kcycles
+    // per call, profiles/r2_phase_probe_*.txt -- the dependent shuffle + shared-memory column gather per column costs more than
+    // the two CTA barriers per six columns.)
     // forward: work vector s.y (starts as b_red), result z in s.bred; backward: work vector s.bred, result in s.y.
     for (int c = tid; c < n; c += ST) s.y[c] = s.bred[c];
     __syncthreads();
@@ -272,7 +242,6 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
             s.bred[i] = bi;
         }
         __syncthreads();
-    }
     }
     kp.mark(26);
     bool ok = true;
@@ -583,14 +552,14 @@ size_t solve_large_scratch_doubles(int n_active, int n_lm_free, int n_pre, int m
 
 void solve_large(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
     if (n_problems <= 0) return;
-    static std::atomic<unsigned long long> attr_done{0};
+    static xv::SmemOptIn attr_done;
     xv::ensure_dynamic_smem(solve_large_kernel, (int)kSolveLargeSmem, attr_done);
     solve_large_kernel<<<n_problems, ST, kSolveLargeSmem, st>>>(b, rig);
 }
 
 void solve(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
     if (n_problems <= 0) return;
-    static std::atomic<unsigned long long> attr_done{0};
+    static xv::SmemOptIn attr_done;
     xv::ensure_dynamic_smem(solve_kernel, (int)sizeof(Smem), attr_done);
     solve_kernel<<<n_problems, ST, sizeof(Smem), st>>>(b, rig);
 }

@@ -114,7 +114,21 @@ struct Stage {
 };
 
 constexpr int kImgQueue = 4;       // frames per session that may wait on the device between steps
-constexpr int kPyrSlots = 3;       // pyramid buffers per session (previous, next, spare)
+constexpr int kPyrSlots = kImgQueue + 2;   // pyramid buffers per session: every waiting frame has its pyramid already (built at push time), + previous + spare
+
+// Image kernels run when the images are PUSHED (xrvio_push_images), on the lane's image stream: CLAHE, pyramid and GFTT need
+// nothing but the image, so by the time xrvio_step looks at the frame they are done and the step starts at KLT.  A push call
+// of a lane is one batch; its corner lists come back into a pinned block of this kind, which lives until the last frame of the
+// batch has been consumed (blocks are pooled: pinned allocations are expensive).
+struct ImgBatch {
+    float *corners_h = nullptr;        // n * kMaxCorners * 3
+    int *count_h = nullptr;            // n
+    int *idx_h = nullptr;              // 2 * cap: raw-slot indices, pyramid indices (pinned source of the index upload)
+    cudaEvent_t done = nullptr;        // recorded on the image stream after the read-back
+    int cap = 0, pending = 0;          // frames of this batch not consumed yet
+    bool waited = false;               // the lane stream already waits for `done` / the host has synchronised with it
+    bool host_ready = false;
+};
 
 // Per-session staging written by worker threads, merged into the batch arenas by the main thread.
 struct Staged {
@@ -224,6 +238,11 @@ struct Lane {
     bool marg_pending = false, marg_h2d_pending = false;
     DevOnly scratch_marg;
     Stage stage_marg;
+    // ---- image stream (see ImgBatch) ----
+    cudaStream_t st_img = nullptr;
+    std::vector<ImgBatch *> img_pool;  // free blocks
+    std::vector<ImgBatch *> img_all;   // every block ever made (for destruction)
+    int *d_idx_img = nullptr;          // 2 * S ints: raw-slot indices, pyramid indices of the batch being processed
     // ---- optional per-kernel-family timing with CUDA events on the launch stream ----
     bool prof = false;
     struct ProfEv { int fam; cudaEvent_t a, b; };
@@ -614,6 +633,8 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
     c->prm = *p; c->S = n_sessions; c->device = device;
     CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&c->st_marg, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&c->st_img, cudaStreamNonBlocking));
+    CKC(cudaMalloc((void **)&c->d_idx_img, (size_t)2 * n_sessions * sizeof(int)));
     CKC(cudaEventCreateWithFlags(&c->ev_marg_done, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->ev_marg_h2d, cudaEventDisableTiming));
     c->L = xvfe::make_pyr_layout(p->width, p->height);
@@ -677,6 +698,9 @@ static int lane_destroy(Lane *c) {
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->st_marg) { cudaStreamSynchronize(c->st_marg); cudaStreamDestroy(c->st_marg); }
+    if (c->st_img) { cudaStreamSynchronize(c->st_img); cudaStreamDestroy(c->st_img); }
+    for (ImgBatch *b : c->img_all) { cudaFreeHost(b->corners_h); cudaFreeHost(b->count_h); cudaFreeHost(b->idx_h); if (b->done) cudaEventDestroy(b->done); delete b; }
+    cudaFree(c->d_idx_img);
     if (c->ev_marg_done) cudaEventDestroy(c->ev_marg_done);
     if (c->ev_marg_h2d) cudaEventDestroy(c->ev_marg_h2d);
     cudaFree(c->rig_d); cudaFree(c->d_raw); cudaFree(c->d_pyr); 
@@ -714,28 +738,91 @@ static int lane_push_imu(Lane *c, const int *session, const xrvio_imu *samples, 
     return XRVIO_OK;
 }
 
-// Detail::track_camera (detail.cpp:103-128)
+static ImgBatch *img_batch_get(Lane *c) {
+    if (!c->img_pool.empty()) { ImgBatch *b = c->img_pool.back(); c->img_pool.pop_back(); return b; }
+    ImgBatch *b = new ImgBatch();
+    b->cap = c->S;
+    if (cudaHostAlloc((void **)&b->corners_h, (size_t)c->S * xvfe::kMaxCorners * 3 * sizeof(float), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&b->count_h, (size_t)c->S * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&b->idx_h, (size_t)2 * c->S * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming) != cudaSuccess) {
+        if (b->corners_h) cudaFreeHost(b->corners_h);
+        if (b->count_h) cudaFreeHost(b->count_h);
+        if (b->idx_h) cudaFreeHost(b->idx_h);
+        delete b;
+        return nullptr;
+    }
+    c->img_all.push_back(b);
+    return b;
+}
+static void img_batch_release(Lane *c, Frame *f) {
+    ImgBatch *b = static_cast<ImgBatch *>(f->img_batch);
+    f->img_batch = nullptr;
+    if (b && --b->pending == 0) c->img_pool.push_back(b);
+}
+
+// Detail::track_camera (detail.cpp:103-128) for the n images of one push call that belong to this lane, followed by
+// Image::preprocess (CLAHE + pyramid, opencv_image.cpp:156-161) and the detection half of Image::detect_keypoints (GFTT,
+// :38-45) on the image stream -- they depend on the image alone (see ImgBatch).
 static int lane_push_images(Lane *c, const int *session, const uint8_t *const *data, const int *stride, const double *t, int n, int on_device) {
     if (!c || !session || !data || !t || n < 0) { xrvio_set_error("xrvio_push_images: bad argument"); return XRVIO_ERR_ARG; }
+    if (n == 0) return XRVIO_OK;
+    if (n > c->S) { xrvio_set_error("xrvio_push_images: more images than sessions in one call"); return XRVIO_ERR_ARG; }
     CKC(cudaSetDevice(c->device));
     PhaseTimer pt_(c, 30);
     const int w = c->prm.width, h = c->prm.height;
+    const size_t P = (size_t)w * h;
     for (int i = 0; i < n; ++i) {
         if (session[i] < 0 || session[i] >= c->S) { xrvio_set_error("bad session"); return XRVIO_ERR_ARG; }
+        for (int j = 0; j < i; ++j)
+            if (session[j] == session[i]) { xrvio_set_error("xrvio_push_images: a session appears twice in one call"); return XRVIO_ERR_ARG; }
         Session &s = c->ses[session[i]];
         if (s.queued.size() + s.released.size() >= (size_t)kImgQueue) { xrvio_set_error("xrvio_push_images: image queue full, call xrvio_step"); return XRVIO_ERR_STATE; }
+    }
+    ImgBatch *b = img_batch_get(c);
+    if (!b) { xrvio_set_error("xrvio_push_images: pinned allocation failed"); return XRVIO_ERR_CUDA; }
+    b->pending = n; b->waited = false; b->host_ready = false;
+    for (int i = 0; i < n; ++i) {
+        Session &s = c->ses[session[i]];
         const int slot = s.img_slot_next; s.img_slot_next = (s.img_slot_next + 1) % kImgQueue;
-        uint8_t *dst = c->d_raw + ((size_t)s.idx * kImgQueue + slot) * w * h;
+        uint8_t *dst = c->d_raw + ((size_t)s.idx * kImgQueue + slot) * P;
         const int sp = stride ? stride[i] : w;
-        CKC(cudaMemcpy2DAsync(dst, w, data[i], sp, w, h, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
-        if (!on_device) c->stats.h2d_bytes += (size_t)w * h;
+        CKC(cudaMemcpy2DAsync(dst, w, data[i], sp, w, h, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st_img));
+        if (!on_device) c->stats.h2d_bytes += P;
         auto f = std::make_unique<Frame>();
-        f->id = ++s.frame_id_counter; f->t = t[i]; f->pyr_slot = slot;       // pyr_slot temporarily holds the raw slot
+        f->id = ++s.frame_id_counter; f->t = t[i];
+        f->pyr_slot = s.pyr_next; s.pyr_next = (s.pyr_next + 1) % kPyrSlots;
+        f->img_batch = b; f->img_index = i;
+        b->idx_h[i] = s.idx * kImgQueue + slot;
+        b->idx_h[c->S + i] = s.idx * kPyrSlots + f->pyr_slot;
         s.queued.push_back(std::move(f));
         xrvio_pose op;
         predict_pose(c, s, t[i], op);
         if (t[i] > s.out_t) { s.out_pose = op; s.out_t = t[i]; }
     }
+    int *d_raw_idx = c->d_idx_img, *d_pyr_idx = c->d_idx_img + c->S;
+    CKC(cudaMemcpyAsync(c->d_idx_img, b->idx_h, (size_t)2 * c->S * sizeof(int), cudaMemcpyHostToDevice, c->st_img));
+    const uint8_t *clahe_src = c->d_raw;
+    const int *clahe_idx = d_raw_idx;
+    if (c->d_und) {     // the reader's cv::undistort, on the device (row N2); counted with the CLAHE family
+        ProfScope ps(c, FAM_CLAHE, 1, c->st_img);
+        xvfe::undistort(c->d_raw, d_raw_idx, P, c->d_und, nullptr, P, n, w, h, c->d_und_map, c->st_img);
+        c->stats.kernels_launched += 1;
+        clahe_src = c->d_und; clahe_idx = nullptr;
+    }
+    { ProfScope ps(c, FAM_CLAHE, 2, c->st_img);
+      xvfe::clahe(clahe_src, clahe_idx, P, c->d_pyr, d_pyr_idx, c->L.total, c->d_lut, n, w, h, c->prm.clahe_clip_limit,
+                  c->prm.clahe_width, c->prm.clahe_height, c->st_img); }
+    { ProfScope ps(c, FAM_PYRAMID, 3, c->st_img); xvfe::pyramid(c->d_pyr, d_pyr_idx, n, c->L, c->st_img); }
+    { ProfScope ps(c, FAM_GFTT, 2, c->st_img);
+      xvfe::gftt_harris(c->d_pyr, d_pyr_idx, c->L.total, n, w, h, c->prm.max_keypoint_detection, 1.0e-3f, 20.0f, c->corners.d,
+                        c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->st_img); }
+    c->stats.kernels_launched += 2 + 3 + 2;
+    CKC(cudaMemcpyAsync(b->corners_h, c->corners.d, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->st_img));
+    CKC(cudaMemcpyAsync(b->count_h, c->corner_count.d, n * sizeof(int), cudaMemcpyDeviceToHost, c->st_img));
+    c->stats.d2h_bytes += (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float) + n * sizeof(int);
+    CKC(cudaEventRecord(b->done, c->st_img));
+    CKC(cudaGetLastError());
     return XRVIO_OK;
 }
 
@@ -778,6 +865,7 @@ static int lane_get_kernel_times(Lane *c, double *ms, long long *launches, int c
     if (!c || !ms || !launches) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
     cudaStreamSynchronize(c->st);
     cudaStreamSynchronize(c->st_marg);
+    cudaStreamSynchronize(c->st_img);
     prof_collect(c);
     for (int k = 0; k < capacity && k < 16; ++k) { ms[k] = c->prof_ms[k]; launches[k] = c->prof_launches[k]; }
     return FAM_COUNT;
@@ -936,9 +1024,21 @@ int xrvio_push_imu(xrvio_ctx *ctx, const int *session, const xrvio_imu *samples,
 
 int xrvio_push_images(xrvio_ctx *ctx, const int *session, const uint8_t *const *data, const int *stride, const double *t, int n, int on_device) {
     if (!ctx || !session || !data || !t || n < 0) { xrvio_set_error("xrvio_push_images: bad argument"); return XRVIO_ERR_ARG; }
+    // the images of one call are grouped per lane: each group is one batch of that lane's image kernels
+    const int L = (int)ctx->lanes.size();
+    std::vector<std::vector<int>> loc(L);
+    std::vector<std::vector<const uint8_t *>> dat(L);
+    std::vector<std::vector<int>> str(L);
+    std::vector<std::vector<double>> tt(L);
     for (int k = 0; k < n; ++k) {
-        LANE_OF(session[k], l, i);
-        int rc = lane_push_images(l, &i, data + k, stride ? stride + k : nullptr, t + k, 1, on_device);
+        if (session[k] < 0 || session[k] >= ctx->S) { xrvio_set_error("bad session index"); return XRVIO_ERR_ARG; }
+        const int l = ctx->where[session[k]].first;
+        loc[l].push_back(ctx->where[session[k]].second); dat[l].push_back(data[k]); tt[l].push_back(t[k]);
+        if (stride) str[l].push_back(stride[k]);
+    }
+    for (int l = 0; l < L; ++l) {
+        if (loc[l].empty()) continue;
+        int rc = lane_push_images(ctx->lanes[l], loc[l].data(), dat[l].data(), stride ? str[l].data() : nullptr, tt[l].data(), (int)loc[l].size(), on_device);
         if (rc) return rc;
     }
     return XRVIO_OK;

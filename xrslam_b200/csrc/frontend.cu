@@ -513,7 +513,7 @@ void gftt_harris(const uint8_t *img, const int *idx, size_t img_stride, int n, i
     int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
     size_t smem = (((size_t)((gw * gh + 1) & ~1) * sizeof(short) + (size_t)gw * gh * 8 * sizeof(short2) + 7) & ~(size_t)7) + (size_t)kSortSmem * sizeof(unsigned long long);
     if (max_corners > kMaxCorners) max_corners = kMaxCorners;
-    static std::atomic<unsigned long long> attr_done{0};
+    static xv::SmemOptIn attr_done;
     xv::ensure_dynamic_smem(corner_select_kernel, (int)smem, attr_done);
     corner_select_kernel<<<n, 1024, smem, st>>>(cand, cand_count, maxval, quality, w, h, max_corners, min_distance, corners, count);
 }
@@ -529,11 +529,14 @@ constexpr int RAWP = WIN + 3;     // 24: + 1 px ring for the Scharr stencil
 constexpr int KLT_WARPS = 4;
 
 constexpr int JREG = 32;          // side of the staged search region (window 22 + 10 px of slack)
-constexpr int RAWPITCH = 32;      // row pitch of the staged template neighbourhood = inner box of its TMA tile (16-byte multiple)
+// Row pitch of both staged tiles = inner box of their TMA loads.  A tile load must START on a 16-byte boundary of global
+// memory (measured: tools/tma_probe.cu, a u8 box starting at x = 17 raises an illegal-instruction fault on sm_100, x = 16 is
+// fine), so the box starts at x & ~15 and is 48 wide: the wanted 24 / 32 columns begin at offset x & 15 <= 15 inside it.
+constexpr int RAWPITCH = 48;
 struct alignas(128) KltSmem {
     union {                           // both are destinations of TMA tile loads: 128-byte aligned, pitch = box width
         uint8_t raw[RAWP][RAWPITCH];  // level image around the template window (reflect-101 border)
-        uint8_t J[JREG][JREG];        // search region in the other image (staged once per level, re-staged on exit)
+        uint8_t J[JREG][RAWPITCH];    // search region in the other image (staged once per level, re-staged on exit)
     };
     short dx[WINP][WINP];             // Scharr derivatives at the 22x22 positions (0 outside the image)
     short dy[WINP][WINP];
@@ -544,15 +547,15 @@ struct alignas(128) KltSmem {
 
 // ---- TMA staging (north_star: "image patches ... staged through TMA into shared memory") --------------------------------
 // One tensor map per pyramid level over the whole pyramid buffer: dims (x = level width, y = level height, z = pyramid
-// index), u8, box 32 x 24 (template neighbourhood) or 32 x 32 (search region).  A tile that lies completely inside the level
+// index), u8, box 48 x 24 (template neighbourhood) or 48 x 32 (search region), see RAWPITCH.  A tile that lies completely inside the level
 // is fetched by ONE cp.async.bulk.tensor issued by lane 0 and awaited on the warp's mbarrier, instead of 18-32 predicated
 // byte loads per lane with reflect-101 index arithmetic; tiles that touch the border keep the scalar path (TMA can only
 // zero-fill outside the tensor, OpenCV reflects).  Levels whose width / offset / pyramid stride is not a multiple of 16
 // bytes (e.g. 94 x 60 of a 752 x 480 image) have no map and always take the scalar path.
 #ifndef CUEMU
 struct KltMaps {
-    CUtensorMap tmpl[kPyrLevels];     // box 32 x 24
-    CUtensorMap srch[kPyrLevels];     // box 32 x 32
+    CUtensorMap tmpl[kPyrLevels];     // box 48 x 24
+    CUtensorMap srch[kPyrLevels];     // box 48 x 32
     unsigned ok;                      // bit l: level l has maps
 };
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -624,9 +627,11 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
         // stage the raw template neighbourhood (24 x 24): loads first, stores after, so the loads overlap
         __syncwarp();
         bool tile_done = false;
+        int ro = 0;                                    // column of the tile's first wanted pixel inside the staged rows
 #ifndef CUEMU
         if (tma.mapsI != nullptr && ((tma.mapsI->ok >> level) & 1u) && ipx >= 1 && ipx + RAWP - 2 < cols && ipy >= 1 && ipy + RAWP - 2 < rows) {
-            if (lane == 0) tma_tile_3d(&sm.raw[0][0], &tma.mapsI->tmpl[level], &sm.bar, ipx - 1, ipy - 1, tma.zI, RAWP * RAWPITCH);
+            ro = (ipx - 1) & 15;
+            if (lane == 0) tma_tile_3d(&sm.raw[0][0], &tma.mapsI->tmpl[level], &sm.bar, (ipx - 1) - ro, ipy - 1, tma.zI, RAWP * RAWPITCH);
             mbar_wait(&sm.bar, tma.phase);
             tma.phase ^= 1u;
             tile_done = true;
@@ -654,7 +659,7 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
             int X = ipx + lx, Y = ipy + ly;
             short ddx = 0, ddy = 0;
             if (X >= 0 && X < cols && Y >= 0 && Y < rows) {
-                int cx = lx + 1, cy = ly + 1;
+                int cx = ro + lx + 1, cy = ly + 1;
                 int t0m = ((int)sm.raw[cy - 1][cx - 1] + (int)sm.raw[cy + 1][cx - 1]) * 3 + (int)sm.raw[cy][cx - 1] * 10;
                 int t0p = ((int)sm.raw[cy - 1][cx + 1] + (int)sm.raw[cy + 1][cx + 1]) * 3 + (int)sm.raw[cy][cx + 1] * 10;
                 int t1m = (int)sm.raw[cy + 1][cx - 1] - (int)sm.raw[cy - 1][cx - 1];
@@ -672,7 +677,7 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
             if (pxy[k] < 0) continue;
             const int y = pxy[k] >> 8, x = pxy[k] & 255;
             const int i = lane + 32 * k;
-            const int cy = y + 1, cx = x + 1;
+            const int cy = y + 1, cx = ro + x + 1;
             int ival = ((int)sm.raw[cy][cx] * iw00 + (int)sm.raw[cy][cx + 1] * iw01 + (int)sm.raw[cy + 1][cx] * iw10 +
                         (int)sm.raw[cy + 1][cx + 1] * iw11 + (1 << 8)) >> 9;
             int ixval = ((int)sm.dx[y][x] * iw00 + (int)sm.dx[y][x + 1] * iw01 + (int)sm.dx[y + 1][x] * iw10 +
@@ -701,7 +706,7 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
         }
         nx -= 10.f; ny -= 10.f;
         float pdx = 0.f, pdy = 0.f;
-        int rox = 0, roy = 0;
+        int rox = 0, roy = 0, jo = 0;                  // jo: column of the region's first pixel inside the staged rows
         bool staged = false;
         for (int j = 0; j < 30; ++j) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
@@ -718,9 +723,11 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
                 rox = inx - (JREG - WINP) / 2; roy = iny - (JREG - WINP) / 2;
                 __syncwarp();
                 bool region_done = false;
+                jo = 0;
 #ifndef CUEMU
                 if (tma.mapsJ != nullptr && ((tma.mapsJ->ok >> level) & 1u) && rox >= 0 && rox + JREG <= cols && roy >= 0 && roy + JREG <= rows) {
-                    if (lane == 0) tma_tile_3d(&sm.J[0][0], &tma.mapsJ->srch[level], &sm.bar, rox, roy, tma.zJ, JREG * JREG);
+                    jo = rox & 15;
+                    if (lane == 0) tma_tile_3d(&sm.J[0][0], &tma.mapsJ->srch[level], &sm.bar, rox - jo, roy, tma.zJ, JREG * RAWPITCH);
                     mbar_wait(&sm.bar, tma.phase);
                     tma.phase ^= 1u;
                     region_done = true;
@@ -738,13 +745,13 @@ __device__ bool lk_track_point(const uint8_t *__restrict__ pyrI, const uint8_t *
                 __syncwarp();
                 staged = true;
             }
-            const uint8_t *Jb = &sm.J[iny - roy][inx - rox];
+            const uint8_t *Jb = &sm.J[iny - roy][jo + inx - rox];
             float b1 = 0.f, b2 = 0.f;
 #pragma unroll
             for (int k = 0; k < NPX; ++k) {
                 if (pxy[k] < 0) continue;
-                const uint8_t *q = Jb + (pxy[k] >> 8) * JREG + (pxy[k] & 255);
-                const int diff = (((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[JREG] * iw10 + (int)q[JREG + 1] * iw11 + (1 << 8)) >> 9) - (int)tI[k];
+                const uint8_t *q = Jb + (pxy[k] >> 8) * RAWPITCH + (pxy[k] & 255);
+                const int diff = (((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[RAWPITCH] * iw10 + (int)q[RAWPITCH + 1] * iw11 + (1 << 8)) >> 9) - (int)tI[k];
                 b1 += (float)(diff * (int)tIx[k]);
                 b2 += (float)(diff * (int)tIy[k]);
             }
@@ -839,11 +846,11 @@ KltMapSet klt_make_maps(const uint8_t *pyr, int n_pyramids, const PyrLayout &L) 
     }();
     if (encode != nullptr && n_pyramids > 0 && L.total % 16 == 0 && ((uintptr_t)pyr % 16) == 0) {
         for (int l = 0; l < kPyrLevels; ++l) {
-            if (L.w[l] % 16 != 0 || L.off[l] % 16 != 0 || L.w[l] < JREG || L.h[l] < JREG) continue;
+            if (L.w[l] % 16 != 0 || L.off[l] % 16 != 0 || L.w[l] < RAWPITCH || L.h[l] < JREG) continue;
             const cuuint64_t dims[3] = {(cuuint64_t)L.w[l], (cuuint64_t)L.h[l], (cuuint64_t)n_pyramids};
             const cuuint64_t strides[2] = {(cuuint64_t)L.w[l], (cuuint64_t)L.total};       // bytes, dims 1 and 2
             const cuuint32_t estr[3] = {1, 1, 1};
-            const cuuint32_t box_t[3] = {RAWPITCH, RAWP, 1}, box_s[3] = {JREG, JREG, 1};
+            const cuuint32_t box_t[3] = {RAWPITCH, RAWP, 1}, box_s[3] = {RAWPITCH, JREG, 1};
             void *base = (void *)(pyr + L.off[l]);
             if (encode(&m.tmpl[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box_t, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) continue;
@@ -887,20 +894,28 @@ __global__ void __launch_bounds__(32) poisson_kernel(const double *__restrict__ 
                                                       double radius) {
     extern __shared__ short grid[];      // PG_W * PG_H, -1 = empty
     __shared__ double P[kMaxPts * 2];    // the list, staged once (the scan is strictly sequential)
+    __shared__ short cell[kMaxPts * 2];  // grid cell of every point, computed up front by all lanes (two FP64 divisions per point)
+    __shared__ uint8_t flag[kMaxPts];    // in: veto, out: keep -- the sequential loop touches shared memory only
     const int list = blockIdx.x, lane = threadIdx.x;
     for (int i = lane; i < PG_W * PG_H; i += 32) grid[i] = -1;
-    {
-        const double *Pg = pts + (size_t)list * kMaxPts * 2;
-        const int nt = n_total[list];
-        for (int i = lane; i < 2 * nt; i += 32) P[i] = Pg[i];
-    }
-    __syncwarp();
     const double r2 = radius * radius;
     const double gs = radius / sqrt(2.0);
     const int npre = n_preset[list], ntot = n_total[list];
+    {
+        const double *Pg = pts + (size_t)list * kMaxPts * 2;
+        for (int i = lane; i < 2 * ntot; i += 32) P[i] = Pg[i];
+        for (int i = lane; i < ntot; i += 32) {
+            const double x = Pg[2 * i], y = Pg[2 * i + 1];
+            const int ix = (int)floor(x / gs), iy = (int)floor(y / gs);
+            cell[2 * i] = (short)min(max(ix, -4), PG_W + 4);          // clamped values stay outside the grid, like the originals
+            cell[2 * i + 1] = (short)min(max(iy, -4), PG_H + 4);
+            flag[i] = veto != nullptr ? veto[(size_t)list * kMaxPts + i] : 0;
+        }
+    }
+    __syncwarp();
     for (int i = 0; i < ntot; ++i) {
         const double x = P[2 * i], y = P[2 * i + 1];
-        const int ix = (int)floor(x / gs), iy = (int)floor(y / gs);
+        const int ix = cell[2 * i], iy = cell[2 * i + 1];
         bool ok = true;
         if (i >= npre) {
             bool hit = false;
@@ -918,17 +933,21 @@ __global__ void __launch_bounds__(32) poisson_kernel(const double *__restrict__ 
                 }
             }
             ok = !__any_sync(0xffffffffu, hit);
-            if (veto != nullptr && veto[(size_t)list * kMaxPts + i]) ok = false;
-            if (lane == 0) keep[(size_t)list * kMaxPts + i] = ok ? 1 : 0;
-        } else if (lane == 0) keep[(size_t)list * kMaxPts + i] = 1;
-        if (ok && lane == 0 && ix >= 0 && ix < PG_W && iy >= 0 && iy < PG_H) grid[iy * PG_W + ix] = (short)i;
+            if (flag[i]) ok = false;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            flag[i] = ok ? 1 : 0;
+            if (ok && ix >= 0 && ix < PG_W && iy >= 0 && iy < PG_H) grid[iy * PG_W + ix] = (short)i;
+        }
         __syncwarp();
     }
+    for (int i = lane; i < ntot; i += 32) keep[(size_t)list * kMaxPts + i] = flag[i];
 }
 
 void poisson_filter(const double *pts, const int *n_preset, const int *n_total, const uint8_t *veto, uint8_t *keep,
                     int n, double radius, cudaStream_t st) {
-    static std::atomic<unsigned long long> attr_done{0};
+    static xv::SmemOptIn attr_done;
     size_t smem = (size_t)PG_W * PG_H * sizeof(short);
     xv::ensure_dynamic_smem(poisson_kernel, (int)smem, attr_done);
     poisson_kernel<<<n, 32, smem, st>>>(pts, n_preset, n_total, veto, keep, radius);

@@ -49,6 +49,8 @@ struct Frame {
     bool keyframe = false, no_translation = false, fix_pose = false, fix_motion = false;
     Map *map = nullptr;
     int pyr_slot = -1;                      // device pyramid buffer of this frame's image (front-end map only)
+    void *img_batch = nullptr;              // the push batch whose image kernels produced that pyramid and the corners (capi_session.cu)
+    int img_index = -1;                     // position of this frame in that batch
     int tmp = -1;                           // scratch index used while building problems
 
     size_t keypoint_num() const { return bearings.size(); }

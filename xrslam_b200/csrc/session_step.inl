@@ -43,15 +43,13 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
     StepBuffers &B = sb(c);
     CKC(B.idx_raw.reserve(n)); CKC(B.idx_next.reserve(n)); CKC(B.idx_prev.reserve(n));
     PhaseClock pt(c, 0);
-    // ---- phase A: CLAHE + pyramid + GFTT on the new image; preintegration (no Jacobian / covariance) ----
+    // ---- phase A: preintegration (no Jacobian / covariance).  CLAHE + pyramid + GFTT of the new image were launched on the
+    //      image stream when the image was pushed (lane_push_images); this stream only has to be ordered behind them ----
     { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
         s.stg.clear_jobs();
         s.cur = std::move(s.released.front());
         s.released.pop_front();
         Frame *f = s.cur.get();
-        const int raw_slot = f->pyr_slot;
-        f->pyr_slot = s.pyr_next; s.pyr_next = (s.pyr_next + 1) % kPyrSlots;
-        B.idx_raw.h[i] = s.idx * kImgQueue + raw_slot;
         B.idx_next.h[i] = s.idx * kPyrSlots + f->pyr_slot;
         s.fe_has_last = s.ft_map.frame_num() > 0;
         s.last = s.fe_has_last ? s.ft_map.frames.back().get() : nullptr;
@@ -87,27 +85,11 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         return 0; }); if (rc) return rc; }
     { int rc = merge_preint_jobs(c, act); if (rc) return rc; }
     pt.next(1);
-    CKC(cudaMemcpyAsync(B.idx_raw.d, B.idx_raw.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
     CKC(cudaMemcpyAsync(B.idx_next.d, B.idx_next.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
-    const uint8_t *clahe_src = c->d_raw;
-    const int *clahe_idx = B.idx_raw.d;
-    if (c->d_und) {     // the reader's cv::undistort, on the device (row N2); counted with the CLAHE family
-        ProfScope ps(c, FAM_CLAHE, 1);
-        xvfe::undistort(c->d_raw, B.idx_raw.d, P, c->d_und, nullptr, P, n, w, h, c->d_und_map, c->st);
-        c->stats.kernels_launched += 1;
-        clahe_src = c->d_und; clahe_idx = nullptr;
+    for (Session *sp : act) {           // the pyramids KLT reads are complete once the batches' events have fired
+        ImgBatch *b = static_cast<ImgBatch *>(sp->cur->img_batch);
+        if (b && !b->waited) { CKC(cudaStreamWaitEvent(c->st, b->done, 0)); b->waited = true; }
     }
-    { ProfScope ps(c, FAM_CLAHE, 2);
-      xvfe::clahe(clahe_src, clahe_idx, P, c->d_pyr, B.idx_next.d, c->L.total, c->d_lut, n, w, h, c->prm.clahe_clip_limit,
-                  c->prm.clahe_width, c->prm.clahe_height, c->st); }
-    { ProfScope ps(c, FAM_PYRAMID, 3); xvfe::pyramid(c->d_pyr, B.idx_next.d, n, c->L, c->st); }
-    { ProfScope ps(c, FAM_GFTT, 2);
-      xvfe::gftt_harris(c->d_pyr, B.idx_next.d, c->L.total, n, w, h, c->prm.max_keypoint_detection, 1.0e-3f, 20.0f, c->corners.d,
-                        c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->st); }
-    c->stats.kernels_launched += 2 + 3 + 2;
-    CKC(cudaMemcpyAsync(c->corners.h, c->corners.d, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
-    CKC(cudaMemcpyAsync(c->corner_count.h, c->corner_count.d, n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    c->stats.d2h_bytes += (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float) + n * sizeof(int);
     { int rc = run_preint_jobs(c); if (rc) return rc; }     // also synchronises the stream
     if (c->pre_jobs.n == 0) CKC(cudaStreamSynchronize(c->st));
     CKC(cudaGetLastError());
@@ -261,16 +243,21 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         return 0; }); if (rc) return rc; }
     pt.next(7);
     // ---- phase D: Frame::detect_keypoints (frame.cpp:55-72, opencv_image.cpp:46-72) ----
+    for (Session *sp : act) {           // corner lists of the push batches: read back on the image stream long ago
+        ImgBatch *b = static_cast<ImgBatch *>(sp->cur->img_batch);
+        if (b && !b->host_ready) { CKC(cudaEventSynchronize(b->done)); b->host_ready = true; }
+    }
     { int rc = for_sessions(c, act, [&](int i, Session &s) -> int {
         Frame *f = s.cur.get();
         const int npre = (int)f->keypoint_num();
-        const int nc = c->corner_count.h[i];
+        const ImgBatch *ib = static_cast<const ImgBatch *>(f->img_batch);
+        const int nc = ib ? ib->count_h[f->img_index] : 0;
         if (npre + nc > xvfe::kMaxPts) { s.err = "too many keypoints for the Poisson filter"; return XRVIO_ERR_LIMIT; }
         c->poi_npre.h[i] = npre; c->poi_ntot.h[i] = npre + nc;
         for (int k = 0; k < npre; ++k) apply_k(f->bearings[k], c->K, c->poi_pts.h + ((size_t)i * xvfe::kMaxPts + k) * 2);
         // GFTT corners arrive strongest first; std::sort by response (opencv_image.cpp:47-50) keeps that order
         for (int k = 0; k < nc; ++k) {
-            const float *cr = c->corners.h + ((size_t)i * xvfe::kMaxCorners + k) * 3;
+            const float *cr = ib->corners_h + ((size_t)f->img_index * xvfe::kMaxCorners + k) * 3;
             double *pp = c->poi_pts.h + ((size_t)i * xvfe::kMaxPts + npre + k) * 2;
             pp[0] = (double)cr[0]; pp[1] = (double)cr[1];
         }
@@ -299,6 +286,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
             s.ft_map.detach_frame(0);
         }
     return 0; }); if (rc) return rc; }
+    for (Session *sp : act) img_batch_release(c, sp->ft_map.frames.back().get());      // serial: the pool is not thread-safe
     c->stats.frames_processed += n;
     pt.stop();
     return XRVIO_OK;

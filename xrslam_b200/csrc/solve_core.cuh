@@ -238,22 +238,19 @@ template <class SM> __device__ __forceinline__ void jtj_uniform_warp(SM &s, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cost-only evaluation (29 of the 31 evaluations of a window BA): the three factor families do not depend
-// on each other, so they run SIDE BY SIDE on different warps instead of one after the other with CTA barriers in between:
-//   * the last warp evaluates the preintegration factors (one lane per factor: a serial chain of ~10 k cycles) and whitens them,
-//   * the warp before it evaluates the marginalisation prior (marg_dx per prior frame, then one lane per row of S dx + infovec),
-//   * the other warps share the reprojection (and rotation-prior) residuals.
-// One block reduction at the end.  Same arithmetic per residual as evaluate(..., want_jac = false); only the order in which
-// the partial costs are summed differs.
+// Cost-only evaluation (29 of the 31 evaluations of a window BA).  The preintegration factors are a serial
+// chain of ~10 k cycles per factor on ONE lane each; they get the last warp to themselves and run UNDER the reprojection
+// residuals of the other warps instead of after them.  The prior's S dx + infovec is memory-latency bound (S^T comes from L2),
+// it needs every thread to have enough loads in flight: it follows the barrier, 4 lanes per row.  (Giving the prior one warp
+// of its own measured 2.2x slower per evaluation on a B200 -- five serial rounds of 135-long L2-latency-bound dot products.)
+// Same arithmetic per residual as evaluate(..., want_jac = false); only the order in which the partial costs are summed differs.
 // ------------------------------------------------------------------------------------------------
 template <class SM> static __device__ double evaluate_cost(const Prob &P, SM &s, const double *S, const double *inv, const RigParams &rg, bool robust) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int M = P.M;
     XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(S); XV_ASSUME_GLOBAL(inv);
     const bool has_pre = P.d.n_pre > 0, has_marg = P.d.marg_k > 0;
     const int w_pre = has_pre ? NW - 1 : -1;
-    const int w_marg = has_marg ? NW - 1 - (has_pre ? 1 : 0) : -1;
-    const int n_rw = NW - (has_pre ? 1 : 0) - (has_marg ? 1 : 0);          // warps 0 .. n_rw - 1 take the reprojection residuals
+    const int n_rw = NW - (has_pre ? 1 : 0);          // warps 0 .. n_rw - 1 take the reprojection residuals
     double cost = 0.0;
     if (warp == w_pre) {
         for (int f = lane; f < P.d.n_pre; f += 32) {
@@ -275,30 +272,12 @@ template <class SM> static __device__ double evaluate_cost(const Prob &P, SM &s,
             for (int k = 0; k < 15; ++k) a += Sic[r * 15 + k] * sc[k];
             cost += 0.5 * a * a;
         }
-    } else if (warp == w_marg) {
-        const int K = P.d.marg_k, n = P.marg_n, rk = P.marg_rank;
-        for (int k = lane; k < K; k += 32) {
-            const int f = P.marg_frames[P.d.marg_frames_off + k];
-            marg_dx(S + f * 16, P.marg_lin + k * 16, P.m_dx + 15 * k, nullptr);
-        }
-        __syncwarp();
-        // r = S dx + infovec over the non-zero rows: one lane per row on the transposed copy (coalesced), four accumulators
-        for (int r = lane; r < rk; r += 32) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int cidx = 0;
-            for (; cidx + 3 < n; cidx += 4) {
-                a0 += P.marg_St[(size_t)cidx * rk + r] * P.m_dx[cidx];
-                a1 += P.marg_St[(size_t)(cidx + 1) * rk + r] * P.m_dx[cidx + 1];
-                a2 += P.marg_St[(size_t)(cidx + 2) * rk + r] * P.m_dx[cidx + 2];
-                a3 += P.marg_St[(size_t)(cidx + 3) * rk + r] * P.m_dx[cidx + 3];
-            }
-            for (; cidx < n; ++cidx) a0 += P.marg_St[(size_t)cidx * rk + r] * P.m_dx[cidx];
-            const double a = ((a0 + a1) + (a2 + a3)) + P.marg_info[r];
-            cost += 0.5 * a * a;
-        }
-        // rows beyond the rank are exactly zero in S; their residual is infovec[r] (zero for our priors)
-        for (int r = rk + lane; r < n; r += 32) { const double a = P.marg_info[r]; cost += 0.5 * a * a; }
     } else {
+        if (has_marg && warp == 0)                                  // error of the prior frames against their linearisation points
+            for (int k = lane; k < P.d.marg_k; k += 32) {
+                const int f = P.marg_frames[P.d.marg_frames_off + k];
+                marg_dx(S + f * 16, P.marg_lin + k * 16, P.m_dx + 15 * k, nullptr);
+            }
         for (int base = warp * 32; base < P.d.n_rpe; base += n_rw * 32) {
             const int o = base + lane;
             if (o < P.d.n_rpe) {
@@ -321,7 +300,30 @@ template <class SM> static __device__ double evaluate_cost(const Prob &P, SM &s,
             cost += 0.5 * log(1.0 + (r[0] * r[0] + r[1] * r[1]));
         }
     }
-    (void)M;
+    if (has_marg) {
+        __syncthreads();                                            // m_dx complete
+        const int n = P.marg_n, rk = P.marg_rank;
+        // r = S dx + infovec over the non-zero rows on the transposed copy (coalesced): 4 lanes per row (column slices
+        // c = q, q + 4, ...), two independent accumulators per lane
+        for (int r0 = 0; r0 < rk; r0 += ST / 4) {
+            const int r = r0 + (tid >> 2), q = tid & 3;
+            double a0 = 0.0, a1 = 0.0;
+            if (r < rk) {
+                int cidx = q;
+                for (; cidx + 4 < n; cidx += 8) {
+                    a0 += P.marg_St[(size_t)cidx * rk + r] * P.m_dx[cidx];
+                    a1 += P.marg_St[(size_t)(cidx + 4) * rk + r] * P.m_dx[cidx + 4];
+                }
+                for (; cidx < n; cidx += 4) a0 += P.marg_St[(size_t)cidx * rk + r] * P.m_dx[cidx];
+            }
+            double a = a0 + a1;
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (r < rk && q == 0) { a += P.marg_info[r]; cost += 0.5 * a * a; }
+        }
+        // rows beyond the rank are exactly zero in S; their residual is infovec[r] (zero for our priors)
+        for (int r = rk + tid; r < n; r += ST) { const double a = P.marg_info[r]; cost += 0.5 * a * a; }
+    }
     return block_sum(cost, s);
 }
 
