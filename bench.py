@@ -214,6 +214,12 @@ def run_cuda_arm(args, rank, world, local_rank):
     dev_ptrs = [[frames_dev.data_ptr() + (s * n_frames + k) * P for s in sess_ids] for k in range(n_frames)]
     host_ptrs = [[frames_host.data_ptr() + (s * n_frames + k) * P for s in sess_ids] for k in range(n_frames)]
 
+    def lane_busy(ctx):
+        import ctypes as _ct
+        a = (_ct.c_double * 64)()
+        n = capi.lib.xrvio_debug_lane_busy(ctx._h, a, 64)
+        return [a[i] for i in range(max(n, 0))]
+
     def one_run(ptrs, on_device, read_back, profile):
         ctx = capi.Context(drive.params_for(streams[0]), N_STREAMS, device=local_rank)
         for s, st in enumerate(streams):
@@ -232,9 +238,13 @@ def run_cuda_arm(args, rank, world, local_rank):
             step(k)
         assert all(ctx.get_state(s) == 1 for s in sess_ids), 'sessions did not reach TRACKING'
         st0 = ctx.stats()
+        busy0 = lane_busy(ctx)
         if profile:
             ctx.set_profiling(True)
             kt0 = ctx.kernel_times()
+        # timed region in the library's asynchronous mode (include/xrvio.h): the calls queue work per lane of sessions and the
+        # lanes run through it at their own pace, at most two steps behind this loop; xrvio_sync at the end waits for all of it
+        ctx.set_async(not args.sync_steps)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -248,11 +258,13 @@ def run_cuda_arm(args, rank, world, local_rank):
         # through the whole path and K image pushes inside the timed region
         for k in range(PRIME_FRAMES + Wm, PRIME_FRAMES + Wm + K):
             step(k)
+        ctx.sync()
         torch.cuda.synchronize()
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
+        ctx.set_async(False)
         clocks = sampler.stop() if sampler else None
         if world > 1:
             dist.barrier()
@@ -261,7 +273,8 @@ def run_cuda_arm(args, rank, world, local_rank):
         if profile:
             kt1 = ctx.kernel_times()
             kt = {k: (kt1[k][0] - kt0[k][0], kt1[k][1] - kt0[k][1]) for k in kt1}
-        res = dict(ms=max(ms, wall * 1e3), stats0=st0, stats1=st1, kt=kt, clocks=clocks)
+        busy1 = lane_busy(ctx)
+        res = dict(ms=max(ms, wall * 1e3), stats0=st0, stats1=st1, kt=kt, clocks=clocks, lane_busy_ms=[round(b - a, 1) for a, b in zip(busy0, busy1)])
         ctx.close()
         return res
 
@@ -311,9 +324,12 @@ def run_cuda_arm(args, rank, world, local_rank):
         'config': {'workload': '64x640x480_streams', 'streams_per_gpu': N_STREAMS, 'image': [W_IMG, H_IMG], 'cam_hz': 20, 'imu_hz': 200,
                    'window_keyframes': 10, 'max_detections': 200, 'prime_frames': PRIME_FRAMES, 'l2': 'inputs_larger_than_L2',
                    'parallelism': 'sessions sharded per GPU, no data-path collective'},
+        'stepping': 'synchronous' if args.sync_steps else 'asynchronous lanes (<= 2 steps ahead), poses polled every step',
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int((e1s['h2d_bytes'] - e0s['h2d_bytes']) / K),
                 'd2h_bytes_per_step': int((e1s['d2h_bytes'] - e0s['d2h_bytes']) / K) + N_STREAMS * 72, 'ms_per_step': ms_e2e / K},
         'gpu_launches': launches,
+        'lane_busy_ms': r_dev['lane_busy_ms'],         # host wall time each lane spent inside its K steps (diagnostic)
+        'host_cpus': len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count(),
         'clocks': r_dev['clocks'],
         'roofline': roofline,
         'work': {'window_solves': window_solves, 'localize_solves': int(s1['localize_solves'] - s0['localize_solves']),
@@ -466,6 +482,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sync-steps', action='store_true', help='every xrvio_step waits for all lanes (A/B against the asynchronous mode)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

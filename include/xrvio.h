@@ -240,6 +240,16 @@ int xrvio_push_bootstrap_state(xrvio_ctx *ctx, int session, double t, const doub
 int xrvio_push_images(xrvio_ctx *ctx, const int *session, const uint8_t *const *data, const int *stride, const double *t,
                       int n, int on_device);
 int xrvio_step(xrvio_ctx *ctx);
+/* Asynchronous mode (off by default; needs a context of >= 8 sessions, i.e. more than one lane).  xrvio_push_imu,
+ * xrvio_push_images and xrvio_step only QUEUE their work per lane and return; every lane of sessions works through its queue at
+ * its own pace, at most two steps behind the caller (xrvio_step blocks beyond that).  Image buffers handed to
+ * xrvio_push_images must stay valid until the lane has consumed them (xrvio_sync, or two further steps).  xrvio_get_pose does
+ * not wait and returns the newest pose available (pose->t says for which frame) -- the behaviour of the reference's threaded
+ * build, where Detail::get_latest_pose reads whatever the tracker has reached; every other getter waits for the session's lane.
+ * Errors of queued work are reported by xrvio_sync or the next waiting call.  Results per session are identical to synchronous
+ * mode: sessions never interact, only the interleaving of lanes changes. */
+int xrvio_set_async(xrvio_ctx *ctx, int enable);
+int xrvio_sync(xrvio_ctx *ctx);
 int xrvio_get_pose(xrvio_ctx *ctx, int session, xrvio_pose *pose);          /* output pose of the latest pushed image */
 int xrvio_get_latest_state(xrvio_ctx *ctx, int session, double *t, double state16[16]);   /* last optimised frame */
 int xrvio_get_state(xrvio_ctx *ctx, int session);                           /* XRVIO_STATE_* or < 0 */
@@ -258,6 +268,8 @@ int xrvio_set_profiling(xrvio_ctx *ctx, int enable);
 int xrvio_get_kernel_times(xrvio_ctx *ctx, double *ms, long long *launches, int capacity);
 /* Host wall time accumulated per internal step phase (diagnostics; up to 32 slots). */
 int xrvio_get_phase_times(xrvio_ctx *ctx, double *ms, int capacity);
+/* Diagnostics: wall time each lane of sessions has spent inside its steps so far (ms); returns the number of lanes. */
+int xrvio_debug_lane_busy(xrvio_ctx *ctx, double *ms_per_lane, int capacity);
 /* Diagnostics: clock64 cycles accumulated per section of the solve kernel over all window problems (32 slots, slot 31 =
  * number of problems); see tools/phase_probe.py for the slot names. */
 int xrvio_debug_kprof(unsigned long long *out32, int reset);

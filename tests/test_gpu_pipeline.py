@@ -247,3 +247,31 @@ def test_window_solves_hit_the_iteration_limit(xrvio):
     assert int(st['window_iterations']) == 30 * refine
     assert int(st['window_at_limit']) == 13
     ctx.close()
+
+
+def test_async_mode_matches_synchronous(xrvio):
+    """xrvio_set_async: the push / step calls only queue work per lane and the lanes run at their own pace; every session must
+    end in the state it reaches in synchronous mode (sessions never interact).  16 sessions = 2 lanes; poses are polled every
+    step without waiting, the way bench.py's e2e leg does."""
+    base = [Stream(3), Stream(4)]
+    n_frames = 50
+    frames2 = [[st.frame(k) for k in range(n_frames)] for st in base]
+    streams = [base[i % 2] for i in range(16)]
+    frames = [frames2[i % 2] for i in range(16)]
+
+    def run(async_mode):
+        ctx = xrvio.Context(drive.params_for(base[0]), 16)
+        if async_mode:
+            ctx.set_async(True)
+        ctx, outs = drive.run_streams_cuda(streams, n_frames, frames=frames, ctx=ctx)
+        ctx.sync()
+        states = [ctx.get_latest_state(s) for s in range(16)]
+        st = ctx.stats()
+        ctx.close()
+        return states, st, outs
+    s_sync, st_sync, _ = run(False)
+    s_async, st_async, outs = run(True)
+    assert st_sync['frames_processed'] == st_async['frames_processed'] and st_sync['window_solves'] == st_async['window_solves']
+    for a, b in zip(s_sync, s_async):
+        assert abs(a[0] - b[0]) < 1e-12 and np.abs(np.asarray(a[1]) - np.asarray(b[1])).max() < 1e-6
+    assert all(len(o) > 0 for o in outs)          # polled poses arrive (possibly one or two frames late)

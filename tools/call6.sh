@@ -7,4 +7,5 @@ timeout 600 python tools/phase_probe.py 64 > gpurun_out/c6_phase_probe.txt 2>&1
 python xrslam_b200/build.py --force > /dev/null 2>&1
 cat gpurun_out/c6_phase_probe.txt
 timeout 400 python bench.py --steps 60 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-1700 > gpurun_out/c6_bench.txt; cat gpurun_out/c6_bench.txt
+timeout 400 python bench.py --steps 60 --warmup 3 --no-cpu-baseline --sync-steps 2>&1 | tail -1 | cut -c1-1700 > gpurun_out/c6_bench_sync.txt; cat gpurun_out/c6_bench_sync.txt
 XRVIO_KLT_TMA=0 timeout 400 python bench.py --steps 60 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-1700 > gpurun_out/c6_bench_notma.txt; cat gpurun_out/c6_bench_notma.txt

@@ -313,6 +313,12 @@ class Context:
         lib.xrvio_get_phase_times(self._h, _p(ms), 32)
         return ms
 
+    def set_async(self, enable=True):
+        lib.check(lib.xrvio_set_async(self._h, 1 if enable else 0))
+
+    def sync(self):
+        lib.check(lib.xrvio_sync(self._h))
+
     def get_features(self, session):
         """(xy [n,2], track ids [n], track lengths [n]) of the newest front-end frame."""
         n = lib.xrvio_get_features(self._h, int(session), None, None, None, 0)

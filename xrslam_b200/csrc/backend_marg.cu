@@ -14,7 +14,7 @@ using namespace xv;
 
 size_t marg_scratch_doubles(int n_frames, int n_lm, int n_rpe) {
     size_t n = (size_t)15 * n_frames;
-    return solve_scratch_doubles(n_frames, n_lm, 2, n_frames, n_rpe) + 2 * n * n + 16 * n + 1024;
+    return solve_scratch_doubles(n_frames, n_lm, 2, n_frames, n_rpe) + 2 * n * n + 16 * n + 1024 + jb_doubles(n_rpe);
 }
 
 __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParams *__restrict__ rig_g) {
@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
         Gm = sc; sc += (size_t)(15 * N) * (15 * N);
         Yg = sc; sc += (size_t)16 * 15 * N;
         prepare_prior(P, m, sc); sc += n * n;
-        prepare_tangents(P, sc);
+        prepare_tangents(P, sc); sc += (size_t)6 * md.n_rpe;
+        prepare_groups(P, s, sc);
         P.du_l = nullptr; P.dw_l = nullptr;
     }
     for (int i = tid; i < N * 16; i += ST) { const double v = P.states_g[i]; s.us[i] = v; s.xs[i] = v; }

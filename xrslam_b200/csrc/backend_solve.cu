@@ -9,7 +9,7 @@ using namespace xv;
 size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k, int n_rpe) {
     size_t M = (size_t)((n_lm_free + 31) / 32) * 32 + 32;
     size_t n = (size_t)15 * marg_k;
-    return 8 * M + (size_t)n_active * 6 * M + HPACK + (size_t)n_pre * kPreScratch + 4 * (n + 32) + 2 * n * n + 64 + (size_t)6 * n_rpe + 2 * M;
+    return 8 * M + (size_t)n_active * 6 * M + HPACK + (size_t)n_pre * kPreScratch + 4 * (n + 32) + 2 * n * n + 64 + (size_t)6 * n_rpe + 2 * M + jb_doubles(n_rpe);
 }
 
 
@@ -64,8 +64,9 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
     for (int c = tid; c < n; c += ST) s.bred[c] = s.g[c];
     __syncthreads();
     kp.mark(29); kp.count(27);
-    if constexpr (SM::kSharedH) schur_landmarks(P, s, s.bred);
-    else schur_landmarks_mma(P, s, s.bred);
+    // landmark Schur complement on the FP64 tensor pipe, W streamed through shared memory by the bulk-copy engine (both instances;
+    // the scalar schur_landmarks of solve_core.cuh remains the marginalisation kernel's, which has no room for the stage)
+    schur_landmarks_mma(P, s, s.bred);
     __syncthreads();
     kp.mark(24);
     // in-place right-looking Cholesky on the packed lower triangle.  The scaled pivot column is mirrored
@@ -103,7 +104,7 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
         __syncthreads();
         for (int p = 0; p < nt; ++p) {
             const int j0 = p * TB;
-            // ---- (1) diagonal tile ----
+            // ---- (1) diagonal tile (and its inverse, for the substitutions) ----
             if (ti == p && tk == p) {
 #pragma unroll
                 for (int c = 0; c < TB; ++c) {
@@ -129,6 +130,28 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
                                     if (li > c && lk > c && lk <= li) a[li][lk] -= a[li][c] * a[lk][c];
                         }
                     }
+                }
+                if (s.flag) {
+                    // N = L_pp^-1 (lower triangular), column by column; rows / columns beyond n act as the identity
+                    double N[TB][TB];
+#pragma unroll
+                    for (int j = 0; j < TB; ++j) {
+#pragma unroll
+                        for (int i = 0; i < TB; ++i) {
+                            if (i < j) { N[i][j] = 0.0; continue; }
+                            const bool in = j0 + i < n && j0 + j < n;
+                            if (i == j) { N[i][j] = in ? idiag[j0 + i] : 1.0; continue; }
+                            double acc = 0.0;
+#pragma unroll
+                            for (int k = 0; k < TB; ++k)
+                                if (k >= j && k < i) acc += a[i][k] * N[k][j];
+                            N[i][j] = in ? -acc * idiag[j0 + i] : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < TB; ++i)
+#pragma unroll
+                        for (int j = 0; j < TB; ++j) s.linv[p * 36 + i * 6 + j] = N[i][j];
                 }
             }
             __syncthreads();
@@ -198,18 +221,25 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
     __syncthreads();
     kp.mark(25);
     if (!s.flag) { kp.count(28); return false; }
-    // forward / backward substitution (L z = b, L^T y = z) in panels of six columns, two barriers per panel: thread 0
-    // solves the 6x6 triangle of the panel and publishes the six values, then every row outside the panel applies them in
-    // column order -- the same operations in the same order as a column-by-column substitution.  (A single-warp version with
-    // the work vector in registers and a shuffle broadcast per column measured 1.75x SLOWER on a B200: 241 against 137 kcycles
-    // per call, profiles/r2_phase_probe_*.txt -- the dependent shuffle + shared-memory column gather per column costs more than
-    // the two CTA barriers per six columns.)
+    // forward / backward substitution (L z = b, L^T y = z) in panels of six columns, two barriers per panel.  Sliding-window
+    // instance: the panel's six values are a 6 x 6 product with the inverse of the diagonal block (six threads, no dependent
+    // chain; the inverses were computed by the factorisation); large instance: thread 0 solves the 6 x 6 triangle.  Then every
+    // row outside the panel applies the six values in column order.  (A single-warp version with the work vector in registers
+    // and a shuffle broadcast per column measured 1.75x SLOWER on a B200: 241 against 137 kcycles per call.)
     // forward: work vector s.y (starts as b_red), result z in s.bred; backward: work vector s.bred, result in s.y.
     for (int c = tid; c < n; c += ST) s.y[c] = s.bred[c];
     __syncthreads();
     for (int j0 = 0; j0 < n; j0 += 6) {
         const int j1 = min(j0 + 6, n);
-        if (tid == 0) {
+        if constexpr (SM::kSharedH) {
+            if (tid < 6 && j0 + tid < n) {               // z_p = L_pp^-1 y_p
+                const double *N = s.linv + (j0 / 6) * 36 + tid * 6;
+                double z = 0.0;
+                for (int k = 0; k <= tid; ++k) z += N[k] * s.y[j0 + k];
+                s.sc[tid] = z;
+                s.bred[j0 + tid] = z;
+            }
+        } else if (tid == 0) {
             for (int j = j0; j < j1; ++j) {
                 const double zj = s.y[j] * idiag[j];
                 s.sc[j - j0] = zj;
@@ -225,9 +255,17 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
         }
         __syncthreads();
     }
-    for (int j1 = n; j1 > 0; j1 -= 6) {
-        const int j0 = max(j1 - 6, 0);
-        if (tid == 0) {
+    for (int j0 = ((n - 1) / 6) * 6; j0 >= 0; j0 -= 6) {       // the panels of the factorisation (multiples of six), last first
+        const int j1 = min(j0 + 6, n);
+        if constexpr (SM::kSharedH) {
+            if (tid < 6 && j0 + tid < j1) {              // y_p = L_pp^-T b_p
+                const double *N = s.linv + (j0 / 6) * 36;
+                double yv = 0.0;
+                for (int k = tid; k < j1 - j0; ++k) yv += N[k * 6 + tid] * s.bred[j0 + k];
+                s.sc[tid] = yv;
+                s.y[j0 + tid] = yv;
+            }
+        } else if (tid == 0) {
             for (int j = j1 - 1; j >= j0; --j) {
                 const double yj = s.bred[j] * idiag[j];
                 s.sc[j - j0] = yj;
@@ -291,7 +329,9 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
         P.m_T = sc; sc += n * n;
         prepare_prior(P, m, sc); sc += n * n;
         prepare_tangents(P, sc); sc += (size_t)6 * P.d.n_rpe;
-        P.du_l = sc; sc += Mp; P.dw_l = sc;
+        P.du_l = sc; sc += Mp; P.dw_l = sc; sc += Mp;
+        P.JB = nullptr; P.grp_start = nullptr; P.n_grp = 0; P.NJ = 0;
+        if constexpr (SM::kSharedH) prepare_groups(P, s, sc);
     }
     SolveOut &out = b.out[blockIdx.x];
     // ---- load user memory ----
@@ -547,7 +587,7 @@ __global__ void __launch_bounds__(ST, 1) solve_large_kernel(SolveBatch b, const 
 }
 
 size_t solve_large_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k, int n_rpe) {
-    return solve_scratch_doubles(n_active, n_lm_free, n_pre, marg_k, n_rpe) - HPACK + 2 * (size_t)SmemL::HP;
+    return solve_scratch_doubles(n_active, n_lm_free, n_pre, marg_k, n_rpe) - HPACK + 2 * (size_t)SmemL::HP - jb_doubles(n_rpe);
 }
 
 void solve_large(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
@@ -560,8 +600,8 @@ void solve_large(const SolveBatch &b, int n_problems, const RigParams *rig, cuda
 void solve(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st) {
     if (n_problems <= 0) return;
     static xv::SmemOptIn attr_done;
-    xv::ensure_dynamic_smem(solve_kernel, (int)sizeof(Smem), attr_done);
-    solve_kernel<<<n_problems, ST, sizeof(Smem), st>>>(b, rig);
+    xv::ensure_dynamic_smem(solve_kernel, (int)kSolveSmem, attr_done);
+    solve_kernel<<<n_problems, ST, kSolveSmem, st>>>(b, rig);
 }
 
 // A0 = S^T S; blockIdx.x = prior, blockIdx.y = slice of the n^2 entries (one entry per thread and pass, rows of S in order)

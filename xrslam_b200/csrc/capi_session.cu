@@ -890,16 +890,24 @@ static int lane_get_stats(Lane *c, xrvio_stats *st) {
 // so one lane's host bookkeeping overlaps the other lanes' kernels and small kernels of different
 // lanes share the GPU.  Sessions never interact, so the lane split does not change any result.
 // =================================================================================================
-// One persistent host thread per lane: xrvio_step hands every lane its step and waits for all of them (creating and
-// joining threads per call would put ~25 us per lane on the critical path of every step).
+// One persistent host thread per lane with a command queue.  Synchronous mode (default): xrvio_step hands every lane its step and
+// waits for all of them; the push calls run on the caller's thread (the workers are idle then).  Asynchronous mode
+// (xrvio_set_async): push_imu / push_images / step are queued per lane and return at once; every lane works through its queue
+// at its own pace, so a lane whose step is short (no window solve this frame) starts its next frame instead of waiting for the
+// lane with the largest bundle adjustment -- throughput follows the MEAN lane time instead of the maximum per step.  A lane is
+// never more than kMaxStepsAhead steps behind the caller (back-pressure in xrvio_step).  Errors of queued commands are sticky
+// per lane and reported by the next call that waits (xrvio_sync, the getters other than xrvio_get_pose).
+constexpr int kMaxStepsAhead = 2;
 struct LaneWorker {
     std::thread th;
     std::mutex mu;
     std::condition_variable cv;
-    std::function<int(Lane *)> job;
-    bool has_job = false, done = true, quit = false;
+    std::deque<std::pair<std::function<int(Lane *)>, bool>> q;      // (command, is_step)
+    int inflight = 0, steps_pending = 0;
+    bool quit = false;
     int rc = 0;
     std::string err;
+    std::mutex pose_mu;                 // output poses are read by xrvio_get_pose without waiting for the queue
 };
 
 struct xrvio_ctx {
@@ -907,6 +915,7 @@ struct xrvio_ctx {
     std::vector<std::unique_ptr<LaneWorker>> workers;
     std::vector<std::pair<int, int>> where;     // session -> (lane, local index)
     int S = 0, device = 0;
+    bool async = false;
     std::vector<std::vector<int>> tmp_idx;
 };
 
@@ -916,15 +925,20 @@ void lane_worker_main(xrvio_ctx *ctx, int l) {
     cudaSetDevice(ctx->device);
     std::unique_lock<std::mutex> lk(w.mu);
     while (true) {
-        w.cv.wait(lk, [&] { return w.has_job || w.quit; });
+        w.cv.wait(lk, [&] { return !w.q.empty() || w.quit; });
         if (w.quit) return;
-        std::function<int(Lane *)> job = w.job;
-        w.has_job = false;
+        std::function<int(Lane *)> job = std::move(w.q.front().first);
+        const bool is_step = w.q.front().second;
+        w.q.pop_front();
+        const bool skip = w.rc != 0;            // after an error the rest of the queue is dropped, the error stays
         lk.unlock();
-        const int rc = job(ctx->lanes[l]);
-        std::string err = rc ? xrvio_last_error() : "";
+        int rc = 0;
+        std::string err;
+        if (!skip) { rc = job(ctx->lanes[l]); if (rc) err = xrvio_last_error(); }
         lk.lock();
-        w.rc = rc; w.err = err; w.done = true;
+        if (rc && !w.rc) { w.rc = rc; w.err = err; }
+        w.inflight--;
+        if (is_step) w.steps_pending--;
         w.cv.notify_all();
     }
 }
@@ -942,26 +956,44 @@ void stop_workers(xrvio_ctx *ctx) {
     }
     ctx->workers.clear();
 }
+void lane_enqueue(xrvio_ctx *ctx, int l, std::function<int(Lane *)> fn, bool is_step) {
+    LaneWorker &w = *ctx->workers[l];
+    std::unique_lock<std::mutex> lk(w.mu);
+    if (is_step) w.cv.wait(lk, [&] { return w.steps_pending < kMaxStepsAhead; });
+    w.q.emplace_back(std::move(fn), is_step);
+    w.inflight++;
+    if (is_step) w.steps_pending++;
+    w.cv.notify_all();
+}
+// waits until lane l has worked through its queue; returns (and clears) its sticky error
+int lane_drain(xrvio_ctx *ctx, int l) {
+    LaneWorker &w = *ctx->workers[l];
+    std::unique_lock<std::mutex> lk(w.mu);
+    w.cv.wait(lk, [&] { return w.inflight == 0; });
+    const int rc = w.rc;
+    if (rc) { xrvio_set_error(w.err); w.rc = 0; w.err.clear(); }
+    return rc;
+}
+int drain_all(xrvio_ctx *ctx) {
+    int rc_all = XRVIO_OK;
+    std::string first;
+    for (int l = 0; l < (int)ctx->workers.size(); ++l) {
+        const int rc = lane_drain(ctx, l);
+        if (rc && rc_all == XRVIO_OK) { rc_all = rc; first = xrvio_last_error(); }
+    }
+    if (rc_all) xrvio_set_error(first);
+    return rc_all;
+}
 template <class F> int each_lane(xrvio_ctx *ctx, F fn) {
     const int L = (int)ctx->lanes.size();
     if (L == 1 || ctx->workers.empty()) {
         for (int l = 0; l < L; ++l) { const int rc = fn(ctx->lanes[l]); if (rc) return rc; }
         return XRVIO_OK;
     }
-    for (int l = 0; l < L; ++l) {
-        LaneWorker &w = *ctx->workers[l];
-        { std::lock_guard<std::mutex> lk(w.mu); w.job = fn; w.has_job = true; w.done = false; }
-        w.cv.notify_all();
-    }
-    int rc_all = XRVIO_OK;
-    for (int l = 0; l < L; ++l) {
-        LaneWorker &w = *ctx->workers[l];
-        std::unique_lock<std::mutex> lk(w.mu);
-        w.cv.wait(lk, [&] { return w.done; });
-        if (w.rc && rc_all == XRVIO_OK) { rc_all = w.rc; xrvio_set_error(w.err); }
-    }
-    return rc_all;
+    for (int l = 0; l < L; ++l) lane_enqueue(ctx, l, fn, false);
+    return drain_all(ctx);
 }
+inline bool is_async(const xrvio_ctx *ctx) { return ctx->async && !ctx->workers.empty(); }
 }  // namespace
 
 extern "C" {
@@ -996,6 +1028,7 @@ int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **
 
 int xrvio_destroy(xrvio_ctx *ctx) {
     if (!ctx) return XRVIO_OK;
+    if (!ctx->workers.empty()) drain_all(ctx);
     stop_workers(ctx);
     for (Lane *l : ctx->lanes) lane_destroy(l);
     delete ctx;
@@ -1007,13 +1040,46 @@ int xrvio_destroy(xrvio_ctx *ctx) {
     Lane *l = ctx->lanes[ctx->where[(sess)].first];                                                  \
     const int i = ctx->where[(sess)].second;
 
+// getters and one-off setters first wait for the lane's queue in asynchronous mode (a no-op in synchronous mode)
+#define LANE_IDLE(sess)                                                                              \
+    if (ctx && (sess) >= 0 && (sess) < ctx->S && is_async(ctx)) { const int rc_ = lane_drain(ctx, ctx->where[(sess)].first); if (rc_) return rc_; }
+
+int xrvio_set_async(xrvio_ctx *ctx, int enable) {
+    if (!ctx) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    if (!ctx->workers.empty()) { const int rc = drain_all(ctx); if (rc) return rc; }
+    ctx->async = enable != 0;
+    return XRVIO_OK;
+}
+int xrvio_sync(xrvio_ctx *ctx) {
+    if (!ctx) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    return ctx->workers.empty() ? XRVIO_OK : drain_all(ctx);
+}
+
 int xrvio_push_bootstrap_state(xrvio_ctx *ctx, int session, double t, const double q[4], const double p[3], const double v[3]) {
+    LANE_IDLE(session);
     LANE_OF(session, l, i);
     return lane_push_bootstrap_state(l, i, t, q, p, v);
 }
 
 int xrvio_push_imu(xrvio_ctx *ctx, const int *session, const xrvio_imu *samples, int n) {
     if (!ctx || !session || !samples || n < 0) { xrvio_set_error("xrvio_push_imu: bad argument"); return XRVIO_ERR_ARG; }
+    if (is_async(ctx)) {        // one queued command per lane, holding a copy of its samples in arrival order
+        const int L = (int)ctx->lanes.size();
+        std::vector<std::shared_ptr<std::pair<std::vector<int>, std::vector<xrvio_imu>>>> per(L);
+        for (int k = 0; k < n; ++k) {
+            if (session[k] < 0 || session[k] >= ctx->S) { xrvio_set_error("bad session index"); return XRVIO_ERR_ARG; }
+            const int l = ctx->where[session[k]].first;
+            if (!per[l]) per[l] = std::make_shared<std::pair<std::vector<int>, std::vector<xrvio_imu>>>();
+            per[l]->first.push_back(ctx->where[session[k]].second);
+            per[l]->second.push_back(samples[k]);
+        }
+        for (int l = 0; l < L; ++l)
+            if (per[l]) {
+                auto d = per[l];
+                lane_enqueue(ctx, l, [d](Lane *lane) { return lane_push_imu(lane, d->first.data(), d->second.data(), (int)d->first.size()); }, false);
+            }
+        return XRVIO_OK;
+    }
     for (int k = 0; k < n; ++k) {
         LANE_OF(session[k], l, i);
         int rc = lane_push_imu(l, &i, samples + k, 1);
@@ -1038,6 +1104,15 @@ int xrvio_push_images(xrvio_ctx *ctx, const int *session, const uint8_t *const *
     }
     for (int l = 0; l < L; ++l) {
         if (loc[l].empty()) continue;
+        if (is_async(ctx)) {    // the image buffers themselves must stay valid until the lane has consumed them (xrvio.h)
+            struct Cmd { std::vector<int> loc; std::vector<const uint8_t *> dat; std::vector<int> str; std::vector<double> tt; int dev; bool has_str; };
+            auto d = std::make_shared<Cmd>(Cmd{loc[l], dat[l], str[l], tt[l], on_device, stride != nullptr});
+            LaneWorker *w = ctx->workers[l].get();
+            lane_enqueue(ctx, l, [d, w](Lane *lane) {
+                std::lock_guard<std::mutex> g(w->pose_mu);          // lane_push_images updates the sessions' output poses
+                return lane_push_images(lane, d->loc.data(), d->dat.data(), d->has_str ? d->str.data() : nullptr, d->tt.data(), (int)d->loc.size(), d->dev); }, false);
+            continue;
+        }
         int rc = lane_push_images(ctx->lanes[l], loc[l].data(), dat[l].data(), stride ? str[l].data() : nullptr, tt[l].data(), (int)loc[l].size(), on_device);
         if (rc) return rc;
     }
@@ -1046,15 +1121,29 @@ int xrvio_push_images(xrvio_ctx *ctx, const int *session, const uint8_t *const *
 
 int xrvio_step(xrvio_ctx *ctx) {
     if (!ctx) { xrvio_set_error("xrvio_step: null context"); return XRVIO_ERR_ARG; }
+    if (is_async(ctx)) {
+        for (int l = 0; l < (int)ctx->lanes.size(); ++l) lane_enqueue(ctx, l, [](Lane *lane) { return lane_step(lane); }, true);
+        return XRVIO_OK;
+    }
     return each_lane(ctx, [](Lane *l) { return lane_step(l); });
 }
 
-int xrvio_get_pose(xrvio_ctx *ctx, int session, xrvio_pose *pose) { LANE_OF(session, l, i); return lane_get_pose(l, i, pose); }
-int xrvio_get_latest_state(xrvio_ctx *ctx, int session, double *t, double state16[16]) { LANE_OF(session, l, i); return lane_get_latest_state(l, i, t, state16); }
-int xrvio_get_state(xrvio_ctx *ctx, int session) { LANE_OF(session, l, i); return lane_get_state(l, i); }
-int xrvio_get_landmarks(xrvio_ctx *ctx, int session, double *xyz, int capacity) { LANE_OF(session, l, i); return lane_get_landmarks(l, i, xyz, capacity); }
+// In asynchronous mode this is the one getter that does not wait: it returns the newest pose the session has produced so far
+// (the frame it belongs to is pose->t), like Detail::get_latest_pose of the reference's threaded build.
+int xrvio_get_pose(xrvio_ctx *ctx, int session, xrvio_pose *pose) {
+    LANE_OF(session, l, i);
+    if (is_async(ctx)) {
+        std::lock_guard<std::mutex> g(ctx->workers[ctx->where[session].first]->pose_mu);
+        return lane_get_pose(l, i, pose);
+    }
+    return lane_get_pose(l, i, pose);
+}
+int xrvio_get_latest_state(xrvio_ctx *ctx, int session, double *t, double state16[16]) { LANE_IDLE(session); LANE_OF(session, l, i); return lane_get_latest_state(l, i, t, state16); }
+int xrvio_get_state(xrvio_ctx *ctx, int session) { LANE_IDLE(session); LANE_OF(session, l, i); return lane_get_state(l, i); }
+int xrvio_get_landmarks(xrvio_ctx *ctx, int session, double *xyz, int capacity) { LANE_IDLE(session); LANE_OF(session, l, i); return lane_get_landmarks(l, i, xyz, capacity); }
 
 int xrvio_get_features(xrvio_ctx *ctx, int session, double *xy, long long *track_id, int *track_len, int capacity) {
+    LANE_IDLE(session);
     LANE_OF(session, l, i);
     Session &s = l->ses[i];
     if (s.ft_map.frame_num() == 0) return 0;
@@ -1070,6 +1159,7 @@ int xrvio_get_features(xrvio_ctx *ctx, int session, double *xy, long long *track
 }
 
 int xrvio_get_init_info(xrvio_ctx *ctx, int session, xrvio_init_info *out) {
+    LANE_IDLE(session);
     LANE_OF(session, l, i);
     if (!out) { xrvio_set_error("xrvio_get_init_info: null output"); return XRVIO_ERR_ARG; }
     *out = l->ses[i].init;
@@ -1079,6 +1169,7 @@ int xrvio_get_init_info(xrvio_ctx *ctx, int session, xrvio_init_info *out) {
 
 int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *st) {
     if (!ctx || !st) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    if (is_async(ctx)) { const int rc = drain_all(ctx); if (rc) return rc; }
     std::memset(st, 0, sizeof(*st));
     for (Lane *l : ctx->lanes) {
         xrvio_stats a;
@@ -1093,11 +1184,13 @@ int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *st) {
 }
 int xrvio_set_profiling(xrvio_ctx *ctx, int enable) {
     if (!ctx) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    if (is_async(ctx)) { const int rc = drain_all(ctx); if (rc) return rc; }
     for (Lane *l : ctx->lanes) lane_set_profiling(l, enable);
     return XRVIO_OK;
 }
 int xrvio_get_kernel_times(xrvio_ctx *ctx, double *ms, long long *launches, int capacity) {
     if (!ctx || !ms || !launches) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    if (is_async(ctx)) { const int rc = drain_all(ctx); if (rc) return rc; }
     for (int k = 0; k < capacity; ++k) { ms[k] = 0; launches[k] = 0; }
     int nf = 0;
     for (Lane *l : ctx->lanes) {
@@ -1107,8 +1200,16 @@ int xrvio_get_kernel_times(xrvio_ctx *ctx, double *ms, long long *launches, int 
     }
     return nf;
 }
+int xrvio_debug_lane_busy(xrvio_ctx *ctx, double *ms_per_lane, int capacity) {
+    if (!ctx || !ms_per_lane) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    if (is_async(ctx)) { const int rc = drain_all(ctx); if (rc) return rc; }
+    const int L = (int)ctx->lanes.size();
+    for (int l = 0; l < L && l < capacity; ++l) ms_per_lane[l] = ctx->lanes[l]->phase_ms[31];
+    return L;
+}
 int xrvio_get_phase_times(xrvio_ctx *ctx, double *ms, int capacity) {
     if (!ctx || !ms) { xrvio_set_error("bad argument"); return XRVIO_ERR_ARG; }
+    if (is_async(ctx)) { const int rc = drain_all(ctx); if (rc) return rc; }
     for (int k = 0; k < capacity; ++k) ms[k] = 0;
     for (Lane *l : ctx->lanes) {
         double m[32];

@@ -866,6 +866,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
 
 static int lane_step(Lane *c) {
     if (!c) { xrvio_set_error("xrvio_step: null context"); return XRVIO_ERR_ARG; }
+    PhaseTimer busy_(c, 31);            // slot 31: wall time this lane spent inside its steps (xrvio_debug_lane_busy)
     CKC(cudaSetDevice(c->device));
     while (true) {
         std::vector<Session *> act;

@@ -84,6 +84,8 @@ template <int KA, bool SHARED> struct SmemT {
     double g[NPv], scale[NPv], D[NPv], y[NPv], bred[NPv];
     double du[NPv], dw[NPv];               // unscaled steepest-descent / Gauss-Newton directions of the current linearisation
     double colp[6 * NPv];                  // the six scaled columns of the current Cholesky panel (gauss_newton)
+    double linv[SHARED ? (NPv / 6) * 36 : 1];   // inverses of the 6 x 6 diagonal blocks of L (sliding-window instance: the substitutions
+                                           // multiply by them instead of solving each triangle on one thread)
     double red[NW];
     double jrinv[KA * 9];
     unsigned char col_free[NPv];
@@ -155,6 +157,9 @@ struct Prob {
     // scratch (global)
     double *inv_x, *inv_c, *h_ll, *g_l, *sc_l, *D_l, *y_l, *ht_l, *W, *Hcopy, *pre_s, *m_dx, *m_r, *m_v, *m_T, *du_l, *dw_l;
     int M, NPc;                    // free landmarks, pose/motion columns = 15 * n_active
+    // J^T J by groups (sliding-window instance): the weighted Jacobian rows of every reprojection residual, transposed
+    // ([26][NJ]: Jt row 0, Jr row 0, Jt row 1, Jr row 1 (6 each), r0, r1), and the runs of equal (target, reference) in the sorted list
+    double *JB; int *grp_start; int n_grp, NJ;
     int Wp;                        // row pitch of W in doubles: M rounded up to 32, so that every row (and every 32-landmark tile of
                                    // it) starts on a 256-byte boundary -- what the bulk-copy staging of solve_large.cuh needs
 };
@@ -168,6 +173,41 @@ static __device__ void prepare_tangents(Prob &P, double *tb) {
         double *t = tb + (size_t)o * 6;
         t[0] = T(0, 0); t[1] = T(1, 0); t[2] = T(2, 0); t[3] = T(0, 1); t[4] = T(1, 1); t[5] = T(2, 1);
     }
+    __syncthreads();
+}
+
+// One-time per problem: the runs of equal (target, reference) in the (sorted) reprojection list.  gs[g] = first observation of
+// run g, gs[n_grp] = n_rpe.  Block-wide stream compaction of the run heads (ballot + warp totals).
+// (an even number of doubles: the scratch of the next problem must stay 16-byte aligned for the bulk copies of W)
+constexpr size_t jb_doubles(int n_rpe) { return (size_t)26 * (((size_t)n_rpe + 31) / 32 * 32) + ((((size_t)n_rpe + 4) / 2 + 3) & ~(size_t)1); }
+template <class SM> static __device__ void prepare_groups(Prob &P, SM &s, double *buf) {
+    XV_ASSUME_SHARED(&s);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = P.d.n_rpe;
+    P.NJ = (n + 31) / 32 * 32;
+    P.JB = buf;
+    int *gs = reinterpret_cast<int *>(buf + (size_t)26 * P.NJ);
+    P.grp_start = gs;
+    int run = 0;
+    for (int base = 0; base < n; base += ST) {
+        const int o = base + tid;
+        bool head = false;
+        if (o < n) {
+            const RpeObs &a = P.rpe[P.d.rpe_off + o];
+            head = o == 0;
+            if (o > 0) { const RpeObs &b = P.rpe[P.d.rpe_off + o - 1]; head = a.tgt != b.tgt || a.ref != b.ref; }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s.red[warp] = (double)__popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int k = 0; k < NW; ++k) { const int cnt = (int)s.red[k]; if (k < warp) woff += cnt; tot += cnt; }
+        if (head) gs[run + woff + __popc(bal & ((1u << lane) - 1u))] = o;
+        run += tot;
+        __syncthreads();
+    }
+    if (tid == 0) gs[run] = n;
+    P.n_grp = run;
     __syncthreads();
 }
 
@@ -384,6 +424,32 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
             for (int k = 0; k < 12; ++k) e.Jt[k] *= w;
             if (!prior) { for (int k = 0; k < 12; ++k) e.Jr[k] *= w; e.Jl[0] *= w; e.Jl[1] *= w; }
         }
+        if constexpr (SM::kSharedH) {
+            // ---- sliding-window instance, phase 1: park the weighted rows (zeroed where the block is constant) and finish the
+            // landmark column; the (target, reference) blocks are summed per run of observations in phase 2 below ----
+            if (valid) {
+                double *jb = P.JB + o;
+                const size_t NJ = (size_t)P.NJ;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    jb[(size_t)k * NJ] = tf ? e.Jt[k] : 0.0;
+                    jb[(size_t)(6 + k) * NJ] = rf ? e.Jr[k] : 0.0;
+                    jb[(size_t)(12 + k) * NJ] = tf ? e.Jt[6 + k] : 0.0;
+                    jb[(size_t)(18 + k) * NJ] = rf ? e.Jr[6 + k] : 0.0;
+                }
+                jb[(size_t)24 * NJ] = e.r[0];
+                jb[(size_t)25 * NJ] = e.r[1];
+                if (lf) {
+                    atomicAdd(&P.h_ll[lm], e.Jl[0] * e.Jl[0] + e.Jl[1] * e.Jl[1]);
+                    atomicAdd(&P.g_l[lm], e.Jl[0] * e.r[0] + e.Jl[1] * e.r[1]);
+                    if (tf)
+                        for (int k = 0; k < 6; ++k) P.W[(size_t)(ts * 6 + k) * P.Wp + lm] = e.Jl[0] * e.Jt[k] + e.Jl[1] * e.Jt[6 + k];
+                    if (rf)
+                        for (int k = 0; k < 6; ++k) atomicAdd(&P.W[(size_t)(rs * 6 + k) * P.Wp + lm], e.Jl[0] * e.Jr[k] + e.Jl[1] * e.Jr[6 + k]);
+                }
+            }
+            continue;
+        }
         bool fast = false;
         if constexpr (!SM::kSharedH) {
             const int ts0 = __shfl_sync(0xffffffffu, ts, 0), rs0 = __shfl_sync(0xffffffffu, rs, 0);
@@ -449,6 +515,48 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
                     for (int k = 0; k < 6; ++k) P.W[(size_t)(ts * 6 + k) * P.Wp + lm] = e.Jl[0] * e.Jt[k] + e.Jl[1] * e.Jt[6 + k];
                 if (rf)
                     for (int k = 0; k < 6; ++k) atomicAdd(&P.W[(size_t)(rs * 6 + k) * P.Wp + lm], e.Jl[0] * e.Jr[k] + e.Jl[1] * e.Jr[6 + k]);
+            }
+        }
+    }
+    if constexpr (SM::kSharedH) {
+        // ---- phase 2: one thread per (run, row) of the 12 x 12 block [Jt | Jr]^T [Jt | Jr] of a (target, reference) run: the row's
+        // entries up to the diagonal and its gradient entry are summed over the run's observations in registers -- no shuffles, one
+        // shared-memory atomic per entry and run, and a summation order that does not depend on how observations fall into warps.
+        // (The segmented warp sums this replaces cost 141 kcycles per Jacobian evaluation of a window problem on a B200.) ----
+        __syncthreads();
+        const size_t NJ = (size_t)P.NJ;
+        for (int task = tid; task < P.n_grp * 12; task += ST) {
+            const int grp = task / 12, c = task % 12;
+            const int o0 = P.grp_start[grp], o1 = P.grp_start[grp + 1];
+            const RpeObs &ob0 = P.rpe[P.d.rpe_off + o0];
+            const int ts = ob0.tgt, rs = ob0.ref;
+            const bool t_act = ts < P.d.n_active && s.pose_free[ts];
+            const bool r_act = rs < P.d.n_active && s.pose_free[rs];
+            if (c < 6 ? !t_act : !r_act) continue;
+            // rows of JB holding this column: k0 (residual row 0) and k0 + 12 (residual row 1); columns 0..5 = Jt, 6..11 = Jr
+            const double *q0 = P.JB + (size_t)c * NJ, *q1 = P.JB + (size_t)(12 + c) * NJ;
+            double acc[12], gacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+            for (int o = o0; o < o1; ++o) {
+                const double a0 = q0[o], a1 = q1[o];
+                gacc += a0 * P.JB[(size_t)24 * NJ + o] + a1 * P.JB[(size_t)25 * NJ + o];
+#pragma unroll
+                for (int k = 0; k < 12; ++k)
+                    if (k <= c) acc[k] += a0 * P.JB[(size_t)k * NJ + o] + a1 * P.JB[(size_t)(12 + k) * NJ + o];
+            }
+            if (c < 6) {
+                for (int k = 0; k <= c; ++k) atomicAdd(&s.H[hidx(15 * ts + c, 15 * ts + k)], acc[k]);
+                atomicAdd(&s.g[15 * ts + c], gacc);
+            } else {
+                const int i = c - 6;
+                if (t_act)
+                    for (int k = 0; k < 6; ++k) {
+                        const int a = 15 * ts + k, b = 15 * rs + i;
+                        atomicAdd(&s.H[a > b ? hidx(a, b) : hidx(b, a)], acc[k]);
+                    }
+                for (int k = 6; k <= c; ++k) atomicAdd(&s.H[hidx(15 * rs + i, 15 * rs + k - 6)], acc[k]);
+                atomicAdd(&s.g[15 * rs + i], gacc);
             }
         }
     }

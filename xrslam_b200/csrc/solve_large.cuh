@@ -42,17 +42,22 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 // Rows are padded to 36 doubles in shared memory: the four row groups a half-warp reads in one fragment load then fall
 // into distinct banks.  A warp carries at most three output blocks (24 accumulator registers), so windows with more than
 // 48 blocks take two passes over the tiles: every W element leaves L2 at most twice.
-constexpr int WT_L = 32;                           // landmarks per tile
-constexpr int WT_PITCH = 36;                       // doubles per staged row
-constexpr int WT_ROWS = 6 * kMaxActiveLarge;       // 192
 constexpr int WT_BLOCKS = 3;                       // output blocks per warp and pass
-struct alignas(128) WStage {
-    double w[2][WT_ROWS][WT_PITCH];
-    double ih[2][WT_L];
+// ROWS: pose rows (6 per free frame); TL: landmarks per tile; PITCH: doubles per staged row, chosen so that PITCH * 2 mod 32 = 8:
+// the four row groups of a half-warp's fragment load (rows g, columns 4u + t) then hit 16 distinct banks.
+template <int ROWS, int TL, int PITCH> struct alignas(128) WStageT {
+    static constexpr int kRows = ROWS, kL = TL, kPitch = PITCH;
+    double w[2][ROWS][PITCH];
+    double ih[2][TL];
     unsigned long long bar[2];
 };
-constexpr size_t kSmemLBytes = (sizeof(SmemL) + 127) / 128 * 128;      // WStage follows SmemL in the dynamic shared memory
-constexpr size_t kSolveLargeSmem = kSmemLBytes + sizeof(WStage);
+using WStage = WStageT<6 * kMaxActiveLarge, 32, 36>;     // large windows: 2 x 55 KB
+using WStageS = WStageT<6 * kMaxActive, 16, 20>;         // sliding windows: 2 x 11.5 KB next to the 130 KB packed H
+template <class SM> struct WStageOf { using type = WStage; };
+template <> struct WStageOf<Smem> { using type = WStageS; };
+template <class SM> struct SmemCore { static constexpr size_t bytes = (sizeof(SM) + 127) / 128 * 128; };      // the stage follows SM in the dynamic shared memory
+constexpr size_t kSolveLargeSmem = SmemCore<SmemL>::bytes + sizeof(WStage);
+constexpr size_t kSolveSmem = SmemCore<Smem>::bytes + sizeof(WStageS);
 
 #ifndef CUEMU
 __device__ __forceinline__ unsigned xv_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -73,19 +78,20 @@ __device__ __forceinline__ void xv_mbar_wait(unsigned long long *bar, unsigned p
 #endif
 
 // warp 0: start the copy of the tile of landmarks [l0, l0 + 32) into buffer `buf`
-__device__ __forceinline__ void wstage_issue(WStage &ws, int buf, const double *W, int Wp, const double *ihv, int R, int l0, int lane) {
+template <class WS> __device__ __forceinline__ void wstage_issue(WS &ws, int buf, const double *W, int Wp, const double *ihv, int R, int l0, int lane) {
+    constexpr int TL = WS::kL;
 #ifndef CUEMU
     if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        xv_mbar_expect_tx(&ws.bar[buf], (unsigned)((R + 1) * WT_L * sizeof(double)));
+        xv_mbar_expect_tx(&ws.bar[buf], (unsigned)((R + 1) * TL * sizeof(double)));
     }
     __syncwarp();
-    for (int r = lane; r < R; r += 32) xv_bulk_g2s(&ws.w[buf][r][0], W + (size_t)r * Wp + l0, WT_L * sizeof(double), &ws.bar[buf]);
-    if (lane == 0) xv_bulk_g2s(&ws.ih[buf][0], ihv + l0, WT_L * sizeof(double), &ws.bar[buf]);
+    for (int r = lane; r < R; r += 32) xv_bulk_g2s(&ws.w[buf][r][0], W + (size_t)r * Wp + l0, TL * sizeof(double), &ws.bar[buf]);
+    if (lane == 0) xv_bulk_g2s(&ws.ih[buf][0], ihv + l0, TL * sizeof(double), &ws.bar[buf]);
 #else
     for (int r = lane; r < R; r += 32)
-        for (int k = 0; k < WT_L; ++k) ws.w[buf][r][k] = W[(size_t)r * Wp + l0 + k];
-    ws.ih[buf][lane] = ihv[l0 + lane];
+        for (int k = 0; k < TL; ++k) ws.w[buf][r][k] = W[(size_t)r * Wp + l0 + k];
+    if (lane < TL) ws.ih[buf][lane] = ihv[l0 + lane];
 #endif
 }
 
@@ -97,7 +103,9 @@ template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M, na = P.d.n_active, Wp = P.Wp;
     if (M <= 0) return;
-    WStage &ws = *reinterpret_cast<WStage *>(reinterpret_cast<unsigned char *>(&s) + kSmemLBytes);
+    using WS = typename WStageOf<SM>::type;
+    constexpr int WT_L = WS::kL, WT_PITCH = WS::kPitch;
+    WS &ws = *reinterpret_cast<WS *>(reinterpret_cast<unsigned char *>(&s) + SmemCore<SM>::bytes);
     XV_ASSUME_SHARED(&ws);
     const int R = 6 * na;
     const int nb = (R + 15) / 16;
