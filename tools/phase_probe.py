@@ -23,6 +23,7 @@ for s, st in enumerate(streams):
         q, p, v = st.gt_state(st.frame_time(k)); ctx.push_bootstrap_state(s, st.frame_time(k), q, p, v)
 P = 640 * 480
 tp = [0, 0, 0]
+lane_hist = []
 import ctypes as _ct
 for k in range(n_frames - 1):
     if k == PRIME:
@@ -30,6 +31,9 @@ for k in range(n_frames - 1):
     if k == PRIME:
         base = ctx.phase_times().copy(); tp = [0, 0, 0]; t00 = time.perf_counter()
     t0 = time.perf_counter(); ctx.push_imu(*batches[k]); t1 = time.perf_counter(); ctx.step(); t2 = time.perf_counter()
+    if k >= PRIME:
+        _b = (_ct.c_double * 64)(); _nl = capi.lib.xrvio_debug_lane_busy(ctx._h, _b, 64)
+        lane_hist.append([_b[i] for i in range(_nl)])
     ctx.push_images(list(range(S)), [fr.data_ptr() + (s * n_frames + k) * P for s in range(S)], [st.frame_time(k) for st in streams], on_device=True)
     t3 = time.perf_counter(); tp[0] += t1 - t0; tp[1] += t2 - t1; tp[2] += t3 - t2
 torch.cuda.synchronize()
@@ -37,6 +41,12 @@ tot = time.perf_counter() - t00
 ph = ctx.phase_times() - base
 n = n_frames - 1 - PRIME
 print('steps', n, 'total ms/step', tot / n * 1e3, 'python push_imu/step/push_images ms', [x / n * 1e3 for x in tp])
+if len(lane_hist) > 2:
+    lh = np.diff(np.array(lane_hist), axis=0)            # per step, per lane: wall time inside lane_step
+    print('lane-step ms: mean %.2f  p50 %.2f  p90 %.2f  p99 %.2f  max %.2f | per-step max over lanes: mean %.2f p50 %.2f max %.2f | lane means %s'
+          % (lh.mean(), np.percentile(lh, 50), np.percentile(lh, 90), np.percentile(lh, 99), lh.max(), lh.max(axis=1).mean(),
+             np.percentile(lh.max(axis=1), 50), lh.max(axis=1).max(), np.round(lh.mean(axis=0), 2).tolist()))
+    print('slowest lane-steps (step, lane, ms):', sorted([(int(i), int(j), round(float(lh[i, j]), 2)) for i in range(lh.shape[0]) for j in range(lh.shape[1])], key=lambda x: -x[2])[:8])
 names = {0: 'A host prep', 1: 'A launch+preint sync', 2: 'B host klt prep', 3: 'B klt launch+sync', 4: 'C host ransac/order', 5: 'C poisson', 6: 'C host apply', 7: 'D host', 8: 'D poisson', 9: 'D host attach',
          10: 'E mirror', 11: 'E preint run', 12: 'F tri+build', 13: 'F solve run', 14: 'G writeback/manage', 15: 'G tri run', 16: 'H host preint build', 17: 'H preint run', 18: 'H build problems', 19: 'H solve run', 20: 'I gates', 21: 'I marg', 22: 'latest', 30: 'push_images'}
 for i in range(32):

@@ -20,6 +20,7 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <string>
@@ -682,6 +683,10 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
     CKC(c->tjobs.reserve((size_t)S * 512)); CKC(c->tviews.reserve((size_t)S * 256 * 8 * 16)); CKC(c->tout.reserve((size_t)S * 512 * 4));
     CKC(c->scratch.reserve((size_t)S * (xvbe::solve_scratch_doubles(XRVIO_MAX_ACTIVE, 768, 12, XRVIO_MAX_ACTIVE, 4096) + (size_t)2 * 180 * 180 + 8192) * sizeof(double)));
     CKC(c->sbuf.idx_raw.reserve(S)); CKC(c->sbuf.idx_next.reserve(S)); CKC(c->sbuf.idx_prev.reserve(S));
+    // the marginalisation stream's own scratch and staging block, sized for a full batch up front (growing them later costs a
+    // cudaFree, i.e. a device-wide synchronisation that stalls every lane of the context)
+    CKC(c->scratch_marg.reserve((size_t)S * xvbe::marg_scratch_doubles(XRVIO_MAX_ACTIVE, 768, 2048) * sizeof(double)));
+    CKC(c->stage_marg.reserve((size_t)S * (sizeof(xvbe::MargDesc) + XRVIO_MAX_ACTIVE * 16 * 8 + 768 * 8 + 2048 * sizeof(xvbe::RpeObs) + XRVIO_PRE_BLOCK * 8 + 1024)));
     CKC(c->stage.reserve((size_t)S * (XRVIO_MAX_FRAMES * 16 * 8 + 1024 * 8 + 4096 * sizeof(xvbe::RpeObs) + 16 * XRVIO_PRE_BLOCK * 8 + 16 * 64 * 7 * 8 + 65536)));
     c->ses.resize(S);
     {

@@ -867,6 +867,20 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
 static int lane_step(Lane *c) {
     if (!c) { xrvio_set_error("xrvio_step: null context"); return XRVIO_ERR_ARG; }
     PhaseTimer busy_(c, 31);            // slot 31: wall time this lane spent inside its steps (xrvio_debug_lane_busy)
+    // diagnostic: XRVIO_SLOW_STEP_MS=<ms> prints the phase breakdown of every lane step that takes longer
+    static const double slow_ms = [] { const char *e = std::getenv("XRVIO_SLOW_STEP_MS"); return e ? std::atof(e) : 0.0; }();
+    struct SlowDump {
+        Lane *c; double thr; double before[32]; std::chrono::steady_clock::time_point t0;
+        SlowDump(Lane *c_, double thr_) : c(c_), thr(thr_), t0(std::chrono::steady_clock::now()) { if (thr > 0) std::memcpy(before, c->phase_ms, sizeof(before)); }
+        ~SlowDump() {
+            if (thr <= 0) return;
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (ms < thr) return;
+            std::string line = "[xrvio] slow lane step " + std::to_string(ms) + " ms:";
+            for (int k = 0; k < 31; ++k) { const double d = c->phase_ms[k] - before[k]; if (d > 0.3) line += " p" + std::to_string(k) + "=" + std::to_string(d).substr(0, 5); }
+            std::fprintf(stderr, "%s\n", line.c_str());
+        }
+    } slow_dump_(c, slow_ms);
     CKC(cudaSetDevice(c->device));
     while (true) {
         std::vector<Session *> act;

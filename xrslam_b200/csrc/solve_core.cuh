@@ -118,6 +118,24 @@ template <class SM> __device__ __forceinline__ double block_max(double v, SM &s)
     return t;
 }
 
+// D(8x8) += A(8x4) B(4x8), FP64.  Fragments (PTX ISA, mma.m8n8k4 .f64): with g = lane >> 2, t = lane & 3 a lane holds
+// A[g][t], B[t][g] and D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+#ifdef CUEMU
+    // test-only SIMT emulator: the same contraction spelled with shuffles, so the fragment layout is what gets tested
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int k = 0; k < 4; ++k) {
+        const double ak = __shfl_sync(0xffffffffu, a, g * 4 + k);
+        const double b0 = __shfl_sync(0xffffffffu, b, (2 * t) * 4 + k);
+        const double b1 = __shfl_sync(0xffffffffu, b, (2 * t + 1) * 4 + k);
+        d0 += ak * b0;
+        d1 += ak * b1;
+    }
+#else
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+#endif
+}
+
 // Segmented suffix sum over lanes with sorted (contiguous) keys; segment heads end up with the sum.  Which partner values a lane
 // takes depends on the keys alone, so the five key comparisons are done once per batch of observations (seg_mask) and every
 // one of the ~90 sums of the batch is five value shuffles with predicated adds.
@@ -519,44 +537,65 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
         }
     }
     if constexpr (SM::kSharedH) {
-        // ---- phase 2: one thread per (run, row) of the 12 x 12 block [Jt | Jr]^T [Jt | Jr] of a (target, reference) run: the row's
-        // entries up to the diagonal and its gradient entry are summed over the run's observations in registers -- no shuffles, one
-        // shared-memory atomic per entry and run, and a summation order that does not depend on how observations fall into warps.
-        // (The segmented warp sums this replaces cost 141 kcycles per Jacobian evaluation of a window problem on a B200.) ----
+        // ---- phase 2: one WARP per run of observations with equal (target, reference).  With X = [Jt | Jr | r] (13 columns, padded
+        // to 16) over the 2 n residual rows of the run, X^T X holds everything the run contributes: the 12 x 12 pose blocks and, in
+        // row 12, the gradient entries.  It is a true contraction over the residual rows and runs on the FP64 tensor pipe
+        // (mma.sync.m8n8k4: A and B fragments are the same two loads per lane and k-step); three 8 x 8 tiles cover the lower
+        // triangle.  No shuffles, one shared-memory atomic per entry and run, and a summation order that does not depend on how
+        // the observations fall into warps.  (Measured on a B200, kcycles per Jacobian evaluation of a window problem: segmented
+        // warp sums 141, one thread per (run, row) with scalar loads from L2 588.) ----
         __syncthreads();
         const size_t NJ = (size_t)P.NJ;
-        for (int task = tid; task < P.n_grp * 12; task += ST) {
-            const int grp = task / 12, c = task % 12;
+        const int g8 = lane >> 2, t4 = lane & 3;
+        for (int grp = warp; grp < P.n_grp; grp += NW) {
             const int o0 = P.grp_start[grp], o1 = P.grp_start[grp + 1];
             const RpeObs &ob0 = P.rpe[P.d.rpe_off + o0];
             const int ts = ob0.tgt, rs = ob0.ref;
             const bool t_act = ts < P.d.n_active && s.pose_free[ts];
             const bool r_act = rs < P.d.n_active && s.pose_free[rs];
-            if (c < 6 ? !t_act : !r_act) continue;
-            // rows of JB holding this column: k0 (residual row 0) and k0 + 12 (residual row 1); columns 0..5 = Jt, 6..11 = Jr
-            const double *q0 = P.JB + (size_t)c * NJ, *q1 = P.JB + (size_t)(12 + c) * NJ;
-            double acc[12], gacc = 0.0;
+            if (!t_act && !r_act) continue;                 // warp-uniform
+            double d00[2] = {0.0, 0.0}, d10[2] = {0.0, 0.0}, d11[2] = {0.0, 0.0};
+            // column g8 of X is a Jacobian column (< 12); column 8 + g8 is a Jacobian column for g8 < 4, r for g8 == 4, padding beyond
+            for (int row = 0; row < 2; ++row) {
+                const double *x0 = P.JB + (size_t)(row * 12 + g8) * NJ;
+                const double *x1 = g8 < 4 ? P.JB + (size_t)(row * 12 + 8 + g8) * NJ : P.JB + (size_t)(24 + row) * NJ;
+                for (int ob = o0; ob < o1; ob += 16) {
+                    double a0[4], a1[4];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) acc[k] = 0.0;
-            for (int o = o0; o < o1; ++o) {
-                const double a0 = q0[o], a1 = q1[o];
-                gacc += a0 * P.JB[(size_t)24 * NJ + o] + a1 * P.JB[(size_t)25 * NJ + o];
-#pragma unroll
-                for (int k = 0; k < 12; ++k)
-                    if (k <= c) acc[k] += a0 * P.JB[(size_t)k * NJ + o] + a1 * P.JB[(size_t)(12 + k) * NJ + o];
-            }
-            if (c < 6) {
-                for (int k = 0; k <= c; ++k) atomicAdd(&s.H[hidx(15 * ts + c, 15 * ts + k)], acc[k]);
-                atomicAdd(&s.g[15 * ts + c], gacc);
-            } else {
-                const int i = c - 6;
-                if (t_act)
-                    for (int k = 0; k < 6; ++k) {
-                        const int a = 15 * ts + k, b = 15 * rs + i;
-                        atomicAdd(&s.H[a > b ? hidx(a, b) : hidx(b, a)], acc[k]);
+                    for (int u = 0; u < 4; ++u) {                 // four k-steps: the eight loads are issued before the tensor-pipe work
+                        const int o = ob + 4 * u + t4;
+                        a0[u] = o < o1 ? x0[o] : 0.0;
+                        a1[u] = (o < o1 && g8 <= 4) ? x1[o] : 0.0;
                     }
-                for (int k = 6; k <= c; ++k) atomicAdd(&s.H[hidx(15 * rs + i, 15 * rs + k - 6)], acc[k]);
-                atomicAdd(&s.g[15 * rs + i], gacc);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        dmma_m8n8k4(d00[0], d00[1], a0[u], a0[u]);
+                        dmma_m8n8k4(d10[0], d10[1], a1[u], a0[u]);
+                        dmma_m8n8k4(d11[0], d11[1], a1[u], a1[u]);
+                    }
+                }
+            }
+            // lane (g8, t4) holds entries (8 ti + g8, 8 tj + 2 t4 + i) of tile (ti, tj)
+#pragma unroll
+            for (int tile = 0; tile < 3; ++tile) {
+                const int ti = tile == 0 ? 0 : 1, tj = tile == 2 ? 1 : 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int R = 8 * ti + g8, C = 8 * tj + 2 * t4 + i;
+                    const double v = tile == 0 ? d00[i] : (tile == 1 ? d10[i] : d11[i]);
+                    if (C > R || R > 12 || C >= 12) continue;
+                    if (R == 12) {                                  // gradient row
+                        if (C < 6) { if (t_act) atomicAdd(&s.g[15 * ts + C], v); }
+                        else if (r_act) atomicAdd(&s.g[15 * rs + C - 6], v);
+                    } else if (R < 6) {
+                        if (t_act) atomicAdd(&s.H[hidx(15 * ts + R, 15 * ts + C)], v);
+                    } else if (C < 6) {
+                        if (t_act && r_act) {
+                            const int a = 15 * ts + C, b = 15 * rs + R - 6;
+                            atomicAdd(&s.H[a > b ? hidx(a, b) : hidx(b, a)], v);
+                        }
+                    } else if (r_act) atomicAdd(&s.H[hidx(15 * rs + R - 6, 15 * rs + C - 6)], v);
+                }
             }
         }
     }

@@ -16,24 +16,6 @@ namespace xvbe {
 constexpr int kMaxActiveLarge = XRVIO_MAX_ACTIVE_LARGE;
 using SmemL = SmemT<kMaxActiveLarge, false>;
 
-// D(8x8) += A(8x4) B(4x8), FP64.  Fragments (PTX ISA, mma.m8n8k4 .f64): with g = lane >> 2, t = lane & 3 a lane holds
-// A[g][t], B[t][g] and D[g][2t], D[g][2t+1].
-__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
-#ifdef CUEMU
-    // test-only SIMT emulator: the same contraction spelled with shuffles, so the fragment layout is what gets tested
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    for (int k = 0; k < 4; ++k) {
-        const double ak = __shfl_sync(0xffffffffu, a, g * 4 + k);
-        const double b0 = __shfl_sync(0xffffffffu, b, (2 * t) * 4 + k);
-        const double b1 = __shfl_sync(0xffffffffu, b, (2 * t + 1) * 4 + k);
-        d0 += ak * b0;
-        d1 += ak * b1;
-    }
-#else
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-#endif
-}
-
 // ---- W tiles through the bulk-copy engine (north_star: "Hessian blocks staged through TMA into shared memory") ----------
 // The Schur complement reads every row of W (6 * n_active rows, one double per landmark) once per 16 x 16 output block that
 // touches it -- 12 times for a 30-keyframe window when the fragments come straight from L2.  Instead the CTA streams W through
