@@ -221,6 +221,9 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
     __syncthreads();
     kp.mark(25);
     if (!s.flag) { kp.count(28); return false; }
+    // (A shared-memory variant -- panels of eight, H left in shared memory, trailing update as 8 x 8 mma.sync.m8n8k4 tiles on the
+    // packed rows, tools/chol_shared8.patch -- measured 347 kcycles per call against 210 for the register tiles above: its diagonal
+    // block work on one thread and the scattered fragment accesses to the packed triangle cost more than the tensor pipe saves.)
     // forward / backward substitution (L z = b, L^T y = z) in panels of six columns, two barriers per panel.  Sliding-window
     // instance: the panel's six values are a 6 x 6 product with the inverse of the diagonal block (six threads, no dependent
     // chain; the inverses were computed by the factorisation); large instance: thread 0 solves the 6 x 6 triangle.  Then every

@@ -251,6 +251,7 @@ struct Lane {
     std::vector<cudaEvent_t> prof_pool;
     double prof_ms[16] = {0};
     double phase_ms[32] = {0};         // host wall time per step phase (diagnostics)
+    bool dbg_on = false; std::string dbg_line;      // XRVIO_SLOW_STEP_MS: per-step notes printed with a slow step
     long long prof_launches[16] = {0};
     double *d_prior = nullptr;         // S * 2 * prior_stride doubles, device-resident priors
     size_t prior_stride = 0;

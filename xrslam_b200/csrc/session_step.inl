@@ -723,6 +723,13 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         if (sp->prob2 >= 0 && sp->is_keyframe) {
             c->stats.last_window_cost_initial = c->sout.h[sp->prob2].initial_cost;
             c->stats.last_window_cost_final = c->sout.h[sp->prob2].final_cost;
+            if (c->dbg_on) {
+                const xvbe::SolveOut &so = c->sout.h[sp->prob2];
+                const xvbe::SolveDesc &sd = c->sdesc.h[sp->prob2];
+                c->dbg_line += " [BA it=" + std::to_string(so.iterations) + " ok=" + std::to_string(so.n_successful) + " rej=" + std::to_string(so.n_unsuccessful) +
+                               " term=" + std::to_string(so.termination) + " rpe=" + std::to_string(sd.n_rpe) + " lm=" + std::to_string(sd.n_lm_free) +
+                               " act=" + std::to_string(sd.n_active) + " c0=" + std::to_string(so.initial_cost).substr(0, 8) + " c1=" + std::to_string(so.final_cost).substr(0, 8) + "]";
+            }
             c->stats.window_iterations += c->sout.h[sp->prob2].iterations - 1;       // the trace also holds iteration 0
             c->stats.window_at_limit += c->sout.h[sp->prob2].termination == 0 ? 1 : 0;
         }
@@ -878,9 +885,11 @@ static int lane_step(Lane *c) {
             if (ms < thr) return;
             std::string line = "[xrvio] slow lane step " + std::to_string(ms) + " ms:";
             for (int k = 0; k < 31; ++k) { const double d = c->phase_ms[k] - before[k]; if (d > 0.3) line += " p" + std::to_string(k) + "=" + std::to_string(d).substr(0, 5); }
+            line += c->dbg_line;
             std::fprintf(stderr, "%s\n", line.c_str());
         }
     } slow_dump_(c, slow_ms);
+    c->dbg_on = slow_ms > 0; c->dbg_line.clear();
     CKC(cudaSetDevice(c->device));
     while (true) {
         std::vector<Session *> act;
