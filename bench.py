@@ -243,7 +243,7 @@ def run_cuda_arm(args, rank, world, local_rank):
             ctx.set_profiling(True)
             kt0 = ctx.kernel_times()
         # timed region in the library's asynchronous mode (include/xrvio.h): the calls queue work per lane of sessions and the
-        # lanes run through it at their own pace, at most two steps behind this loop; xrvio_sync at the end waits for all of it
+        # lanes run through it at their own pace, at most six steps behind this loop; xrvio_sync at the end waits for all of it
         ctx.set_async(not args.sync_steps)
         if world > 1:
             dist.barrier()
@@ -324,7 +324,7 @@ def run_cuda_arm(args, rank, world, local_rank):
         'config': {'workload': '64x640x480_streams', 'streams_per_gpu': N_STREAMS, 'image': [W_IMG, H_IMG], 'cam_hz': 20, 'imu_hz': 200,
                    'window_keyframes': 10, 'max_detections': 200, 'prime_frames': PRIME_FRAMES, 'l2': 'inputs_larger_than_L2',
                    'parallelism': 'sessions sharded per GPU, no data-path collective'},
-        'stepping': 'synchronous' if args.sync_steps else 'asynchronous lanes (<= 2 steps ahead), poses polled every step',
+        'stepping': 'synchronous' if args.sync_steps else 'asynchronous lanes (<= 6 steps ahead), poses polled every step',
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': int((e1s['h2d_bytes'] - e0s['h2d_bytes']) / K),
                 'd2h_bytes_per_step': int((e1s['d2h_bytes'] - e0s['d2h_bytes']) / K) + N_STREAMS * 72, 'ms_per_step': ms_e2e / K},
         'gpu_launches': launches,

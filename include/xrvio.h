@@ -242,8 +242,8 @@ int xrvio_push_images(xrvio_ctx *ctx, const int *session, const uint8_t *const *
 int xrvio_step(xrvio_ctx *ctx);
 /* Asynchronous mode (off by default; needs a context of >= 8 sessions, i.e. more than one lane).  xrvio_push_imu,
  * xrvio_push_images and xrvio_step only QUEUE their work per lane and return; every lane of sessions works through its queue at
- * its own pace, at most two steps behind the caller (xrvio_step blocks beyond that).  Image buffers handed to
- * xrvio_push_images must stay valid until the lane has consumed them (xrvio_sync, or two further steps).  xrvio_get_pose does
+ * its own pace, at most six steps behind the caller (xrvio_step blocks beyond that).  Image buffers handed to
+ * xrvio_push_images must stay valid until the lane has consumed them (xrvio_sync, or six further steps).  xrvio_get_pose does
  * not wait and returns the newest pose available (pose->t says for which frame) -- the behaviour of the reference's threaded
  * build, where Detail::get_latest_pose reads whatever the tracker has reached; every other getter waits for the session's lane.
  * Errors of queued work are reported by xrvio_sync or the next waiting call.  Results per session are identical to synchronous

@@ -74,6 +74,8 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return c
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = 0; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *st, unsigned flags, int) { return cudaStreamCreateWithFlags(st, flags); }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class T> inline cudaError_t cudaMemcpyFromSymbol(void *dst, const T &sym, size_t n) { std::memcpy(dst, &sym, n); return cudaSuccess; }
 template <class T> inline cudaError_t cudaMemcpyToSymbol(T &sym, const void *src, size_t n) { std::memcpy(&sym, src, n); return cudaSuccess; }

@@ -104,7 +104,7 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
         __syncthreads();
         for (int p = 0; p < nt; ++p) {
             const int j0 = p * TB;
-            // ---- (1) diagonal tile (and its inverse, for the substitutions) ----
+            // ---- (1) diagonal tile ----
             if (ti == p && tk == p) {
 #pragma unroll
                 for (int c = 0; c < TB; ++c) {
@@ -130,28 +130,6 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
                                     if (li > c && lk > c && lk <= li) a[li][lk] -= a[li][c] * a[lk][c];
                         }
                     }
-                }
-                if (s.flag) {
-                    // N = L_pp^-1 (lower triangular), column by column; rows / columns beyond n act as the identity
-                    double N[TB][TB];
-#pragma unroll
-                    for (int j = 0; j < TB; ++j) {
-#pragma unroll
-                        for (int i = 0; i < TB; ++i) {
-                            if (i < j) { N[i][j] = 0.0; continue; }
-                            const bool in = j0 + i < n && j0 + j < n;
-                            if (i == j) { N[i][j] = in ? idiag[j0 + i] : 1.0; continue; }
-                            double acc = 0.0;
-#pragma unroll
-                            for (int k = 0; k < TB; ++k)
-                                if (k >= j && k < i) acc += a[i][k] * N[k][j];
-                            N[i][j] = in ? -acc * idiag[j0 + i] : 0.0;
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < TB; ++i)
-#pragma unroll
-                        for (int j = 0; j < TB; ++j) s.linv[p * 36 + i * 6 + j] = N[i][j];
                 }
             }
             __syncthreads();
@@ -216,6 +194,35 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
                     const int gi = ti * TB + li, gk = tk * TB + lk;
                     if (ti >= 0 && gi < n && gk <= gi) s.H[hidx(gi, gk)] = a[li][lk];
                 }
+        }
+        __syncthreads();
+        // inverses of the diagonal blocks for the substitutions, all panels at once (one thread per panel, off the factorisation's
+        // critical path): N = L_pp^-1, column by column; rows / columns beyond n act as the identity
+        if (s.flag && tid < nt) {
+            const int p = tid, j0 = p * TB;
+            double Lb[TB][TB], N[TB][TB];
+#pragma unroll
+            for (int i = 0; i < TB; ++i)
+#pragma unroll
+                for (int k = 0; k < TB; ++k) Lb[i][k] = (k < i && j0 + i < n) ? s.H[hidx(j0 + i, j0 + k)] : 0.0;
+#pragma unroll
+            for (int j = 0; j < TB; ++j) {
+#pragma unroll
+                for (int i = 0; i < TB; ++i) {
+                    if (i < j) { N[i][j] = 0.0; continue; }
+                    const bool in = j0 + i < n && j0 + j < n;
+                    if (i == j) { N[i][j] = in ? idiag[j0 + i] : 1.0; continue; }
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < TB; ++k)
+                        if (k >= j && k < i) acc += Lb[i][k] * N[k][j];
+                    N[i][j] = in ? -acc * idiag[j0 + i] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < TB; ++i)
+#pragma unroll
+                for (int j = 0; j < TB; ++j) s.linv[p * 36 + i * 6 + j] = N[i][j];
         }
     }
     __syncthreads();

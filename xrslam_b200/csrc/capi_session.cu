@@ -114,7 +114,7 @@ struct Stage {
     }
 };
 
-constexpr int kImgQueue = 4;       // frames per session that may wait on the device between steps
+constexpr int kImgQueue = 8;       // frames per session that may wait on the device between steps (asynchronous lanes run up to 6 steps behind)
 constexpr int kPyrSlots = kImgQueue + 2;   // pyramid buffers per session: every waiting frame has its pyramid already (built at push time), + previous + spare
 
 // Image kernels run when the images are PUSHED (xrvio_push_images), on the lane's image stream: CLAHE, pyramid and GFTT need
@@ -633,9 +633,13 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
     Lane *c = new Lane();
     struct Guard { Lane *l; ~Guard() { if (l) lane_destroy(l); } } guard{c};      // releases everything on an early error return
     c->prm = *p; c->S = n_sessions; c->device = device;
-    CKC(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&c->st_marg, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&c->st_img, cudaStreamNonBlocking));
+    // The lane's main stream carries the latency chain of the step (single-CTA solves, one-warp filters): highest priority, so that
+    // its few CTAs are placed ahead of the big grids of the image kernels (image stream) and the marginalisation of other lanes.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    CKC(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, prio_hi));
+    CKC(cudaStreamCreateWithPriority(&c->st_marg, cudaStreamNonBlocking, prio_lo));
+    CKC(cudaStreamCreateWithPriority(&c->st_img, cudaStreamNonBlocking, prio_lo));
     CKC(cudaMalloc((void **)&c->d_idx_img, (size_t)2 * n_sessions * sizeof(int)));
     CKC(cudaEventCreateWithFlags(&c->ev_marg_done, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->ev_marg_h2d, cudaEventDisableTiming));
@@ -901,9 +905,10 @@ static int lane_get_stats(Lane *c, xrvio_stats *st) {
 // (xrvio_set_async): push_imu / push_images / step are queued per lane and return at once; every lane works through its queue
 // at its own pace, so a lane whose step is short (no window solve this frame) starts its next frame instead of waiting for the
 // lane with the largest bundle adjustment -- throughput follows the MEAN lane time instead of the maximum per step.  A lane is
-// never more than kMaxStepsAhead steps behind the caller (back-pressure in xrvio_step).  Errors of queued commands are sticky
+// never more than kMaxStepsAhead steps behind the caller (back-pressure in xrvio_step): a window solve that accepts all of its
+// 30 trust-region steps makes a lane step 3-4 times longer than the median, and the slack lets the other lanes run on meanwhile.  Errors of queued commands are sticky
 // per lane and reported by the next call that waits (xrvio_sync, the getters other than xrvio_get_pose).
-constexpr int kMaxStepsAhead = 2;
+constexpr int kMaxStepsAhead = 6;   // < kImgQueue: every queued step may have a frame waiting in the session's image queue
 struct LaneWorker {
     std::thread th;
     std::mutex mu;

@@ -411,8 +411,88 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
     __syncthreads();
     if (kp) kp->mark(kb + 0);
     double cost = 0.0;
+    // Sliding-window instance: the raw evaluation of the preintegration factors (one lane per factor, a serial chain of ~30 k cycles
+    // with Jacobians) gets the last warp and runs under the reprojection residuals of the others; their whitening / J^T J products
+    // join the per-run tensor-pipe tasks of phase 2 in one warp-task list.  Large instance: the sequential layout further down.
+    const bool split_pre = SM::kSharedH && P.d.n_pre > 0;
+    const int n_rw = split_pre ? NW - 1 : NW;
+    // whitening and J^T J / gradient products of one preintegration factor by one warp (raw residual and Jacobians are in its scratch)
+    auto pre_coop = [&](int f, bool whiten_residual) {
+        const PreRef pf = P.pre[P.d.pre_off + f];
+        const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
+        double *sc = P.pre_s + (size_t)f * kPreScratch;
+        const double *Sic = pb + PB_SIC;
+        if (whiten_residual) {                                // (the sequential layout does this with one thread per row before the barrier)
+            if (lane < 15) {
+                double a = 0.0;
+#pragma unroll
+                for (int k = 0; k < 15; ++k) a += Sic[lane * 15 + k] * sc[k];
+                sc[916 + lane] = a;
+                cost += 0.5 * a * a;
+            }
+            __syncwarp();
+        }
+        for (int e = lane; e < 450; e += 32) {              // whiten: Jw = sqrt_inv_cov * J
+            const int which = e / 225, idx = e % 225, r = idx / 15, c = idx % 15;
+            const double *J = sc + (which ? 241 : 16);
+            double a = 0.0;
+            for (int k = 0; k < 15; ++k) a += Sic[r * 15 + k] * J[k * 15 + c];
+            sc[(which ? 691 : 466) + idx] = a;
+        }
+        __syncwarp();
+        const double *Jwi = sc + 466, *Jwj = sc + 691, *rw = sc + 916;
+        const bool has_i = !pf.prior && pf.i < P.d.n_active;
+        const bool has_j = pf.j < P.d.n_active;
+        const int ci = 15 * pf.i, cj = 15 * pf.j;
+        // (i,i) and (j,j) lower triangles, cross block, gradients
+        for (int e = lane; e < 120 + 120 + 225 + 30; e += 32) {
+            if (e < 240) {
+                const bool isj = e >= 120;
+                if (isj ? !has_j : !has_i) continue;
+                int t = isj ? e - 120 : e;
+                int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while (r * (r + 1) / 2 > t) --r;
+                while ((r + 1) * (r + 2) / 2 <= t) ++r;
+                int c = t - r * (r + 1) / 2;
+                const double *J = isj ? Jwj : Jwi;
+                const int c0 = isj ? cj : ci;
+                if (!s.col_free[c0 + r] || !s.col_free[c0 + c]) continue;
+                double a = 0.0;
+                for (int k = 0; k < 15; ++k) a += J[k * 15 + r] * J[k * 15 + c];
+                atomicAdd(&s.H[hidx(c0 + r, c0 + c)], a);
+            } else if (e < 465) {
+                if (!has_i || !has_j) continue;
+                int t = e - 240, r = t / 15, c = t % 15;     // r: column of Jwi, c: column of Jwj
+                if (!s.col_free[ci + r] || !s.col_free[cj + c]) continue;
+                double a = 0.0;
+                for (int k = 0; k < 15; ++k) a += Jwi[k * 15 + r] * Jwj[k * 15 + c];
+                const int A = ci + r, B = cj + c;
+                atomicAdd(&s.H[A > B ? hidx(A, B) : hidx(B, A)], a);
+            } else {
+                int t = e - 465;
+                const bool isj = t >= 15;
+                if (isj ? !has_j : !has_i) continue;
+                int c = isj ? t - 15 : t;
+                const double *J = isj ? Jwj : Jwi;
+                const int c0 = isj ? cj : ci;
+                if (!s.col_free[c0 + c]) continue;
+                double a = 0.0;
+                for (int k = 0; k < 15; ++k) a += J[k * 15 + c] * rw[k];
+                atomicAdd(&s.g[c0 + c], a);
+            }
+        }
+        };
+    if (split_pre && warp == NW - 1)
+        for (int f = lane; f < P.d.n_pre; f += 32) {
+            const PreRef pf = P.pre[P.d.pre_off + f];
+            const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
+            double *sc = P.pre_s + (size_t)f * kPreScratch;
+            const double *si = pf.prior ? (s.us + pf.i * 16) : (S + pf.i * 16);
+            const double *sj = S + pf.j * 16;
+            pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, true, sc, sc + 16, sc + 241);
+        }
     // ---------------- reprojection residuals (Cauchy loss) ----------------
-    for (int base = warp * 32; base < P.d.n_rpe; base += NW * 32) {
+    for (int base = warp * 32; warp < n_rw && base < P.d.n_rpe; base += n_rw * 32) {
         const int o = base + lane;
         const bool valid = o < P.d.n_rpe;
         RpeEval e;
@@ -547,7 +627,10 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
         __syncthreads();
         const size_t NJ = (size_t)P.NJ;
         const int g8 = lane >> 2, t4 = lane & 3;
-        for (int grp = warp; grp < P.n_grp; grp += NW) {
+        const int n_pre_tasks = split_pre ? P.d.n_pre : 0;       // the long tasks first
+        for (int task = warp; task < n_pre_tasks + P.n_grp; task += NW) {
+            if (task < n_pre_tasks) { pre_coop(task, true); continue; }
+            const int grp = task - n_pre_tasks;
             const int o0 = P.grp_start[grp], o1 = P.grp_start[grp + 1];
             const RpeObs &ob0 = P.rpe[P.d.rpe_off + o0];
             const int ts = ob0.tgt, rs = ob0.ref;
@@ -621,7 +704,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
     // ---------------- preintegration factors (no loss) ----------------
     // residuals (and raw Jacobians) of all factors are evaluated SIMT by the first n_pre threads; the
     // whitening and J^T J products of the Jacobian pass are then done cooperatively, one warp per factor
-    if (tid < P.d.n_pre) {
+    if (!split_pre && tid < P.d.n_pre) {
         const int f = tid;
         const PreRef pf = P.pre[P.d.pre_off + f];
         const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
@@ -631,7 +714,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
         pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, want_jac, sc, sc + 16, sc + 241);
     }
     __syncthreads();
-    if (tid < 15 * P.d.n_pre) {          // whitened residual, one thread per row
+    if (!split_pre && tid < 15 * P.d.n_pre) {          // whitened residual, one thread per row
         const int f = tid / 15, r = tid % 15;
         const PreRef pf = P.pre[P.d.pre_off + f];
         const double *Sic = P.pre_blocks + (size_t)pf.block * kPreBlock + PB_SIC;
@@ -644,62 +727,8 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
     }
     if (kp) kp->mark(kb + 3);
     if (want_jac) __syncthreads();
-    for (int f = warp; want_jac && f < P.d.n_pre; f += NW) {
-        const PreRef pf = P.pre[P.d.pre_off + f];
-        const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
-        double *sc = P.pre_s + (size_t)f * kPreScratch;
-        const double *Sic = pb + PB_SIC;
-        if (!want_jac) continue;
-        for (int e = lane; e < 450; e += 32) {              // whiten: Jw = sqrt_inv_cov * J
-            const int which = e / 225, idx = e % 225, r = idx / 15, c = idx % 15;
-            const double *J = sc + (which ? 241 : 16);
-            double a = 0.0;
-            for (int k = 0; k < 15; ++k) a += Sic[r * 15 + k] * J[k * 15 + c];
-            sc[(which ? 691 : 466) + idx] = a;
-        }
-        __syncwarp();
-        const double *Jwi = sc + 466, *Jwj = sc + 691, *rw = sc + 916;
-        const bool has_i = !pf.prior && pf.i < P.d.n_active;
-        const bool has_j = pf.j < P.d.n_active;
-        const int ci = 15 * pf.i, cj = 15 * pf.j;
-        // (i,i) and (j,j) lower triangles, cross block, gradients
-        for (int e = lane; e < 120 + 120 + 225 + 30; e += 32) {
-            if (e < 240) {
-                const bool isj = e >= 120;
-                if (isj ? !has_j : !has_i) continue;
-                int t = isj ? e - 120 : e;
-                int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-                while (r * (r + 1) / 2 > t) --r;
-                while ((r + 1) * (r + 2) / 2 <= t) ++r;
-                int c = t - r * (r + 1) / 2;
-                const double *J = isj ? Jwj : Jwi;
-                const int c0 = isj ? cj : ci;
-                if (!s.col_free[c0 + r] || !s.col_free[c0 + c]) continue;
-                double a = 0.0;
-                for (int k = 0; k < 15; ++k) a += J[k * 15 + r] * J[k * 15 + c];
-                atomicAdd(&s.H[hidx(c0 + r, c0 + c)], a);
-            } else if (e < 465) {
-                if (!has_i || !has_j) continue;
-                int t = e - 240, r = t / 15, c = t % 15;     // r: column of Jwi, c: column of Jwj
-                if (!s.col_free[ci + r] || !s.col_free[cj + c]) continue;
-                double a = 0.0;
-                for (int k = 0; k < 15; ++k) a += Jwi[k * 15 + r] * Jwj[k * 15 + c];
-                const int A = ci + r, B = cj + c;
-                atomicAdd(&s.H[A > B ? hidx(A, B) : hidx(B, A)], a);
-            } else {
-                int t = e - 465;
-                const bool isj = t >= 15;
-                if (isj ? !has_j : !has_i) continue;
-                int c = isj ? t - 15 : t;
-                const double *J = isj ? Jwj : Jwi;
-                const int c0 = isj ? cj : ci;
-                if (!s.col_free[c0 + c]) continue;
-                double a = 0.0;
-                for (int k = 0; k < 15; ++k) a += J[k * 15 + c] * rw[k];
-                atomicAdd(&s.g[c0 + c], a);
-            }
-        }
-    }
+    if (!split_pre)
+        for (int f = warp; f < P.d.n_pre; f += NW) pre_coop(f, false);
     __syncthreads();
     if (kp) kp->mark(kb + 4);
     // ---------------- marginalisation prior (no loss) ----------------
