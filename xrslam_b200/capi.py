@@ -13,6 +13,11 @@ class XrvioError(RuntimeError):
     pass
 
 
+# see bench.py / INTEGRATION.md: one hardware work queue per stream (the library uses up to 24); only effective if no CUDA
+# context exists yet in this process
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
+
 class _Lib:
     def __init__(self):
         self._dll = None

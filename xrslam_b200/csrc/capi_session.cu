@@ -1013,6 +1013,9 @@ int xrvio_default_params(xrvio_params *p, int width, int height) { return xrvio_
 
 int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **out) {
     if (!p || !out || n_sessions <= 0) { xrvio_set_error("xrvio_create: bad argument"); return XRVIO_ERR_ARG; }
+    // one hardware work queue per stream (8 lanes x 3 streams); only effective when this process has no CUDA context yet -- a host
+    // application that initialises CUDA first sets the variable itself
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int L = n_sessions >= 64 ? 8 : (n_sessions >= 32 ? 4 : (n_sessions >= 8 ? 2 : 1));
     if (const char *e = std::getenv("XRVIO_LANES")) L = std::max(1, std::min(std::atoi(e), n_sessions));
     unsigned hc = std::thread::hardware_concurrency();
