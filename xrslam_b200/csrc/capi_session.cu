@@ -235,6 +235,7 @@ struct Lane {
     // device and is first needed by the NEXT window solve of the session, so the host never waits for it (ev_marg_done orders
     // the solves behind it, ev_marg_h2d protects the pinned staging block until its upload has been consumed).
     cudaStream_t st_marg = nullptr;
+    bool own_marg_stream = true;
     cudaEvent_t ev_marg_done = nullptr, ev_marg_h2d = nullptr;
     bool marg_pending = false, marg_h2d_pending = false;
     DevOnly scratch_marg;
@@ -638,8 +639,12 @@ static int lane_create(const xrvio_params *p, int n_sessions, int device, int ho
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     CKC(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, prio_hi));
-    CKC(cudaStreamCreateWithPriority(&c->st_marg, cudaStreamNonBlocking, prio_lo));
     CKC(cudaStreamCreateWithPriority(&c->st_img, cudaStreamNonBlocking, prio_lo));
+    // XRVIO_SHARE_LOW_STREAM=1: marginalisation shares the image stream (two streams per lane, so that 16 lanes still get a
+    // hardware queue per stream out of the 32 available); default: its own stream
+    { const char *e = std::getenv("XRVIO_SHARE_LOW_STREAM"); c->own_marg_stream = !(e && e[0] == '1'); }
+    if (c->own_marg_stream) CKC(cudaStreamCreateWithPriority(&c->st_marg, cudaStreamNonBlocking, prio_lo));
+    else c->st_marg = c->st_img;
     CKC(cudaMalloc((void **)&c->d_idx_img, (size_t)2 * n_sessions * sizeof(int)));
     CKC(cudaEventCreateWithFlags(&c->ev_marg_done, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&c->ev_marg_h2d, cudaEventDisableTiming));
@@ -707,7 +712,7 @@ static int lane_destroy(Lane *c) {
     if (!c) return XRVIO_OK;
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
-    if (c->st_marg) { cudaStreamSynchronize(c->st_marg); cudaStreamDestroy(c->st_marg); }
+    if (c->st_marg) { cudaStreamSynchronize(c->st_marg); if (c->own_marg_stream) cudaStreamDestroy(c->st_marg); }
     if (c->st_img) { cudaStreamSynchronize(c->st_img); cudaStreamDestroy(c->st_img); }
     for (ImgBatch *b : c->img_all) { cudaFreeHost(b->corners_h); cudaFreeHost(b->count_h); cudaFreeHost(b->idx_h); if (b->done) cudaEventDestroy(b->done); delete b; }
     cudaFree(c->d_idx_img);
@@ -1016,7 +1021,9 @@ int xrvio_create(const xrvio_params *p, int n_sessions, int device, xrvio_ctx **
     // one hardware work queue per stream (8 lanes x 3 streams); only effective when this process has no CUDA context yet -- a host
     // application that initialises CUDA first sets the variable itself
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
-    int L = n_sessions >= 64 ? 8 : (n_sessions >= 32 ? 4 : (n_sessions >= 8 ? 2 : 1));
+    // 64 sessions: 10 lanes x 3 streams = 30 of the 32 hardware work queues; the measured optimum (profiles/r2_lane_sweep.txt:
+    // 13.2 k frames/s against 10.6 k with 8 lanes, 12.2 k with 12, 12.0 k with 16 lanes sharing the low-priority stream)
+    int L = n_sessions >= 64 ? 10 : (n_sessions >= 32 ? 4 : (n_sessions >= 8 ? 2 : 1));
     if (const char *e = std::getenv("XRVIO_LANES")) L = std::max(1, std::min(std::atoi(e), n_sessions));
     unsigned hc = std::thread::hardware_concurrency();
     int nt = (int)std::min<unsigned>(hc ? hc : 4u, 64u);

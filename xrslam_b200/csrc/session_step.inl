@@ -86,11 +86,7 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
     { int rc = merge_preint_jobs(c, act); if (rc) return rc; }
     pt.next(1);
     CKC(cudaMemcpyAsync(B.idx_next.d, B.idx_next.h, n * sizeof(int), cudaMemcpyHostToDevice, c->st));
-    for (Session *sp : act) {           // the pyramids KLT reads are complete once the batches' events have fired
-        ImgBatch *b = static_cast<ImgBatch *>(sp->cur->img_batch);
-        if (b && !b->waited) { CKC(cudaStreamWaitEvent(c->st, b->done, 0)); b->waited = true; }
-    }
-    { int rc = run_preint_jobs(c); if (rc) return rc; }     // also synchronises the stream
+    { int rc = run_preint_jobs(c); if (rc) return rc; }     // also synchronises the stream (it needs nothing from the image stream)
     if (c->pre_jobs.n == 0) CKC(cudaStreamSynchronize(c->st));
     CKC(cudaGetLastError());
     pt.next(2);
@@ -143,6 +139,10 @@ int front_end_round(Lane *c, std::vector<Session *> &act) {
         const int *d_n = g.put(c->klt_n.h, (size_t)n);
         const int *d_idx_prev = g.put(B.idx_prev.h, (size_t)n);
         CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));
+        for (Session *sp : act) {       // the pyramids KLT reads are complete once the push batches' events have fired
+            ImgBatch *b = static_cast<ImgBatch *>(sp->cur->img_batch);
+            if (b && !b->waited) { CKC(cudaStreamWaitEvent(c->st, b->done, 0)); b->waited = true; }
+        }
         { ProfScope ps(c, FAM_KLT, 1);
           xvfe::klt_track(c->d_pyr, c->d_pyr, d_idx_prev, B.idx_next.d, n, c->L, d_prev, d_next, d_n, d_status, c->st, &c->klt_maps, &c->klt_maps); }
         c->stats.kernels_launched += 1;
