@@ -217,6 +217,7 @@ typedef struct xrvio_stats {
     double last_window_cost_initial, last_window_cost_final;
     long long window_iterations;        /* trust-region iterations (accepted + rejected) summed over the refine_window solves */
     long long window_at_limit;          /* refine_window solves that ended at solver_iteration_limit (all of them) */
+    long long graph_launches;           /* CUDA graph launches (each replays the 12-13 image-stream operations of one push batch) */
 } xrvio_stats;
 
 /* Outcome of the initializer attempts of a session (core/initializer.cpp:78-571).  last_fail: 0 initialised (or not yet

@@ -85,10 +85,12 @@ def test_session_api_error_paths(xrvio):
         ctx.push_images([2], [img.ctypes.data], [0.0])                      # session index out of range
     with pytest.raises(capi.XrvioError):
         ctx.get_init_info(-1)
-    for k in range(4):                                                       # the image queue holds 4 frames per session
+    for k in range(8):                                                       # the image queue holds 8 frames per session
         ctx.push_images([0], [img.ctypes.data], [0.05 * k])
     with pytest.raises(capi.XrvioError) as e:
-        ctx.push_images([0], [img.ctypes.data], [0.25])
+        ctx.push_images([0], [img.ctypes.data], [0.45])
+    with pytest.raises(capi.XrvioError):
+        ctx.push_images([0, 0], [img.ctypes.data, img.ctypes.data], [0.5, 0.55])   # a session twice in one call
     assert 'queue full' in str(e.value)
     ctx.step()                                                               # no IMU yet: nothing is released, nothing breaks
     assert ctx.get_state(0) == 0 and not ctx.get_pose(0)['valid']

@@ -232,7 +232,7 @@ init_info_dtype = np.dtype([("attempts", "i4"), ("last_fail", "i4"), ("matches",
 stats_dtype = np.dtype([("frames_processed", "i8"), ("kernels_launched", "i8"), ("h2d_bytes", "i8"), ("d2h_bytes", "i8"),
                         ("window_solves", "i8"), ("localize_solves", "i8"), ("subwindow_solves", "i8"), ("marginalizations", "i8"),
                         ("last_window_cost_initial", "f8"), ("last_window_cost_final", "f8"),
-                        ("window_iterations", "i8"), ("window_at_limit", "i8")], align=True)
+                        ("window_iterations", "i8"), ("window_at_limit", "i8"), ("graph_launches", "i8")], align=True)
 
 
 def default_params(width=640, height=480):

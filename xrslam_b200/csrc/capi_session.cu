@@ -126,6 +126,10 @@ struct ImgBatch {
     int *count_h = nullptr;            // n
     int *idx_h = nullptr;              // 2 * cap: raw-slot indices, pyramid indices (pinned source of the index upload)
     cudaEvent_t done = nullptr;        // recorded on the image stream after the read-back
+#ifndef CUEMU
+    cudaGraphExec_t gexec = nullptr;   // the image kernels of a push of graph_n images into this block, captured once
+#endif
+    int graph_n = 0, uses = 0;
     int cap = 0, pending = 0;          // frames of this batch not consumed yet
     bool waited = false;               // the lane stream already waits for `done` / the host has synchronised with it
     bool host_ready = false;
@@ -714,6 +718,9 @@ static int lane_destroy(Lane *c) {
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->st_marg) { cudaStreamSynchronize(c->st_marg); if (c->own_marg_stream) cudaStreamDestroy(c->st_marg); }
     if (c->st_img) { cudaStreamSynchronize(c->st_img); cudaStreamDestroy(c->st_img); }
+#ifndef CUEMU
+    for (ImgBatch *b : c->img_all) if (b->gexec) cudaGraphExecDestroy(b->gexec);
+#endif
     for (ImgBatch *b : c->img_all) { cudaFreeHost(b->corners_h); cudaFreeHost(b->count_h); cudaFreeHost(b->idx_h); if (b->done) cudaEventDestroy(b->done); delete b; }
     cudaFree(c->d_idx_img);
     if (c->ev_marg_done) cudaEventDestroy(c->ev_marg_done);
@@ -816,25 +823,55 @@ static int lane_push_images(Lane *c, const int *session, const uint8_t *const *d
         if (t[i] > s.out_t) { s.out_pose = op; s.out_t = t[i]; }
     }
     int *d_raw_idx = c->d_idx_img, *d_pyr_idx = c->d_idx_img + c->S;
-    CKC(cudaMemcpyAsync(c->d_idx_img, b->idx_h, (size_t)2 * c->S * sizeof(int), cudaMemcpyHostToDevice, c->st_img));
-    const uint8_t *clahe_src = c->d_raw;
-    const int *clahe_idx = d_raw_idx;
-    if (c->d_und) {     // the reader's cv::undistort, on the device (row N2); counted with the CLAHE family
-        ProfScope ps(c, FAM_CLAHE, 1, c->st_img);
-        xvfe::undistort(c->d_raw, d_raw_idx, P, c->d_und, nullptr, P, n, w, h, c->d_und_map, c->st_img);
-        c->stats.kernels_launched += 1;
-        clahe_src = c->d_und; clahe_idx = nullptr;
+    // index upload, (undistortion,) CLAHE, pyramid, GFTT and the read-back of the corner lists: 12-13 stream operations whose
+    // arguments depend only on the batch block and the image count -- captured into a CUDA graph the second time a block sees
+    // the same count and replayed with ONE launch afterwards (the raw image copies above come from caller pointers and stay
+    // outside).  With per-family profiling on (xrvio_set_profiling) the operations are issued one by one so that the events
+    // of xrvio_get_kernel_times keep their meaning.
+    auto issue = [&]() -> int {
+        CKC(cudaMemcpyAsync(c->d_idx_img, b->idx_h, (size_t)2 * c->S * sizeof(int), cudaMemcpyHostToDevice, c->st_img));
+        const uint8_t *clahe_src = c->d_raw;
+        const int *clahe_idx = d_raw_idx;
+        if (c->d_und) {     // the reader's cv::undistort, on the device (row N2); counted with the CLAHE family
+            ProfScope ps(c, FAM_CLAHE, 1, c->st_img);
+            xvfe::undistort(c->d_raw, d_raw_idx, P, c->d_und, nullptr, P, n, w, h, c->d_und_map, c->st_img);
+            clahe_src = c->d_und; clahe_idx = nullptr;
+        }
+        { ProfScope ps(c, FAM_CLAHE, 2, c->st_img);
+          xvfe::clahe(clahe_src, clahe_idx, P, c->d_pyr, d_pyr_idx, c->L.total, c->d_lut, n, w, h, c->prm.clahe_clip_limit,
+                      c->prm.clahe_width, c->prm.clahe_height, c->st_img); }
+        { ProfScope ps(c, FAM_PYRAMID, 3, c->st_img); xvfe::pyramid(c->d_pyr, d_pyr_idx, n, c->L, c->st_img); }
+        { ProfScope ps(c, FAM_GFTT, 2, c->st_img);
+          xvfe::gftt_harris(c->d_pyr, d_pyr_idx, c->L.total, n, w, h, c->prm.max_keypoint_detection, 1.0e-3f, 20.0f, c->corners.d,
+                            c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->st_img); }
+        CKC(cudaMemcpyAsync(b->corners_h, c->corners.d, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->st_img));
+        CKC(cudaMemcpyAsync(b->count_h, c->corner_count.d, n * sizeof(int), cudaMemcpyDeviceToHost, c->st_img));
+        return XRVIO_OK;
+    };
+    bool launched = false;
+#ifndef CUEMU
+    static const bool graphs_on = [] { const char *e = std::getenv("XRVIO_IMG_GRAPH"); return !(e && e[0] == '0'); }();
+    if (graphs_on && !c->prof && b->uses >= 1) {
+        if (b->gexec == nullptr || b->graph_n != n) {
+            if (b->gexec) { cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CKC(cudaStreamBeginCapture(c->st_img, cudaStreamCaptureModeThreadLocal));
+            const int rc = issue();
+            const cudaError_t ce = cudaStreamEndCapture(c->st_img, &graph);
+            if (rc != XRVIO_OK || ce != cudaSuccess || graph == nullptr) { if (graph) cudaGraphDestroy(graph); xrvio_set_error("xrvio_push_images: graph capture failed"); return XRVIO_ERR_CUDA; }
+            const cudaError_t ie = cudaGraphInstantiate(&b->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) { b->gexec = nullptr; xrvio_set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return XRVIO_ERR_CUDA; }
+            b->graph_n = n;
+        }
+        CKC(cudaGraphLaunch(b->gexec, c->st_img));
+        c->stats.graph_launches += 1;
+        launched = true;
     }
-    { ProfScope ps(c, FAM_CLAHE, 2, c->st_img);
-      xvfe::clahe(clahe_src, clahe_idx, P, c->d_pyr, d_pyr_idx, c->L.total, c->d_lut, n, w, h, c->prm.clahe_clip_limit,
-                  c->prm.clahe_width, c->prm.clahe_height, c->st_img); }
-    { ProfScope ps(c, FAM_PYRAMID, 3, c->st_img); xvfe::pyramid(c->d_pyr, d_pyr_idx, n, c->L, c->st_img); }
-    { ProfScope ps(c, FAM_GFTT, 2, c->st_img);
-      xvfe::gftt_harris(c->d_pyr, d_pyr_idx, c->L.total, n, w, h, c->prm.max_keypoint_detection, 1.0e-3f, 20.0f, c->corners.d,
-                        c->corner_count.d, c->d_cand, c->d_cand_count, c->d_maxval, c->st_img); }
-    c->stats.kernels_launched += 2 + 3 + 2;
-    CKC(cudaMemcpyAsync(b->corners_h, c->corners.d, (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->st_img));
-    CKC(cudaMemcpyAsync(b->count_h, c->corner_count.d, n * sizeof(int), cudaMemcpyDeviceToHost, c->st_img));
+#endif
+    if (!launched) { const int rc = issue(); if (rc) return rc; }
+    b->uses++;
+    c->stats.kernels_launched += 2 + 3 + 2 + (c->d_und ? 1 : 0);      // the same kernels run whether issued one by one or replayed from the graph
     c->stats.d2h_bytes += (size_t)n * xvfe::kMaxCorners * 3 * sizeof(float) + n * sizeof(int);
     CKC(cudaEventRecord(b->done, c->st_img));
     CKC(cudaGetLastError());
@@ -1198,7 +1235,7 @@ int xrvio_get_stats(xrvio_ctx *ctx, xrvio_stats *st) {
         st->frames_processed += a.frames_processed; st->kernels_launched += a.kernels_launched; st->h2d_bytes += a.h2d_bytes; st->d2h_bytes += a.d2h_bytes;
         st->window_solves += a.window_solves; st->localize_solves += a.localize_solves; st->subwindow_solves += a.subwindow_solves;
         st->marginalizations += a.marginalizations;
-        st->window_iterations += a.window_iterations; st->window_at_limit += a.window_at_limit;
+        st->window_iterations += a.window_iterations; st->window_at_limit += a.window_at_limit; st->graph_launches += a.graph_launches;
         if (a.last_window_cost_initial != 0) { st->last_window_cost_initial = a.last_window_cost_initial; st->last_window_cost_final = a.last_window_cost_final; }
     }
     return XRVIO_OK;
