@@ -9,6 +9,8 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libxrvio.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
+if os.environ.get("XRVIO_DEBUG_ASSUME") == "1":   # diagnostic build: address-space assumptions of the solve kernels become assertions
+    COMMON.append("-DXRVIO_DEBUG_ASSUME")
 if os.environ.get("XRVIO_KPROF") == "1":      # diagnostic build: clock64 sections inside the solve kernel (tools/phase_probe.py)
     COMMON.append("-DXRVIO_KPROF")
 # per-source extra flags: the front end mirrors OpenCV's non-FMA float arithmetic

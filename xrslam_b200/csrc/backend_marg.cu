@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
     P.flags_g = nullptr;
     P.invd_user = const_cast<double *>(b.inv_depth) + md.lm_off;
     P.rpe = b.rpe; P.rot = nullptr; P.pre = b.pre; P.pre_blocks = b.pre_blocks; P.marg_frames = b.marg_frames;
-    P.M = md.n_lm; P.Wp = (P.M + 31) / 32 * 32; P.NPc = 15 * N; P.marg_n = 15 * md.marg_k;
+    P.M = md.n_lm; P.Wp = (P.M + 31) / 32 * 32; P.W_sh = WLayout<true>::sh; P.W_pitch = WLayout<true>::pitch; P.W_rows = 6 * N; P.NPc = 15 * N; P.marg_n = 15 * md.marg_k;
     double *Gm;      // factor rows (global)
     double *Yg;      // n1 x 15
     {
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
         const size_t Mp = (size_t)((P.M + 31) / 32) * 32 + 32;
         P.inv_x = sc; sc += Mp; P.inv_c = sc; sc += Mp; P.h_ll = sc; sc += Mp; P.g_l = sc; sc += Mp;
         P.sc_l = sc; sc += Mp; P.D_l = sc; sc += Mp; P.y_l = sc; sc += Mp; P.ht_l = sc; sc += Mp;
-        P.W = sc; sc += (size_t)N * 6 * Mp;
+        P.W = sc; sc += (size_t)N * 6 * (Mp + Mp / 4);
         P.Hcopy = sc; sc += HPACK;
         P.pre_s = sc; sc += (size_t)2 * kPreScratch;
         P.m_dx = sc; sc += n + 32; P.m_r = sc; sc += n + 32; P.m_v = sc; sc += n + 32; sc += n + 32;

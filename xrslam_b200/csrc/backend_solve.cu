@@ -9,7 +9,7 @@ using namespace xv;
 size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k, int n_rpe) {
     size_t M = (size_t)((n_lm_free + 31) / 32) * 32 + 32;
     size_t n = (size_t)15 * marg_k;
-    return 8 * M + (size_t)n_active * 6 * M + HPACK + (size_t)n_pre * kPreScratch + 4 * (n + 32) + 2 * n * n + 64 + (size_t)6 * n_rpe + 2 * M + jb_doubles(n_rpe);
+    return 8 * M + (size_t)n_active * 6 * (M + M / 4) + HPACK + (size_t)n_pre * kPreScratch + 4 * (n + 32) + 2 * n * n + 64 + (size_t)6 * n_rpe + 2 * M + jb_doubles(n_rpe);
 }
 
 
@@ -299,7 +299,7 @@ template <class SM> __device__ bool gauss_newton(const Prob &P, SM &s, double mu
         double a = P.g_l[l];
         for (int f = 0; f < na; ++f) {
             if (!s.pose_free[f]) continue;
-            for (int k = 0; k < 6; ++k) a -= P.W[(size_t)(f * 6 + k) * P.Wp + l] * s.y[15 * f + k];
+            for (int k = 0; k < 6; ++k) a -= P.W[widx(P, f * 6 + k, l)] * s.y[15 * f + k];
         }
         a /= P.ht_l[l];
         P.y_l[l] = a;
@@ -320,7 +320,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
     P.invd_user = b.inv_depth + P.d.lm_off;
     P.rpe = b.rpe; P.rot = b.rot; P.pre = b.pre; P.pre_blocks = b.pre_blocks; P.marg_frames = b.marg_frames;
     P.M = P.d.n_lm_free;
-    P.Wp = (P.M + 31) / 32 * 32;
+    P.Wp = (P.M + 31) / 32 * 32; P.W_sh = WLayout<SM::kSharedH>::sh; P.W_pitch = WLayout<SM::kSharedH>::pitch; P.W_rows = 6 * P.d.n_active;
     P.NPc = 15 * P.d.n_active;
     P.marg_n = 15 * P.d.marg_k;
     {
@@ -331,7 +331,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
         const size_t Mp = (size_t)((P.M + 31) / 32) * 32 + 32;
         P.inv_x = sc; sc += Mp; P.inv_c = sc; sc += Mp; P.h_ll = sc; sc += Mp; P.g_l = sc; sc += Mp;
         P.sc_l = sc; sc += Mp; P.D_l = sc; sc += Mp; P.y_l = sc; sc += Mp; P.ht_l = sc; sc += Mp;
-        P.W = sc; sc += (size_t)P.d.n_active * 6 * Mp;
+        P.W = sc; sc += (size_t)P.d.n_active * 6 * (Mp + Mp / 4);       // >= w_doubles(): room for the row padding of either layout
         if constexpr (!SM::kSharedH) { if (tid == 0) s.H.a = sc; sc += SM::HP; }     // published by the barrier in prepare_tangents()
         P.Hcopy = sc; sc += SM::HP;
         P.pre_s = sc; sc += (size_t)P.d.n_pre * kPreScratch;
@@ -394,8 +394,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
         for (int l = tid; l < P.M; l += ST) { const double sl = P.sc_l[l]; P.h_ll[l] *= sl * sl; P.g_l[l] *= sl; }
         for (int ck = tid >> 5; ck < P.d.n_active * 6; ck += NW) {          // one warp per row of W
             const double sck = s.scale[15 * (ck / 6) + ck % 6];
-            double *wr = P.W + (size_t)ck * P.Wp;
-            for (int l = tid & 31; l < P.M; l += 32) wr[l] *= P.sc_l[l] * sck;
+            for (int l = tid & 31; l < P.M; l += 32) P.W[widx(P, ck, l)] *= P.sc_l[l] * sck;
         }
         __syncthreads();
         for (int e = tid; e < P.NPc * (P.NPc + 1) / 2; e += ST) P.Hcopy[e] = s.H[e];
@@ -461,7 +460,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
                 double wv = 0.0;
                 for (int f = 0; f < P.d.n_active; ++f)
                     if (s.pose_free[f])
-                        for (int k = 0; k < 6; ++k) wv += P.W[(size_t)(f * 6 + k) * P.Wp + l] * s.bred[15 * f + k];
+                        for (int k = 0; k < 6; ++k) wv += P.W[widx(P, f * 6 + k, l)] * s.bred[15 * f + k];
                 q += 2.0 * vl * wv + P.h_ll[l] * vl * vl;
             }
             uHu = block_sum(q, s);

@@ -46,7 +46,13 @@ struct KProf {
 
 // Address-space facts the compiler cannot see once a function is not inlined into the kernel (the large-window instance):
 // without them every access through `s` or H becomes a generic LD.E / ST.E / CAS-loop atomic.
-#ifndef CUEMU
+#if defined(XRVIO_DEBUG_ASSUME) && !defined(CUEMU)
+// diagnostic build (XRVIO_DEBUG_ASSUME=1 python xrslam_b200/build.py --force): the assumptions become device-side assertions, so a
+// wrong address space traps instead of being undefined behaviour
+#include <cassert>
+#define XV_ASSUME_SHARED(p) assert(__isShared(p))
+#define XV_ASSUME_GLOBAL(p) assert(__isGlobal(p))
+#elif !defined(CUEMU)
 #define XV_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 #define XV_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
 #else
@@ -178,9 +184,20 @@ struct Prob {
     // J^T J by groups (sliding-window instance): the weighted Jacobian rows of every reprojection residual, transposed
     // ([26][NJ]: Jt row 0, Jr row 0, Jt row 1, Jr row 1 (6 each), r0, r1), and the runs of equal (target, reference) in the sorted list
     double *JB; int *grp_start; int n_grp, NJ;
-    int Wp;                        // row pitch of W in doubles: M rounded up to 32, so that every row (and every 32-landmark tile of
-                                   // it) starts on a 256-byte boundary -- what the bulk-copy staging of solve_large.cuh needs
+    // W = H_pl (pose rows x landmarks) is stored TILE-MAJOR: tile t holds the landmarks [t 2^W_sh, (t + 1) 2^W_sh) of all W_rows pose
+    // rows, rows W_pitch doubles apart (the padding the shared-memory copy of a tile needs against bank conflicts) -- so a whole tile is
+    // ONE contiguous cp.async.bulk in the tensor-pipe Schur complement (solve_large.cuh; one copy per row made the copy engine the
+    // bottleneck: 181 issues per tile).  Wp = M rounded up to 32 landmarks; widx() is the only place that knows the layout.
+    int Wp, W_sh, W_pitch, W_rows;
 };
+
+template <bool SHARED> struct WLayout { static constexpr int sh = SHARED ? 4 : 5, pitch = SHARED ? 20 : 36; };   // = WStageT<...>::kL / kPitch
+__device__ __forceinline__ size_t widx(const Prob &P, int row, int l) {
+    return ((size_t)(l >> P.W_sh) * P.W_rows + row) * P.W_pitch + (l & ((1 << P.W_sh) - 1));
+}
+__host__ __device__ constexpr size_t w_doubles(int n_active, size_t Wp, bool shared) {      // storage of W incl. the row padding
+    return (size_t)n_active * 6 * (shared ? Wp / 16 * 20 : Wp / 32 * 36);
+}
 
 // One-time per-problem precomputation: tangent bases of all reprojection observations.
 static __device__ void prepare_tangents(Prob &P, double *tb) {
@@ -405,7 +422,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
         for (int i = tid; i < SM::HP; i += ST) s.H[i] = 0.0;
         for (int i = tid; i < SM::NPv; i += ST) s.g[i] = 0.0;
         for (int i = tid; i < M; i += ST) { P.h_ll[i] = 0.0; P.g_l[i] = 0.0; }
-        const int nw = P.d.n_active * 6 * P.Wp;          // including the padding columns: they enter the tensor-pipe tiles
+        const int nw = (int)w_doubles(P.d.n_active, P.Wp, SM::kSharedH);      // including the padding: it enters the tensor-pipe tiles
         for (int i = tid; i < nw; i += ST) P.W[i] = 0.0;
     }
     __syncthreads();
@@ -541,9 +558,9 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
                     atomicAdd(&P.h_ll[lm], e.Jl[0] * e.Jl[0] + e.Jl[1] * e.Jl[1]);
                     atomicAdd(&P.g_l[lm], e.Jl[0] * e.r[0] + e.Jl[1] * e.r[1]);
                     if (tf)
-                        for (int k = 0; k < 6; ++k) P.W[(size_t)(ts * 6 + k) * P.Wp + lm] = e.Jl[0] * e.Jt[k] + e.Jl[1] * e.Jt[6 + k];
+                        for (int k = 0; k < 6; ++k) P.W[widx(P, ts * 6 + k, lm)] = e.Jl[0] * e.Jt[k] + e.Jl[1] * e.Jt[6 + k];
                     if (rf)
-                        for (int k = 0; k < 6; ++k) atomicAdd(&P.W[(size_t)(rs * 6 + k) * P.Wp + lm], e.Jl[0] * e.Jr[k] + e.Jl[1] * e.Jr[6 + k]);
+                        for (int k = 0; k < 6; ++k) atomicAdd(&P.W[widx(P, rs * 6 + k, lm)], e.Jl[0] * e.Jr[k] + e.Jl[1] * e.Jr[6 + k]);
                 }
             }
             continue;
@@ -610,9 +627,9 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
                 atomicAdd(&P.h_ll[lm], e.Jl[0] * e.Jl[0] + e.Jl[1] * e.Jl[1]);
                 atomicAdd(&P.g_l[lm], e.Jl[0] * e.r[0] + e.Jl[1] * e.r[1]);
                 if (tf)
-                    for (int k = 0; k < 6; ++k) P.W[(size_t)(ts * 6 + k) * P.Wp + lm] = e.Jl[0] * e.Jt[k] + e.Jl[1] * e.Jt[6 + k];
+                    for (int k = 0; k < 6; ++k) P.W[widx(P, ts * 6 + k, lm)] = e.Jl[0] * e.Jt[k] + e.Jl[1] * e.Jt[6 + k];
                 if (rf)
-                    for (int k = 0; k < 6; ++k) atomicAdd(&P.W[(size_t)(rs * 6 + k) * P.Wp + lm], e.Jl[0] * e.Jr[k] + e.Jl[1] * e.Jr[6 + k]);
+                    for (int k = 0; k < 6; ++k) atomicAdd(&P.W[widx(P, rs * 6 + k, lm)], e.Jl[0] * e.Jr[k] + e.Jl[1] * e.Jr[6 + k]);
             }
         }
     }
@@ -856,7 +873,7 @@ template <class SM> static __device__ void schur_landmarks(const Prob &P, SM &s,
                 if (!isfinite(ih)) ih = 0.0;
                 double wa[6], wb[6];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) { wa[k] = P.W[(size_t)(a * 6 + k) * P.Wp + l]; wb[k] = P.W[(size_t)(b * 6 + k) * P.Wp + l] * ih; }
+                for (int k = 0; k < 6; ++k) { wa[k] = P.W[widx(P, a * 6 + k, l)]; wb[k] = P.W[widx(P, b * 6 + k, l)] * ih; }
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -881,7 +898,7 @@ template <class SM> static __device__ void schur_landmarks(const Prob &P, SM &s,
             const int a = c / 6, k = c % 6;
             if (!s.pose_free[a]) continue;
             double v = 0.0;
-            for (int l = lane; l < M; l += 32) { double ih = 1.0 / P.ht_l[l]; if (!isfinite(ih)) ih = 0.0; v += P.W[(size_t)c * P.Wp + l] * P.g_l[l] * ih; }
+            for (int l = lane; l < M; l += 32) { double ih = 1.0 / P.ht_l[l]; if (!isfinite(ih)) ih = 0.0; v += P.W[widx(P, c, l)] * P.g_l[l] * ih; }
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) rhs[15 * a + k] -= v;
         }

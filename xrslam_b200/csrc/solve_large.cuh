@@ -60,20 +60,21 @@ __device__ __forceinline__ void xv_mbar_wait(unsigned long long *bar, unsigned p
 #endif
 
 // warp 0: start the copy of the tile of landmarks [l0, l0 + 32) into buffer `buf`
-template <class WS> __device__ __forceinline__ void wstage_issue(WS &ws, int buf, const double *W, int Wp, const double *ihv, int R, int l0, int lane) {
-    constexpr int TL = WS::kL;
+// (W is stored tile-major with the stage's row pitch, solve_core.cuh: the tile is one contiguous block of R * kPitch doubles)
+template <class WS> __device__ __forceinline__ void wstage_issue(WS &ws, int buf, const double *W, const double *ihv, int R, int tile, int lane) {
+    constexpr int TL = WS::kL, PITCH = WS::kPitch;
+    const double *src = W + (size_t)tile * R * PITCH;
 #ifndef CUEMU
     if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        xv_mbar_expect_tx(&ws.bar[buf], (unsigned)((R + 1) * TL * sizeof(double)));
+        const unsigned wb = (unsigned)(R * PITCH * sizeof(double)), ib = (unsigned)(TL * sizeof(double));
+        xv_mbar_expect_tx(&ws.bar[buf], wb + ib);
+        xv_bulk_g2s(&ws.w[buf][0][0], src, wb, &ws.bar[buf]);
+        xv_bulk_g2s(&ws.ih[buf][0], ihv + (size_t)tile * TL, ib, &ws.bar[buf]);
     }
-    __syncwarp();
-    for (int r = lane; r < R; r += 32) xv_bulk_g2s(&ws.w[buf][r][0], W + (size_t)r * Wp + l0, TL * sizeof(double), &ws.bar[buf]);
-    if (lane == 0) xv_bulk_g2s(&ws.ih[buf][0], ihv + l0, TL * sizeof(double), &ws.bar[buf]);
 #else
-    for (int r = lane; r < R; r += 32)
-        for (int k = 0; k < TL; ++k) ws.w[buf][r][k] = W[(size_t)r * Wp + l0 + k];
-    if (lane < TL) ws.ih[buf][lane] = ihv[l0 + lane];
+    for (int e = lane; e < R * PITCH; e += 32) (&ws.w[buf][0][0])[e] = src[e];
+    if (lane < TL) ws.ih[buf][lane] = ihv[(size_t)tile * TL + lane];
 #endif
 }
 
@@ -120,10 +121,10 @@ template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM
 #pragma unroll
             for (int e = 0; e < 8; ++e) (&acc[q][0][0][0])[e] = 0.0;
         }
-        if (warp == 0) wstage_issue(ws, 0, P.W, Wp, ihv, R, 0, lane);
+        if (warp == 0) wstage_issue(ws, 0, P.W, ihv, R, 0, lane);
         for (int k = 0; k < T; ++k) {
             const int buf = k & 1;
-            if (warp == 0 && k + 1 < T) wstage_issue(ws, buf ^ 1, P.W, Wp, ihv, R, (k + 1) * WT_L, lane);     // its readers passed the barrier below
+            if (warp == 0 && k + 1 < T) wstage_issue(ws, buf ^ 1, P.W, ihv, R, k + 1, lane);     // its readers passed the barrier below
 #ifndef CUEMU
             xv_mbar_wait(&ws.bar[buf], (buf ? uses1 : uses0) & 1u);
 #else
@@ -173,7 +174,7 @@ template <class SM> static __device__ void schur_landmarks_mma(const Prob &P, SM
         const int a = c / 6, k = c % 6;
         if (!s.pose_free[a]) continue;
         double v = 0.0;
-        for (int l = lane; l < M; l += 32) v += P.W[(size_t)c * Wp + l] * P.g_l[l] * ihv[l];
+        for (int l = lane; l < M; l += 32) v += P.W[widx(P, c, l)] * P.g_l[l] * ihv[l];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) rhs[15 * a + k] -= v;
     }
