@@ -343,7 +343,7 @@ def run_cuda_arm(args, rank, world, local_rank):
                 # the path moves 2.57 MB per frame: it is latency / FP64-issue bound, not bandwidth bound -- the HBM fraction is reported
                 # because the contract asks for it, the pipe utilisations of the same capture say where the kernel really stands
                 'fp64_pipe_pct': pe.get('fp64_pipe_pct'), 'dmma_pipe_pct': pe.get('dmma_pipe_pct'), 'issue_active_pct': pe.get('issue_active_pct'),
-                'family_ms_note': 'CUDA-event time per kernel family summed over the 8 lanes\' streams, which overlap: the sum exceeds the step time',
+                'family_ms_note': 'CUDA-event time per kernel family summed over the lanes\' streams, which overlap: the sum exceeds the step time',
                 'family_ms': {k: round(v[0], 3) for k, v in kt.items()}}
     out = {
         'metric': 'VIO frames/sec (batched streams)', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': K,

@@ -16,7 +16,7 @@ for s in barrier long_scoreboard short_scoreboard wait math_pipe_throttle mio_th
 done
 mkdir -p gpurun_out
 export XRVIO_BENCH_PRIME=100
-timeout 600 ncu --metrics "$M" --clock-control none --kernel-name "$KREGEX" --launch-skip 15500 -c 200 -o /tmp/${TAG}_full \
+timeout 600 ncu --metrics "$M" --clock-control none --kernel-name "$KREGEX" --launch-skip 9000 -c 400 -o /tmp/${TAG}_full \
     python bench.py --steps 10 --warmup 3 --no-cpu-baseline --sync-steps --dev-only > /tmp/under_ncu2.log 2>&1
 ncu -i /tmp/${TAG}_full.ncu-rep --page raw --csv 2>/dev/null | gzip > gpurun_out/${TAG}_full_raw.csv.gz
 timeout 420 ncu --set full --clock-control none --import-source on --kernel-name regex:solve_kernel --launch-skip 1400 -c 2 -o gpurun_out/${TAG}_solve_src \
