@@ -110,8 +110,10 @@ XV_HD void put3x3(double *J, int r0, int c0, const M3 &A) {   // J is 15x15 row-
 // preintegration_factor.h:20-159.  si / sj: 16-double states (candidate values); bias0: frame_i's
 // bg (3) and ba (3) in user memory (the D10 quirk, :38-39).  r: UNWHITENED residual (15);
 // Ji / Jj: UNWHITENED 15x15 Jacobians in error-state order (caller multiplies by sqrt_inv_cov).
+// part: -1 everything; 0 / 1 / 2 only the rotation / position / velocity (+ bias) rows of the residual (cost-only evaluations
+// spread the three independent chains of a factor over three lanes; each row is computed by exactly the same operations)
 __host__ __device__ inline void pre_eval(const double *si, const double *sj, const double *bias0, const double *pb,
-                                const RigParams &rg, bool want_jac, double *r, double *Ji, double *Jj) {
+                                const RigParams &rg, bool want_jac, double *r, double *Ji, double *Jj, int part = -1) {
     const V3 gravity = v3(0.0, 0.0, -9.80665);
     const Q4 q_ci = ld4(si), q_cj = ld4(sj);
     const V3 p_ci = ld3(si + 4), v_i = ld3(si + 7), bg_i = ld3(si + 10), ba_i = ld3(si + 13);
@@ -130,6 +132,13 @@ __host__ __device__ inline void pre_eval(const double *si, const double *sj, con
         dv_dbg.m[k] = pb[PB_DV_DBG + k]; dv_dba.m[k] = pb[PB_DV_DBA + k];
     }
     const V3 th = dq_dbg * dbg;
+    if (part == 0) { st3(r, logmap(qmul(qmul(qconj(qmul(dq, expmap(th))), qconj(q_i)), q_j))); return; }
+    if (part == 1) { st3(r + 3, qrot(qconj(q_i), p_j - p_i - dt * v_i - (0.5 * dt * dt) * gravity) - (dp + dp_dbg * dbg + dp_dba * dba)); return; }
+    if (part == 2) {
+        st3(r + 6, qrot(qconj(q_i), v_j - v_i - dt * gravity) - (dv + dv_dbg * dbg + dv_dba * dba));
+        st3(r + 9, bg_j - bg_i); st3(r + 12, ba_j - ba_i);
+        return;
+    }
     const V3 rq = logmap(qmul(qmul(qconj(qmul(dq, expmap(th))), qconj(q_i)), q_j));
     const V3 rp = qrot(qconj(q_i), p_j - p_i - dt * v_i - (0.5 * dt * dt) * gravity) - (dp + dp_dbg * dbg + dp_dba * dba);
     const V3 rv = qrot(qconj(q_i), v_j - v_i - dt * gravity) - (dv + dv_dbg * dbg + dv_dba * dba);

@@ -328,13 +328,15 @@ template <class SM> static __device__ double evaluate_cost(const Prob &P, SM &s,
     const int n_rw = NW - (has_pre ? 1 : 0);          // warps 0 .. n_rw - 1 take the reprojection residuals
     double cost = 0.0;
     if (warp == w_pre) {
-        for (int f = lane; f < P.d.n_pre; f += 32) {
+        // three lanes per factor: the rotation, position and velocity rows are independent chains
+        for (int t = lane; t < 3 * P.d.n_pre; t += 32) {
+            const int f = t / 3;
             const PreRef pf = P.pre[P.d.pre_off + f];
             const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
             double *sc = P.pre_s + (size_t)f * kPreScratch;
             const double *si = pf.prior ? (s.us + pf.i * 16) : (S + pf.i * 16);
             const double *sj = S + pf.j * 16;
-            pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, false, sc, sc + 16, sc + 241);
+            pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, false, sc, sc + 16, sc + 241, t % 3);
         }
         __syncwarp();
         for (int e = lane; e < 15 * P.d.n_pre; e += 32) {          // whitened residual, one lane per row
