@@ -103,3 +103,35 @@ def test_session_api_error_paths(xrvio):
     bad['distortion_model'] = 7
     with pytest.raises(capi.XrvioError):
         capi.Context(bad, 1)
+
+
+def test_uninitialised_front_end_map_is_capped(xrvio):
+    """Before initialisation latest_optimized_frame_id is nil() == SIZE_MAX, so FeatureTracker::work trims the front-end map to
+    feature_tracker.max_init_frames = 60 (feature_tracker.cpp:46,132-135; ADVICE r1: the trim used to be gated on "initialised").
+    A session that is never initialised (no bootstrap states, initializer off) must stop growing: no track can be longer than
+    60 frames, and the oracle's map holds exactly 60 frames."""
+    from oracle.synth import Stream
+    from oracle.pipeline import Session, Config
+    from oracle import drive
+    s = Stream(3)
+    n = 72
+    p = drive.params_for(s)
+    p['initializer'] = 0
+    ctx = xrvio.Context(p, 1)
+    ctx, outs = drive.run_streams_cuda([s], n, ctx=ctx, bootstrap=False)
+    assert ctx.get_state(0) == 0 and len(outs[0]) == 0
+    xy, tid, tl = ctx.get_features(0)
+    assert len(tl) > 30 and 50 <= int(tl.max()) <= 60, int(tl.max())
+    ctx.close()
+    sess = Session(Config(s.w, s.h, s.K), gt_fn=None)
+    sess.initialize = lambda init_frame_id: None            # same switch as params['initializer'] = 0
+    imu = s.imu(n * s.imu_per_cam + 2)
+    k_imu = 0
+    for k in range(n):
+        t_img = s.frame_time(k)
+        while k_imu < len(imu) and imu[k_imu, 0] <= t_img + 1e-9:
+            sess.track_imu(imu[k_imu, 0], imu[k_imu, 1:4], imu[k_imu, 4:7]); k_imu += 1
+        sess.track_camera(t_img, s.frame(k))
+    assert sess.swt is None and sess.ft_map.frame_num() == 60
+    lens = [len(tr.refs) for tr in sess.ft_map.tracks]
+    assert max(lens) == int(tl.max())
