@@ -9,31 +9,64 @@ using namespace xv;
 size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k, int n_rpe) {
     size_t M = (size_t)((n_lm_free + 31) / 32) * 32 + 32;
     size_t n = (size_t)15 * marg_k;
-    return 8 * M + (size_t)n_active * 6 * (M + M / 4) + HPACK + (size_t)n_pre * kPreScratch + 4 * (n + 32) + 2 * n * n + 64 + (size_t)6 * n_rpe + 2 * M + jb_doubles(n_rpe);
+    return 8 * M + (size_t)n_active * 6 * (M + M / 4) + HPACK + (size_t)n_pre * kPreScratch + 4 * (n + 32) + 2 * n * n + 64 + (size_t)6 * n_rpe + 2 * M + jb_doubles(n_rpe)
+           + kSpec * M + (size_t)16 * n_pre * kSpec;      // inverse depths / preintegration residuals of the speculative candidates
 }
 
 
-// q <- normalize(q * exp(d)) for free pose blocks, additive elsewhere (quaternion_parameterization.h:11-17)
-template <class SM> __device__ void make_candidate(const Prob &P, SM &s, double c1, double c2) {
+// Candidates b = 0 .. nb-1 of a batch (evaluate_cost_multi): q <- normalize(q * exp(d)) for free pose blocks, additive elsewhere
+// (quaternion_parameterization.h:11-17), with delta_j = c1 du_j + c2 dw_j, du = -gs / D^2 * scale, dw = -y * scale (prepared per
+// linearisation) and (c1, c2) of candidate b in s.sp.  s.red4[(kSpec + b) * NW + warp] receives the warp's part of
+// |x - candidate_b|^2 over the free blocks (ParameterToleranceReached), summed with the costs in evaluate_cost_multi.
+template <class SM> __device__ void make_candidates(const Prob &P, SM &s, int nb) {
     XV_ASSUME_SHARED(&s);
     const int tid = threadIdx.x;
-    // delta_j = c1 * du_j + c2 * dw_j with du = -gs / D^2 * scale, dw = -y * scale (prepared per linearisation)
-    for (int f = tid; f < P.d.n_frames; f += ST) {
-        double *c = s.cs + f * 16;
+    double ss[kSpec];
+#pragma unroll
+    for (int k = 0; k < kSpec; ++k) ss[k] = 0.0;
+    const int nf0 = P.d.n_frames, na = P.d.n_active;
+    for (int t = tid; t < nf0 + (nb - 1) * na; t += ST) {
+        const int b = t < nf0 ? 0 : 1 + (t - nf0) / na;
+        const int f = t < nf0 ? t : (t - nf0) % na;
+        const double c1 = s.sp[b * 8 + 1], c2 = s.sp[b * 8 + 2];
+        double *c = cand_frame_w(s, b, f);
         const double *x = s.xs + f * 16;
         for (int k = 0; k < 16; ++k) c[k] = x[k];
-        if (f < P.d.n_active) {
+        if (f < na) {
             double dl[15];
             for (int k = 0; k < 15; ++k) { const int j = 15 * f + k; dl[k] = c1 * s.du[j] + c2 * s.dw[j]; }
+            double a = 0.0;
             if (s.pose_free[f]) {
                 st4(c, qnormalized(qmul(ld4(x), expmap(v3(dl[0], dl[1], dl[2])))));
                 for (int k = 0; k < 3; ++k) c[4 + k] = x[4 + k] + dl[3 + k];
+                for (int k = 0; k < 7; ++k) { const double d = x[k] - c[k]; a += d * d; }
             }
-            if (s.motion_free[f])
+            if (s.motion_free[f]) {
                 for (int k = 0; k < 9; ++k) c[7 + k] = x[7 + k] + dl[6 + k];
+                for (int k = 7; k < 16; ++k) { const double d = x[k] - c[k]; a += d * d; }
+            }
+#pragma unroll
+            for (int k = 0; k < kSpec; ++k) if (k == b) ss[k] += a;
         }
     }
-    for (int l = tid; l < P.M; l += ST) P.inv_c[l] = P.inv_x[l] + (c1 * P.du_l[l] + c2 * P.dw_l[l]);
+    for (int l = tid; l < P.M; l += ST) {
+        const double x = P.inv_x[l], du = P.du_l[l], dw = P.dw_l[l];
+#pragma unroll
+        for (int b = 0; b < kSpec; ++b) {
+            if (b >= nb) continue;
+            const double c = x + (s.sp[b * 8 + 1] * du + s.sp[b * 8 + 2] * dw);
+            P.inv_c[(size_t)b * P.Mp + l] = c;
+            const double d = x - c;
+            ss[b] += d * d;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < kSpec; ++b) {
+        if (b >= nb) continue;
+        double v = ss[b];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) s.red4[(kSpec + b) * NW + (tid >> 5)] = v;
+    }
     __syncthreads();
 }
 
@@ -340,6 +373,9 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
         prepare_prior(P, m, sc); sc += n * n;
         prepare_tangents(P, sc); sc += (size_t)6 * P.d.n_rpe;
         P.du_l = sc; sc += Mp; P.dw_l = sc; sc += Mp;
+        P.Mp = Mp;
+        P.inv_c = sc; sc += kSpec * Mp;                                  // the candidates' inverse depths, Mp apart
+        P.pre_r = sc; sc += (size_t)16 * P.d.n_pre * kSpec;
         P.JB = nullptr; P.grp_start = nullptr; P.n_grp = 0; P.NJ = 0;
         if constexpr (SM::kSharedH) prepare_groups(P, s, sc);
     }
@@ -411,6 +447,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
     int iteration = 0, termination = -1, n_succ = 0, n_unsucc = 0, n_invalid = 0, n_rec = 0;
     bool it_success = true;
     double it_cost = x_cost;
+    int spec_k = 0, spec_n = 0, spec_last = 1;      // candidate batch: next slot to consume, slots filled, size of the last batch
     if (tid == 0) { out.initial_cost = x_cost; }
 
     while (true) {
@@ -434,8 +471,10 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
         it_success = false;
         // ---- DoglegStrategy::ComputeStep ----
         bool solver_failed = false;
+        const bool fresh = !reuse;
         if (!reuse) {
             reuse = true;
+            spec_n = 0;                                             // candidates of the previous linearisation are void
             // diagonal = sqrt(clamp(diag(Js^T Js)))
             for (int c = tid; c < P.NPc; c += ST)
                 s.D[c] = s.col_free[c] ? sqrt(fmin(fmax(s.H[hidx(c, c)], kMinDiag), kMaxDiag)) : 1.0;
@@ -497,29 +536,59 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
                 (void)t3;
             }
         }
-        double c1 = 0.0, c2 = 0.0, model_cost_change = 0.0;
+        double model_cost_change = 0.0, cand_cost = 0.0, step_norm = 0.0;
         bool step_valid = false;
         if (!solver_failed) {
-            // ComputeTraditionalDoglegStep
-            const double gnorm = sqrt(gnorm2), gn_norm = sqrt(gn_norm2);
-            if (gn_norm <= radius) { c1 = 0.0; c2 = 1.0; dogleg_step_norm = gn_norm; }
-            else if (gnorm * alpha >= radius) { c1 = radius / gnorm; c2 = 0.0; dogleg_step_norm = radius; }
-            else {
-                const double b_dot_a = -alpha * grad_dot_gn;
-                const double a_sq = (alpha * gnorm) * (alpha * gnorm);
-                const double bma_sq = a_sq - 2.0 * b_dot_a + gn_norm2;
-                const double c = b_dot_a - a_sq;
-                const double d = sqrt(c * c + bma_sq * (radius * radius - a_sq));
-                const double beta = (c <= 0) ? (d - c) / bma_sq : (radius * radius - a_sq) / (d + c);
-                c1 = alpha * (1.0 - beta); c2 = beta;
-                dogleg_step_norm = sqrt(fmax(c1 * c1 * gnorm2 - 2.0 * c1 * c2 * grad_dot_gn + c2 * c2 * gn_norm2, 0.0));
+            if (!(spec_k < spec_n && s.sp[spec_k * 8] == radius)) {
+                // ---- a new batch of candidates: this radius and, speculatively, the radii of the next rejections ----
+                int nb = fresh ? 1 : min(kSpec, 2 * spec_last);    // a step right after a new linearisation is usually accepted
+                nb = min(nb, P.d.max_iterations - iteration + 1);
+                spec_last = nb;
+                __syncthreads();                                    // every thread is done with the previous batch's slots
+                if ((tid >> 5) < nb) {
+                    // ComputeTraditionalDoglegStep for candidate b on warp b, side by side
+                    const int b = tid >> 5;
+                    double rad = radius;
+                    for (int k = 0; k < b; ++k) rad *= 0.5;
+                    double c1, c2, norm;
+                    const double gnorm = sqrt(gnorm2), gn_norm = sqrt(gn_norm2);
+                    if (gn_norm <= rad) { c1 = 0.0; c2 = 1.0; norm = gn_norm; }
+                    else if (gnorm * alpha >= rad) { c1 = rad / gnorm; c2 = 0.0; norm = rad; }
+                    else {
+                        const double b_dot_a = -alpha * grad_dot_gn;
+                        const double a_sq = (alpha * gnorm) * (alpha * gnorm);
+                        const double bma_sq = a_sq - 2.0 * b_dot_a + gn_norm2;
+                        const double c = b_dot_a - a_sq;
+                        const double d = sqrt(c * c + bma_sq * (rad * rad - a_sq));
+                        const double beta = (c <= 0) ? (d - c) / bma_sq : (rad * rad - a_sq) / (d + c);
+                        c1 = alpha * (1.0 - beta); c2 = beta;
+                        norm = sqrt(fmax(c1 * c1 * gnorm2 - 2.0 * c1 * c2 * grad_dot_gn + c2 * c2 * gn_norm2, 0.0));
+                    }
+                    // step = c1 u + c2 w (Jacobi-scaled space), u = -gs/D^2, w = -y, Hs w = -gs + mu D^2 y
+                    const double u_g = -gnorm2, w_g = -gsy;
+                    const double uHw = gnorm2 - mu * gsy;
+                    const double wHw = gsy - mu * D2y2;
+                    const double mcc = -(c1 * u_g + c2 * w_g) - 0.5 * (c1 * c1 * uHu + 2.0 * c1 * c2 * uHw + c2 * c2 * wHw);
+                    if ((tid & 31) == 0) {
+                        double *sp = s.sp + b * 8;
+                        sp[0] = rad; sp[1] = c1; sp[2] = c2; sp[3] = norm; sp[4] = mcc; sp[5] = (mcc > 0.0) ? 1.0 : 0.0;
+                    }
+                }
+                __syncthreads();
+                int nbv = 0;
+                while (nbv < nb && s.sp[nbv * 8 + 5] != 0.0) ++nbv;  // an invalid step ends the run of rejections (HandleInvalidStep)
+                kp.mark(20);
+                if (nbv > 0) {
+                    make_candidates(P, s, nbv);
+                    kp.mark(17);
+                    evaluate_cost_multi(P, s, nbv, rg, true);           // -> s.sp[b * 8 + 6 .. 7]
+                    kp.mark(9);
+                }
+                spec_k = 0; spec_n = max(nbv, 1);
             }
-            // step = c1 u + c2 w (Jacobi-scaled space), u = -gs/D^2, w = -y, Hs w = -gs + mu D^2 y
-            const double u_g = -gnorm2, w_g = -gsy;
-            const double uHw = gnorm2 - mu * gsy;
-            const double wHw = gsy - mu * D2y2;
-            model_cost_change = -(c1 * u_g + c2 * w_g) - 0.5 * (c1 * c1 * uHu + 2.0 * c1 * c2 * uHw + c2 * c2 * wHw);
-            step_valid = model_cost_change > 0.0;
+            const double *sp = s.sp + spec_k * 8;
+            dogleg_step_norm = sp[3]; model_cost_change = sp[4]; step_valid = sp[5] != 0.0;
+            cand_cost = sp[6]; step_norm = sqrt(sp[7]);
         }
         if (!step_valid) {
             n_invalid++;
@@ -531,23 +600,18 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
             continue;
         }
         n_invalid = 0;
-        kp.mark(20);
-        make_candidate(P, s, c1, c2);
-        kp.mark(17);
-        double cand_cost = evaluate(P, s, s.cs, P.inv_c, rg, false, true, &kp);
         // a failed evaluation leaves candidate_cost = DBL_MAX (ComputeCandidatePointAndEvaluateCost): the step is rejected and
         // the radius halved; it must not look like "function tolerance reached"
         if (!isfinite(cand_cost)) cand_cost = DBL_MAX;
-        const double step_norm = sqrt(ambient_sq(P, s, s.xs, s.cs, P.inv_x, P.inv_c));
-        kp.mark(21);
         if (step_norm <= kParamTol * (x_norm + kParamTol)) { termination = 4; if (tid == 0 && n_rec < kMaxIter) out.cost_trace[n_rec] = it_cost; n_rec++; break; }
         const double cost_change = x_cost - cand_cost;
         if (fabs(cost_change) <= kFuncTol * x_cost) { termination = 5; if (tid == 0 && n_rec < kMaxIter) out.cost_trace[n_rec] = it_cost; n_rec++; break; }
         const double rel = cost_change / model_cost_change;
         if (rel > kMinRelDecrease) {
             // HandleSuccessfulStep: user memory still holds the previous iterate here (D10)
-            for (int i = tid; i < P.d.n_frames * 16; i += ST) s.xs[i] = s.cs[i];
-            for (int l = tid; l < P.M; l += ST) P.inv_x[l] = P.inv_c[l];
+            // (frames beyond the active ones are constant: equal in every candidate)
+            for (int i = tid; i < P.d.n_active * 16; i += ST) s.xs[i] = cand_frame(s, spec_k, i >> 4, P.d.n_active)[i & 15];
+            for (int l = tid; l < P.M; l += ST) P.inv_x[l] = P.inv_c[(size_t)spec_k * P.Mp + l];
             __syncthreads();
             x_norm = sqrt(ambient_sq(P, s, s.xs, nullptr, P.inv_x, nullptr));
             x_cost = evaluate(P, s, s.xs, P.inv_x, rg, true, true, &kp);
@@ -571,6 +635,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
             it_cost = cand_cost;
             radius *= 0.5;
             reuse = true;
+            spec_k++;                                               // the next candidate of the batch, if any, is this radius
         }
     }
     if (tid == 0) {

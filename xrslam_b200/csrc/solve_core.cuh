@@ -17,6 +17,7 @@ constexpr int ST = 512;                    // threads per CTA
 constexpr int NW = ST / 32;
 constexpr int HPACK = kNP * (kNP + 1) / 2;          // sliding-window instance (Smem)
 constexpr int kPreScratch = 1024;          // doubles of scratch per preintegration factor
+constexpr int kSpec = 4;                   // candidates of consecutive rejected steps evaluated in one pass (evaluate_cost_multi)
 
 // Ceres 1.14 Solver::Options defaults (Appendix C of SURVEY.md)
 constexpr double kInitialRadius = 1e4, kMinRadius = 1e-32, kMinRelDecrease = 1e-3;
@@ -86,6 +87,7 @@ template <int KA, bool SHARED> struct SmemT {
     HStore<HP, SHARED> H;                  // packed lower-triangular, row i at i(i+1)/2
     double xs[kMaxFrames * 16];            // current iterate
     double cs[kMaxFrames * 16];            // candidate
+    double csx[(kSpec - 1) * KA * 16];     // active frames of the speculative candidates 1 .. kSpec-1 (their constant frames are those of xs)
     double us[kMaxFrames * 16];            // user memory (last state written back)
     double g[NPv], scale[NPv], D[NPv], y[NPv], bred[NPv];
     double du[NPv], dw[NPv];               // unscaled steepest-descent / Gauss-Newton directions of the current linearisation
@@ -93,6 +95,8 @@ template <int KA, bool SHARED> struct SmemT {
     double linv[SHARED ? (NPv / 6) * 36 : 1];   // inverses of the 6 x 6 diagonal blocks of L (sliding-window instance: the substitutions
                                            // multiply by them instead of solving each triangle on one thread)
     double red[NW];
+    double red4[2 * kSpec * NW];           // partial sums of evaluate_cost_multi
+    double sp[kSpec * 8];                  // per candidate of a batch: radius, c1, c2, step norm, model cost change, valid, cost, |dx|^2
     double jrinv[KA * 9];
     unsigned char col_free[NPv];
     unsigned char pose_free[KA], motion_free[KA];
@@ -179,7 +183,8 @@ struct Prob {
     double *marg_St;               // transposed copy of the non-zero rows of S (scratch), St[c * rank + r]
     int marg_n, marg_rank;
     // scratch (global)
-    double *inv_x, *inv_c, *h_ll, *g_l, *sc_l, *D_l, *y_l, *ht_l, *W, *Hcopy, *pre_s, *m_dx, *m_r, *m_v, *m_T, *du_l, *dw_l;
+    double *inv_x, *inv_c, *h_ll, *g_l, *sc_l, *D_l, *y_l, *ht_l, *W, *Hcopy, *pre_s, *m_dx, *m_r, *m_v, *m_T, *du_l, *dw_l, *pre_r;
+    size_t Mp;                     // doubles between the inverse-depth arrays of consecutive candidates (P.inv_c + b * Mp)
     int M, NPc;                    // free landmarks, pose/motion columns = 15 * n_active
     // J^T J by groups (sliding-window instance): the weighted Jacobian rows of every reprojection residual, transposed
     // ([26][NJ]: Jt row 0, Jr row 0, Jt row 1, Jr row 1 (6 each), r0, r1), and the runs of equal (target, reference) in the sorted list
@@ -313,47 +318,76 @@ template <class SM> __device__ __forceinline__ void jtj_uniform_warp(SM &s, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cost-only evaluation (29 of the 31 evaluations of a window BA).  The preintegration factors are a serial
-// chain of ~10 k cycles per factor on ONE lane each; they get the last warp to themselves and run UNDER the reprojection
-// residuals of the other warps instead of after them.  The prior's S dx + infovec is memory-latency bound (S^T comes from L2),
-// it needs every thread to have enough loads in flight: it follows the barrier, 4 lanes per row.  (Giving the prior one warp
-// of its own measured 2.2x slower per evaluation on a B200 -- five serial rounds of 135-long L2-latency-bound dot products.)
-// Same arithmetic per residual as evaluate(..., want_jac = false); only the order in which the partial costs are summed differs.
+// Cost-only evaluation of up to kSpec candidates at once (29 of the 31 evaluations of a window BA).
+// After a rejected step Ceres keeps the linearisation and only halves the radius, and a rejection changes neither the iterate nor
+// user memory: the candidates of the next rejections are known in advance (radius / 2, / 4, ...).  The loop in backend_solve.cu
+// evaluates a batch of them in one pass and consumes the results one iteration at a time, in order, with the unchanged accept /
+// reject / tolerance logic -- a candidate behind an accepted one is simply never looked at.  One pass over b candidates costs far
+// less than b passes: an observation is loaded once, the serial sections (dogleg scalars, candidate update, reductions, the
+// preintegration chains) run side by side, and the prior's S^T is read once for all of them.
+//   candidate b: frames cand_frame(s, b, f), inverse depths P.inv_c + b * P.Mp, frame errors of the prior P.m_dx + b * (marg_n + 32)
+//   (m_r / m_v / the spare row are free outside the Jacobian evaluation), preintegration residuals P.pre_r + (b * n_pre + f) * 16.
+// Warp roles: the last nb warps take the preintegration factors of one candidate each (three lanes per factor: the rotation,
+// position and velocity rows are independent serial chains), the others the reprojection and rotation residuals; warps 0 .. nb-1
+// first compute the prior's frame errors.  The prior's S dx + infovec follows the barrier, 4 lanes per row.  (Giving the prior
+// one warp of its own measured 2.2x slower -- five serial rounds of 135-long L2-latency-bound dot products.)
+// Results: s.sp[b * 8 + 6] = cost of candidate b, s.sp[b * 8 + 7] = |x - candidate_b|^2 (its warp sums come from make_candidates
+// in s.red4).  Same arithmetic per residual as evaluate(..., want_jac = true) computes.
 // ------------------------------------------------------------------------------------------------
-template <class SM> static __device__ double evaluate_cost(const Prob &P, SM &s, const double *S, const double *inv, const RigParams &rg, bool robust) {
+#ifdef CUEMU
+#define XV_NOINLINE
+#else
+#define XV_NOINLINE __noinline__          // its own register allocation: inlined into the trust-region loop it spilled 2 KB
+#endif
+template <class SM> __device__ __forceinline__ const double *cand_frame(const SM &s, int b, int f, int n_active) {
+    return b == 0 ? s.cs + f * 16 : (f < n_active ? s.csx + ((b - 1) * SM::kA + f) * 16 : s.xs + f * 16);
+}
+template <class SM> __device__ __forceinline__ double *cand_frame_w(SM &s, int b, int f) {      // f < n_active for b > 0
+    return b == 0 ? s.cs + f * 16 : s.csx + ((b - 1) * SM::kA + f) * 16;
+}
+__device__ __forceinline__ void acc_add(double (&acc)[kSpec], int b, double v) {
+#pragma unroll
+    for (int k = 0; k < kSpec; ++k) if (k == b) acc[k] += v;
+}
+
+template <class SM> static __device__ XV_NOINLINE void evaluate_cost_multi(const Prob &P, SM &s, int nb, const RigParams &rg, bool robust) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    XV_ASSUME_SHARED(&s); XV_ASSUME_SHARED(S); XV_ASSUME_GLOBAL(inv);
+    XV_ASSUME_SHARED(&s);
     const bool has_pre = P.d.n_pre > 0, has_marg = P.d.marg_k > 0;
-    const int w_pre = has_pre ? NW - 1 : -1;
-    const int n_rw = NW - (has_pre ? 1 : 0);          // warps 0 .. n_rw - 1 take the reprojection residuals
-    double cost = 0.0;
-    if (warp == w_pre) {
-        // three lanes per factor: the rotation, position and velocity rows are independent chains
+    const int na = P.d.n_active;
+    const int n_rw = NW - (has_pre ? nb : 0);         // warps 0 .. n_rw - 1 take the reprojection residuals
+    double acc[kSpec];
+#pragma unroll
+    for (int k = 0; k < kSpec; ++k) acc[k] = 0.0;
+    if (warp >= n_rw) {
+        const int b = warp - n_rw;
+        double *rb = P.pre_r + (size_t)b * P.d.n_pre * 16;
         for (int t = lane; t < 3 * P.d.n_pre; t += 32) {
             const int f = t / 3;
             const PreRef pf = P.pre[P.d.pre_off + f];
             const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
-            double *sc = P.pre_s + (size_t)f * kPreScratch;
-            const double *si = pf.prior ? (s.us + pf.i * 16) : (S + pf.i * 16);
-            const double *sj = S + pf.j * 16;
-            pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, false, sc, sc + 16, sc + 241, t % 3);
+            const double *si = pf.prior ? (s.us + pf.i * 16) : cand_frame(s, b, pf.i, na);
+            const double *sj = cand_frame(s, b, pf.j, na);
+            pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, false, rb + f * 16, nullptr, nullptr, t % 3);
         }
         __syncwarp();
+        double c = 0.0;
         for (int e = lane; e < 15 * P.d.n_pre; e += 32) {          // whitened residual, one lane per row
             const int f = e / 15, r = e % 15;
             const PreRef pf = P.pre[P.d.pre_off + f];
             const double *Sic = P.pre_blocks + (size_t)pf.block * kPreBlock + PB_SIC;
-            const double *sc = P.pre_s + (size_t)f * kPreScratch;
+            const double *sc = rb + f * 16;
             double a = 0.0;
 #pragma unroll
             for (int k = 0; k < 15; ++k) a += Sic[r * 15 + k] * sc[k];
-            cost += 0.5 * a * a;
+            c += 0.5 * a * a;
         }
+        acc_add(acc, b, c);
     } else {
-        if (has_marg && warp == 0)                                  // error of the prior frames against their linearisation points
+        if (has_marg && warp < nb)                                  // error of the prior frames against their linearisation points
             for (int k = lane; k < P.d.marg_k; k += 32) {
                 const int f = P.marg_frames[P.d.marg_frames_off + k];
-                marg_dx(S + f * 16, P.marg_lin + k * 16, P.m_dx + 15 * k, nullptr);
+                marg_dx(cand_frame(s, warp, f, na), P.marg_lin + k * 16, P.m_dx + (size_t)warp * (P.marg_n + 32) + 15 * k, nullptr);
             }
         for (int base = warp * 32; base < P.d.n_rpe; base += n_rw * 32) {
             const int o = base + lane;
@@ -361,47 +395,79 @@ template <class SM> static __device__ double evaluate_cost(const Prob &P, SM &s,
                 const RpeObs ob = P.rpe[P.d.rpe_off + o];
                 const int ts = ob.tgt, rs = ob.ref, lm = ob.lm;
                 const bool prior = ob.prior != 0;
-                const double *st = S + ts * 16;
-                const double *sr = prior ? (s.us + rs * 16) : (S + rs * 16);
-                const double idp = prior ? P.invd_user[lm] : inv[lm];
-                RpeEval e;
-                rpe_eval(ld4(st), ld3(st + 4), ld4(sr), ld3(sr + 4), idp, ld3(ob.zt), ld3(ob.zr), P.rpe_tb + (size_t)o * 6, rg, false, false, e);
-                const double sq = e.r[0] * e.r[0] + e.r[1] * e.r[1];
-                cost += robust ? 0.5 * log(1.0 + sq) : 0.5 * sq;
+                const V3 zt = ld3(ob.zt), zr = ld3(ob.zr);
+                const double *tb = P.rpe_tb + (size_t)o * 6;
+#pragma unroll 1
+                for (int b = 0; b < nb; ++b) {
+                    const double *st = cand_frame(s, b, ts, na);
+                    const double *sr = prior ? (s.us + rs * 16) : cand_frame(s, b, rs, na);
+                    const double idp = prior ? P.invd_user[lm] : P.inv_c[(size_t)b * P.Mp + lm];
+                    RpeEval e;
+                    rpe_eval(ld4(st), ld3(st + 4), ld4(sr), ld3(sr + 4), idp, zt, zr, tb, rg, false, false, e);
+                    const double sq = e.r[0] * e.r[0] + e.r[1] * e.r[1];
+                    acc_add(acc, b, robust ? 0.5 * log(1.0 + sq) : 0.5 * sq);
+                }
             }
         }
         for (int o = warp * 32 + lane; o < P.d.n_rot; o += n_rw * 32) {
             const RotObs ob = P.rot[P.d.rot_off + o];
-            double r[2], Jq[6];
-            rot_eval(ld4(S + ob.tgt * 16), ld4(s.us + ob.ref * 16), ld3(ob.zt), ld3(ob.zr), rg, false, r, Jq);
-            cost += 0.5 * log(1.0 + (r[0] * r[0] + r[1] * r[1]));
+#pragma unroll 1
+            for (int b = 0; b < nb; ++b) {
+                double r[2], Jq[6];
+                rot_eval(ld4(cand_frame(s, b, ob.tgt, na)), ld4(s.us + ob.ref * 16), ld3(ob.zt), ld3(ob.zr), rg, false, r, Jq);
+                acc_add(acc, b, 0.5 * log(1.0 + (r[0] * r[0] + r[1] * r[1])));
+            }
         }
     }
     if (has_marg) {
         __syncthreads();                                            // m_dx complete
         const int n = P.marg_n, rk = P.marg_rank;
+        const size_t dxs = P.marg_n + 32;
         // r = S dx + infovec over the non-zero rows on the transposed copy (coalesced): 4 lanes per row (column slices
-        // c = q, q + 4, ...), two independent accumulators per lane
+        // c = q, q + 4, ...); every element of S^T is loaded once for all candidates
         for (int r0 = 0; r0 < rk; r0 += ST / 4) {
             const int r = r0 + (tid >> 2), q = tid & 3;
-            double a0 = 0.0, a1 = 0.0;
-            if (r < rk) {
-                int cidx = q;
-                for (; cidx + 4 < n; cidx += 8) {
-                    a0 += P.marg_St[(size_t)cidx * rk + r] * P.m_dx[cidx];
-                    a1 += P.marg_St[(size_t)(cidx + 4) * rk + r] * P.m_dx[cidx + 4];
+            double a[kSpec];
+#pragma unroll
+            for (int b = 0; b < kSpec; ++b) a[b] = 0.0;
+            if (r < rk)
+#pragma unroll 2
+                for (int cidx = q; cidx < n; cidx += 4) {
+                    const double sv = P.marg_St[(size_t)cidx * rk + r];
+#pragma unroll
+                    for (int b = 0; b < kSpec; ++b) if (b < nb) a[b] += sv * P.m_dx[b * dxs + cidx];
                 }
-                for (; cidx < n; cidx += 4) a0 += P.marg_St[(size_t)cidx * rk + r] * P.m_dx[cidx];
+#pragma unroll
+            for (int b = 0; b < kSpec; ++b) {
+                if (b >= nb) continue;                              // uniform
+                double t = a[b];
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                if (r < rk && q == 0) { t += P.marg_info[r]; acc[b] += 0.5 * t * t; }
             }
-            double a = a0 + a1;
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            a += __shfl_xor_sync(0xffffffffu, a, 2);
-            if (r < rk && q == 0) { a += P.marg_info[r]; cost += 0.5 * a * a; }
         }
         // rows beyond the rank are exactly zero in S; their residual is infovec[r] (zero for our priors)
-        for (int r = rk + tid; r < n; r += ST) { const double a = P.marg_info[r]; cost += 0.5 * a * a; }
+        for (int r = rk + tid; r < n; r += ST) {
+            const double t = P.marg_info[r];
+#pragma unroll
+            for (int b = 0; b < kSpec; ++b) if (b < nb) acc[b] += 0.5 * t * t;
+        }
     }
-    return block_sum(cost, s);
+    // one block reduction for the costs and the step norms (whose warp sums make_candidates left in red4); results go to s.sp
+#pragma unroll
+    for (int k = 0; k < kSpec; ++k) {
+        if (k >= nb) continue;
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s.red4[k * NW + warp] = v;
+    }
+    __syncthreads();
+    if (tid < 2 * kSpec && (tid % kSpec) < nb) {
+        double t = 0.0;
+        for (int w = 0; w < NW; ++w) t += s.red4[tid * NW + w];
+        s.sp[(tid % kSpec) * 8 + 6 + tid / kSpec] = t;
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -411,11 +477,6 @@ template <class SM> static __device__ double evaluate_cost(const Prob &P, SM &s,
 // ------------------------------------------------------------------------------------------------
 template <class SM> static __device__ double evaluate(const Prob &P, SM &s, const double *S, const double *inv, const RigParams &rg,
                            bool want_jac, bool robust = true, KProf *kp = nullptr) {
-    if (!want_jac) {
-        const double c = evaluate_cost(P, s, S, inv, rg, robust);
-        if (kp) kp->mark(9);
-        return c;
-    }
     const int kb = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = P.M;
