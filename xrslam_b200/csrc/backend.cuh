@@ -47,6 +47,7 @@ struct SolveBatch {
     const double *marg;
     double *scratch;
     SolveOut *out;
+    const double *pre_out = nullptr; // optional: preintegration results that never left the device; a PreRef with block < 0 reads block ~block here
 };
 size_t solve_scratch_doubles(int n_active, int n_lm_free, int n_pre, int marg_k, int n_rpe);
 void solve(const SolveBatch &b, int n_problems, const RigParams *rig, cudaStream_t st);

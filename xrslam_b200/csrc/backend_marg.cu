@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(ST, 1) marg_kernel(MargBatch b, const RigParam
     P.states_g = const_cast<double *>(b.states) + (size_t)md.frame_off * 16;
     P.flags_g = nullptr;
     P.invd_user = const_cast<double *>(b.inv_depth) + md.lm_off;
-    P.rpe = b.rpe; P.rot = nullptr; P.pre = b.pre; P.pre_blocks = b.pre_blocks; P.marg_frames = b.marg_frames;
+    P.rpe = b.rpe; P.rot = nullptr; P.pre = b.pre; P.pre_blocks = b.pre_blocks; P.pre_out = nullptr; P.marg_frames = b.marg_frames;
     P.M = md.n_lm; P.Wp = (P.M + 31) / 32 * 32; P.W_sh = WLayout<true>::sh; P.W_pitch = WLayout<true>::pitch; P.W_rows = 6 * N; P.NPc = 15 * N; P.marg_n = 15 * md.marg_k;
     double *Gm;      // factor rows (global)
     double *Yg;      // n1 x 15

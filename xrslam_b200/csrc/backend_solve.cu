@@ -351,7 +351,7 @@ template <class SM> __device__ void solve_body(const SolveBatch &b, const RigPar
     P.states_g = b.states + (size_t)P.d.frame_off * 16;
     P.flags_g = b.frame_flags + P.d.frame_off;
     P.invd_user = b.inv_depth + P.d.lm_off;
-    P.rpe = b.rpe; P.rot = b.rot; P.pre = b.pre; P.pre_blocks = b.pre_blocks; P.marg_frames = b.marg_frames;
+    P.rpe = b.rpe; P.rot = b.rot; P.pre = b.pre; P.pre_blocks = b.pre_blocks; P.pre_out = b.pre_out; P.marg_frames = b.marg_frames;
     P.M = P.d.n_lm_free;
     P.Wp = (P.M + 31) / 32 * 32; P.W_sh = WLayout<SM::kSharedH>::sh; P.W_pitch = WLayout<SM::kSharedH>::pitch; P.W_rows = 6 * P.d.n_active;
     P.NPc = 15 * P.d.n_active;

@@ -235,6 +235,8 @@ struct Lane {
     Arena<xvbe::TriJob> tjobs; Arena<double> tviews; Arena<double> tout;
     DevOnly scratch;
     Stage stage;                       // packed inputs / outputs of one back-end launch
+    Stage stage_pre;                   // inputs of a preintegration launch the host does not wait for (its copy may still be in flight
+                                       // when the solve's inputs are packed into `stage`)
     // Marginalisation runs on its own stream with its own staging block and scratch: its result (the new prior) stays on the
     // device and is first needed by the NEXT window solve of the session, so the host never waits for it (ev_marg_done orders
     // the solves behind it, ev_marg_h2d protects the pinned staging block until its upload has been consumed).
@@ -379,11 +381,13 @@ int merge_preint_jobs(Lane *c, std::vector<Session *> &act) {
     return XRVIO_OK;
 }
 
-int run_preint_jobs(Lane *c) {
+// wait = false: the launch and the copy of the results to the host are only queued; the caller reads pre_out.h after its next
+// synchronisation of the lane's stream (the window solve reads the blocks on the device in the meantime, PreRef::block < 0)
+int run_preint_jobs(Lane *c, bool wait = true) {
     const int n = (int)c->pre_jobs.n;
     if (n == 0) return XRVIO_OK;
     CKC(c->pre_out.reserve((size_t)n * XRVIO_PRE_BLOCK));
-    Stage &g = c->stage;
+    Stage &g = wait ? c->stage : c->stage_pre;
     CKC(g.reserve(Stage::padded(n * sizeof(xvbe::PreintJob)) + Stage::padded(c->imu.n * sizeof(double)) + 512));
     g.reset();
     const xvbe::PreintJob *d_jobs = g.put(c->pre_jobs.h, (size_t)n);
@@ -392,7 +396,7 @@ int run_preint_jobs(Lane *c) {
     { ProfScope ps(c, FAM_PREINT, 1); xvbe::preintegrate(d_jobs, n, d_imu, c->rig_d, c->pre_out.d, c->st); }
     c->stats.kernels_launched += 1;
     CKC(cudaMemcpyAsync(c->pre_out.h, c->pre_out.d, (size_t)n * XRVIO_PRE_BLOCK * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    CKC(cudaStreamSynchronize(c->st));
+    if (wait) CKC(cudaStreamSynchronize(c->st));
     c->stats.h2d_bytes += n * sizeof(xvbe::PreintJob) + c->imu.n * sizeof(double);
     c->stats.d2h_bytes += (size_t)n * XRVIO_PRE_BLOCK * sizeof(double);
     return XRVIO_OK;
@@ -411,7 +415,7 @@ struct Builder {
     std::vector<Track *> free_lm, const_lm;
     struct R { Frame *tgt, *ref; Track *tr; bool prior; V3 zt, zr; };
     struct Ro { Frame *tgt, *ref; V3 zt, zr; };
-    struct P { Frame *i, *j; bool prior; const std::vector<double> *blk; };
+    struct P { Frame *i, *j; bool prior; const std::vector<double> *blk; int dev_job; };   // blk == nullptr: block dev_job of the lane's pre_out, on the device
     std::vector<R> rpe; std::vector<Ro> rot; std::vector<P> pre;
     bool use_marg = false;
     bool with_motion = true;       // false: Solver::add_frame_states(frame, false) -- pose blocks only (initializer.cpp:342)
@@ -430,7 +434,8 @@ struct Builder {
         touch(f); touch(ref);
         rot.push_back({f, ref, f->bearings[tr->get_keypoint_index(f)], ref->bearings[tr->refs.front().second]});
     }
-    void add_pre(Frame *i, Frame *j, const std::vector<double> *blk, bool prior) { touch(i); touch(j); pre.push_back({i, j, prior, blk}); }
+    void add_pre(Frame *i, Frame *j, const std::vector<double> *blk, bool prior) { touch(i); touch(j); pre.push_back({i, j, prior, blk, -1}); }
+    void add_pre_dev(Frame *i, Frame *j, int lane_job, bool prior) { touch(i); touch(j); pre.push_back({i, j, prior, nullptr, lane_job}); }
 };
 
 // Packs one problem into the session's staging buffers (thread-safe across sessions).  Returns 0 or < 0.
@@ -480,12 +485,15 @@ int pack_problem(Lane *c, Session &s, Builder &b, int max_iterations) {
     d.n_rot = (int)b.rot.size();
     for (auto &r : b.rot) { xvbe::RotObs o{}; o.tgt = (short)r.tgt->tmp; o.ref = (short)r.ref->tmp; st3(o.zt, r.zt); st3(o.zr, r.zr); g.rot.push_back(o); }
     d.n_pre = (int)b.pre.size();
-    g.pblocks.resize(b.pre.size() * XRVIO_PRE_BLOCK);
+    g.pblocks.clear();
     for (size_t k = 0; k < b.pre.size(); ++k) {
         const Builder::P &p = b.pre[k];
         xvbe::PreRef r{};
-        r.i = (short)p.i->tmp; r.j = (short)p.j->tmp; r.prior = p.prior ? 1 : 0; r.block = (int)k;
-        std::memcpy(&g.pblocks[k * XRVIO_PRE_BLOCK], p.blk->data(), XRVIO_PRE_BLOCK * sizeof(double));
+        r.i = (short)p.i->tmp; r.j = (short)p.j->tmp; r.prior = p.prior ? 1 : 0;
+        if (p.blk) {
+            r.block = (int)(g.pblocks.size() / XRVIO_PRE_BLOCK);
+            g.pblocks.insert(g.pblocks.end(), p.blk->begin(), p.blk->begin() + XRVIO_PRE_BLOCK);
+        } else r.block = ~p.dev_job;                                 // stays on the device (SolveBatch::pre_out)
         g.pref.push_back(r);
     }
     if (b.use_marg) {
@@ -528,7 +536,7 @@ int merge_problems(Lane *c, std::vector<Session *> &act, int which) {
         const int blk_base = (int)(c->pblocks.n / XRVIO_PRE_BLOCK);
         auto app = [](auto &arena, const auto &v) { if (!v.empty()) { std::memcpy(arena.h + arena.n, v.data(), v.size() * sizeof(v[0])); arena.n += v.size(); } };
         app(c->states, g.states); app(c->fflags, g.flags); app(c->invd, g.invd); app(c->rpe, g.rpe); app(c->rot, g.rot);
-        for (xvbe::PreRef r : g.pref) { r.block += blk_base; c->pref.push(r); }
+        for (xvbe::PreRef r : g.pref) { if (r.block >= 0) r.block += blk_base; c->pref.push(r); }
         app(c->pblocks, g.pblocks); app(c->mframes, g.mframes);
         slot = (int)c->sdesc.push(d);
         g.has_prob = false;
@@ -572,6 +580,7 @@ int run_solves(Lane *c) {
     b.pre_blocks = g.put(c->pblocks.h, c->pblocks.n);
     b.marg_frames = g.put(c->mframes.h, c->mframes.n);
     b.marg = c->d_prior; b.scratch = c->scratch.as<double>();
+    b.pre_out = c->pre_out.d;
     CKC(cudaMemcpyAsync(g.d, g.h, g.off, cudaMemcpyHostToDevice, c->st));
     c->stats.h2d_bytes += in_bytes - n * sizeof(xvbe::SolveOut);
     if (c->marg_pending) { CKC(cudaStreamWaitEvent(c->st, c->ev_marg_done, 0)); c->marg_pending = false; }   // priors written by the marginalisation stream

@@ -609,7 +609,10 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
         return 0; }); if (rc) return rc; }
     { int rc = merge_preint_jobs(c, act); if (rc) return rc; }
     pt.next(17);
-    { int rc = run_preint_jobs(c); if (rc) return rc; }
+    // queued, not waited for: the host packs the problems while the kernel runs, the solve reads the blocks on the device
+    // (PreRef::block < 0) and the host copies (kf_pre / pre, needed from the marginalisation on) are taken after the solve's
+    // synchronisation
+    { int rc = run_preint_jobs(c, false); if (rc) return rc; }
     pt.next(18);
     // ---- refine_window / refine_subwindow problems ----
     // initial priors (estimation/marginalization_factor.h:18-33): zero information except 1e15 on frame-0 q and p
@@ -650,8 +653,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
             for (size_t j = 1; j < m->frame_num(); ++j) {
                 if (s.pre_jobs[j - 1] < 0) continue;
                 Frame *fj = s.pre_job_frames[j - 1];
-                fetch_pre(c, s.pre_base + s.pre_jobs[j - 1], fj->kf_pre);
-                b.add_pre(m->frames[j - 1].get(), fj, &fj->kf_pre, false);
+                b.add_pre_dev(m->frames[j - 1].get(), fj, s.pre_base + s.pre_jobs[j - 1], false);
             }
             return pack_problem(c, s, b, c->prm.solver_iteration_limit);
         }
@@ -665,7 +667,7 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
             Frame *sf = frame->subframes[i].get();
             Frame *prev = i == 0 ? frame : frame->subframes[i - 1].get();
             b.add_active(sf);
-            if (s.pre_jobs[i] >= 0) { fetch_pre(c, s.pre_base + s.pre_jobs[i], sf->pre); b.add_pre(prev, sf, &sf->pre, false); }
+            if (s.pre_jobs[i] >= 0) b.add_pre_dev(prev, sf, s.pre_base + s.pre_jobs[i], false);
             if (!rbranch)
                 for (size_t k = 0; k < sf->keypoint_num(); ++k)
                     if (Track *t = sf->tracks[k]) if (t->valid && t->triangulated && t->is_static) {
@@ -687,8 +689,12 @@ int back_end_round(Lane *c, std::vector<Session *> &act) {
     { int rc = merge_problems(c, act, 2); if (rc) return rc; }
     pt.next(19);
     { int rc = run_solves(c); if (rc) return rc; }
+    if (c->sdesc.n == 0 && c->pre_jobs.n > 0) CKC(cudaStreamSynchronize(c->st));      // no solve waited for the preintegration results
     pt.next(20);
     { int rc = for_sessions(c, act, [&](int, Session &s) -> int {
+        if (s.be_mode == 2)
+            for (size_t k = 0; k < s.pre_jobs.size(); ++k)
+                if (s.pre_jobs[k] >= 0) fetch_pre(c, s.pre_base + s.pre_jobs[k], s.is_keyframe ? s.pre_job_frames[k]->kf_pre : s.pre_job_frames[k]->pre);
         if (s.prob2 < 0) return 0;
         writeback(c, s, s.prob2);
         Map *m = s.sw_map.get();

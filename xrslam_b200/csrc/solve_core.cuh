@@ -177,6 +177,7 @@ struct Prob {
     const RotObs *rot;
     const PreRef *pre;
     const double *pre_blocks;
+    const double *pre_out;         // output blocks of the preintegration kernel still on the device (PreRef::block < 0: block ~block there)
     const int *marg_frames;
     const double *marg_lin, *marg_S, *marg_info, *marg_A0;
     double *rpe_tb;                // per observation: tangent basis b1, b2 of the target bearing (6 doubles)
@@ -195,6 +196,10 @@ struct Prob {
     // bottleneck: 181 issues per tile).  Wp = M rounded up to 32 landmarks; widx() is the only place that knows the layout.
     int Wp, W_sh, W_pitch, W_rows;
 };
+
+__device__ __forceinline__ const double *pre_block(const Prob &P, const PreRef &pf) {
+    return pf.block >= 0 ? P.pre_blocks + (size_t)pf.block * kPreBlock : P.pre_out + (size_t)(~pf.block) * kPreBlock;
+}
 
 template <bool SHARED> struct WLayout { static constexpr int sh = SHARED ? 4 : 5, pitch = SHARED ? 20 : 36; };   // = WStageT<...>::kL / kPitch
 __device__ __forceinline__ size_t widx(const Prob &P, int row, int l) {
@@ -365,7 +370,7 @@ template <class SM> static __device__ XV_NOINLINE void evaluate_cost_multi(const
         for (int t = lane; t < 3 * P.d.n_pre; t += 32) {
             const int f = t / 3;
             const PreRef pf = P.pre[P.d.pre_off + f];
-            const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
+            const double *pb = pre_block(P, pf);
             const double *si = pf.prior ? (s.us + pf.i * 16) : cand_frame(s, b, pf.i, na);
             const double *sj = cand_frame(s, b, pf.j, na);
             pre_eval(si, sj, s.us + pf.i * 16 + 10, pb, rg, false, rb + f * 16, nullptr, nullptr, t % 3);
@@ -375,7 +380,7 @@ template <class SM> static __device__ XV_NOINLINE void evaluate_cost_multi(const
         for (int e = lane; e < 15 * P.d.n_pre; e += 32) {          // whitened residual, one lane per row
             const int f = e / 15, r = e % 15;
             const PreRef pf = P.pre[P.d.pre_off + f];
-            const double *Sic = P.pre_blocks + (size_t)pf.block * kPreBlock + PB_SIC;
+            const double *Sic = pre_block(P, pf) + PB_SIC;
             const double *sc = rb + f * 16;
             double a = 0.0;
 #pragma unroll
@@ -499,7 +504,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
     // whitening and J^T J / gradient products of one preintegration factor by one warp (raw residual and Jacobians are in its scratch)
     auto pre_coop = [&](int f, bool whiten_residual) {
         const PreRef pf = P.pre[P.d.pre_off + f];
-        const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
+        const double *pb = pre_block(P, pf);
         double *sc = P.pre_s + (size_t)f * kPreScratch;
         const double *Sic = pb + PB_SIC;
         if (whiten_residual) {                                // (the sequential layout does this with one thread per row before the barrier)
@@ -565,7 +570,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
     if (split_pre && warp == NW - 1)
         for (int f = lane; f < P.d.n_pre; f += 32) {
             const PreRef pf = P.pre[P.d.pre_off + f];
-            const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
+            const double *pb = pre_block(P, pf);
             double *sc = P.pre_s + (size_t)f * kPreScratch;
             const double *si = pf.prior ? (s.us + pf.i * 16) : (S + pf.i * 16);
             const double *sj = S + pf.j * 16;
@@ -787,7 +792,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
     if (!split_pre && tid < P.d.n_pre) {
         const int f = tid;
         const PreRef pf = P.pre[P.d.pre_off + f];
-        const double *pb = P.pre_blocks + (size_t)pf.block * kPreBlock;
+        const double *pb = pre_block(P, pf);
         double *sc = P.pre_s + (size_t)f * kPreScratch;     // [0,15) r  [16,241) Ji  [241,466) Jj  [466,691) Jwi [691,916) Jwj [916,931) rw
         const double *si = pf.prior ? (s.us + pf.i * 16) : (S + pf.i * 16);
         const double *sj = S + pf.j * 16;
@@ -797,7 +802,7 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
     if (!split_pre && tid < 15 * P.d.n_pre) {          // whitened residual, one thread per row
         const int f = tid / 15, r = tid % 15;
         const PreRef pf = P.pre[P.d.pre_off + f];
-        const double *Sic = P.pre_blocks + (size_t)pf.block * kPreBlock + PB_SIC;
+        const double *Sic = pre_block(P, pf) + PB_SIC;
         double *sc = P.pre_s + (size_t)f * kPreScratch;
         double a = 0.0;
 #pragma unroll
