@@ -855,42 +855,52 @@ template <class SM> static __device__ double evaluate(const Prob &P, SM &s, cons
         }
         if (want_jac) {
             __syncthreads();
-            for (int c = tid; c < n; c += ST) {            // v = S^T r
-                double a = 0.0;
-                for (int r = 0; r < P.marg_rank; ++r) a += P.marg_S[(size_t)r * n + c] * P.m_r[r];
-                P.m_v[c] = a;
+            {   // v = S^T r on the transposed copy: one warp per column, lanes over the (contiguous) non-zero rows
+                const int rk = P.marg_rank;
+                for (int c = warp; c < n; c += NW) {
+                    double a = 0.0;
+                    for (int r = lane; r < rk; r += 32) a += P.marg_St[(size_t)c * rk + r] * P.m_r[r];
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    if (lane == 0) P.m_v[c] = a;
+                }
             }
-            // T = A0 * B  (B = blockdiag(Jr^-1 on q blocks, I))
-            for (int e = tid; e < n * K * 5; e += ST) {
-                const int r = e / (K * 5), cb = e % (K * 5);       // 3-column block cb
-                const int k = cb / 5, sub = cb % 5;
-                const double *a0 = P.marg_A0 + (size_t)r * n + 15 * k + 3 * sub;
-                double *t = P.m_T + (size_t)r * n + 15 * k + 3 * sub;
-                if (sub == 0) {
-                    const double *Jr = s.jrinv + 9 * k;
-                    for (int c = 0; c < 3; ++c) t[c] = a0[0] * Jr[0 * 3 + c] + a0[1] * Jr[1 * 3 + c] + a0[2] * Jr[2 * 3 + c];
-                } else { t[0] = a0[0]; t[1] = a0[1]; t[2] = a0[2]; }
+            // H += B^T A0 B (lower triangle) with B = blockdiag(Jr^-1 on the q blocks, I): every 15-block is five 3-blocks, so one
+            // thread per 3 x 3 block of A0 applies B on both sides in registers -- one pass over A0, no intermediate product
+            {
+                const int nb3 = n / 3;
+                for (int e = tid; e < nb3 * (nb3 + 1) / 2; e += ST) {
+                    int I = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+                    while (I * (I + 1) / 2 > e) --I;
+                    while ((I + 1) * (I + 2) / 2 <= e) ++I;
+                    const int J = e - I * (I + 1) / 2;
+                    const int ki = I / 5, kj = J / 5;
+                    const int fi = P.marg_frames[P.d.marg_frames_off + ki], fj = P.marg_frames[P.d.marg_frames_off + kj];
+                    if (fi >= P.d.n_active || fj >= P.d.n_active) continue;
+                    double t[3][3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const double *a0 = P.marg_A0 + (size_t)(3 * I + r) * n + 3 * J;
+                        if (J % 5 == 0) {
+                            const double *Jr = s.jrinv + 9 * kj;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) t[r][c] = a0[0] * Jr[0 * 3 + c] + a0[1] * Jr[1 * 3 + c] + a0[2] * Jr[2 * 3 + c];
+                        } else { t[r][0] = a0[0]; t[r][1] = a0[1]; t[r][2] = a0[2]; }
+                    }
+                    const bool roti = I % 5 == 0;
+                    const double *Ji = s.jrinv + 9 * ki;
+#pragma unroll
+                    for (int oi = 0; oi < 3; ++oi)
+#pragma unroll
+                        for (int oj = 0; oj < 3; ++oj) {
+                            if (I == J && oj > oi) continue;
+                            const double a = roti ? Ji[0 * 3 + oi] * t[0][oj] + Ji[1 * 3 + oi] * t[1][oj] + Ji[2 * 3 + oi] * t[2][oj] : t[oi][oj];
+                            const int A = 15 * fi + 3 * (I % 5) + oi, B = 15 * fj + 3 * (J % 5) + oj;
+                            if (!s.col_free[A] || !s.col_free[B]) continue;
+                            s.H[A >= B ? hidx(A, B) : hidx(B, A)] += a;     // distinct (i,j) map to distinct (A,B)
+                        }
+                }
             }
-            __syncthreads();
-            // H += B^T T (lower triangle), g += B^T v ; one thread per entry, no atomics needed now
-            for (int e = tid; e < n * (n + 1) / 2; e += ST) {
-                int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-                while (i * (i + 1) / 2 > e) --i;
-                while ((i + 1) * (i + 2) / 2 <= e) ++i;
-                const int j = e - i * (i + 1) / 2;
-                const int ki = i / 15, oi = i % 15;
-                double a;
-                if (oi < 3) {
-                    const double *Jr = s.jrinv + 9 * ki;
-                    a = Jr[0 * 3 + oi] * P.m_T[(size_t)(15 * ki + 0) * n + j] + Jr[1 * 3 + oi] * P.m_T[(size_t)(15 * ki + 1) * n + j] +
-                        Jr[2 * 3 + oi] * P.m_T[(size_t)(15 * ki + 2) * n + j];
-                } else a = P.m_T[(size_t)i * n + j];
-                const int fi = P.marg_frames[P.d.marg_frames_off + ki], fj = P.marg_frames[P.d.marg_frames_off + j / 15];
-                if (fi >= P.d.n_active || fj >= P.d.n_active) continue;
-                const int A = 15 * fi + oi, B = 15 * fj + j % 15;
-                if (!s.col_free[A] || !s.col_free[B]) continue;
-                s.H[A >= B ? hidx(A, B) : hidx(B, A)] += a;     // distinct (i,j) map to distinct (A,B)
-            }
+            __syncthreads();                                        // m_v complete
             for (int c = tid; c < n; c += ST) {
                 const int k = c / 15, oc = c % 15;
                 double a;
