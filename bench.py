@@ -345,6 +345,7 @@ def run_cuda_arm(args, rank, world, local_rank):
     pe = prof.get(pk, {}) if prof else {}
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': pe.get('dram_bytes'), 'traffic_source': ('profiles/r2_kernels.json:' + pk) if pe else None,
+                'traffic_capture': prof.get('_capture') if prof else None,      # which library state the committed ncu capture belongs to
                 'launches': n_launch, 'avg_launch_ms': fam_ms / n_launch,
                 'pass': 'per-launch events in a separate pass over the same K steps: %.3f ms/step with them, %.3f in the metric pass' % (r_prof['ms'] / K, ms_dev / K),
                 'share_of_kernel_time': fam_ms / max(sum(v[0] for v in kt.values()), 1e-9),
