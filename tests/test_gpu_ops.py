@@ -304,3 +304,25 @@ def test_triangulation(xrvio):
     assert np.array_equal(out[:, 3], ref[:, 3])
     ok = ref[:, 3] > 0
     assert np.abs(out[ok, :3] - ref[ok, :3]).max() < 1e-7
+
+
+@pytest.mark.parametrize('limit', [1, 2, 3, 4, 5, 7, 12])
+def test_solver_iteration_limits_with_batched_candidates(xrvio, golden_problems, limit):
+    """The trust-region loop evaluates the candidates of consecutive rejections in batches (evaluate_cost_multi) and consumes them
+    one iteration at a time; a batch may not reach past max_num_iterations.  Every limit must give the oracle's iteration count,
+    termination and cost trace -- in particular the limits that end in the middle of a batch (the window problem accepts two
+    steps and then rejects: batches 1, 1, 1, 2, 4, 4, ...)."""
+    import copy
+    from oracle import ceres_tr
+    pb = problem_io.problem_from_dict(golden_problems, 'window/pre/')
+    pb.max_iterations = limit
+    ref = copy.deepcopy(pb)
+    summ = ceres_tr.solve(ref)
+    out = bridge.solve_problem_cuda(pb)
+    assert int(out['iterations']) == len(summ.iterations)
+    trace = np.array([it['cost'] for it in summ.iterations])
+    assert np.allclose(out['cost_trace'][:len(trace)], trace, rtol=1e-6, atol=0)
+    assert abs(out['final_cost'] - summ.final_cost) <= 1e-6 * summ.final_cost
+    flags = [bool(it.get('successful', False)) for it in summ.iterations]
+    assert int(out['n_successful']) == sum(flags) and int(out['n_unsuccessful']) == len(flags) - sum(flags)
+    assert np.abs(pb.states[:, 0:4] - ref.states[:, 0:4]).max() < 1e-7 and np.abs(pb.states[:, 4:7] - ref.states[:, 4:7]).max() < 1e-6
