@@ -326,3 +326,41 @@ def test_solver_iteration_limits_with_batched_candidates(xrvio, golden_problems,
     flags = [bool(it.get('successful', False)) for it in summ.iterations]
     assert int(out['n_successful']) == sum(flags) and int(out['n_unsuccessful']) == len(flags) - sum(flags)
     assert np.abs(pb.states[:, 0:4] - ref.states[:, 0:4]).max() < 1e-7 and np.abs(pb.states[:, 4:7] - ref.states[:, 4:7]).max() < 1e-6
+
+
+def _perturb_problem(pb, seed, amp):
+    rng = np.random.default_rng(seed)
+    na = pb.states.shape[0]
+    pb.states[:, 4:7] += amp * rng.standard_normal((na, 3))
+    dq = amp * 0.5 * rng.standard_normal((na, 3))
+    q = pb.states[:, 0:4].copy()
+    for i in range(na):
+        d = np.array([dq[i, 0] / 2, dq[i, 1] / 2, dq[i, 2] / 2, 1.0])
+        d /= np.linalg.norm(d)
+        x1, y1, z1, w1 = q[i]
+        x2, y2, z2, w2 = d
+        pb.states[i, 0:4] = [w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+                             w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2]
+    pb.inv_depth = pb.inv_depth * np.exp(amp * rng.standard_normal(pb.inv_depth.shape))
+
+
+@pytest.mark.parametrize('seed,amp', [(2, 0.05), (3, 0.05), (4, 0.05), (5, 0.5)])
+def test_solver_accepts_inside_candidate_batches(xrvio, golden_problems, seed, amp):
+    """Window problems started far from the optimum: the oracle's runs mix accepted and rejected steps (e.g. AAAAAArrrAAAArAAAArrr...,
+    AAAArrrrrAArAArrAAArrr...), so candidates are accepted out of the middle of a speculative batch and the rest of the batch
+    is discarded.  Iteration count, accept / reject totals and the whole cost trace must equal the oracle's."""
+    import copy
+    from oracle import ceres_tr
+    pb = problem_io.problem_from_dict(golden_problems, 'window/pre/')
+    _perturb_problem(pb, seed, amp)
+    ref = copy.deepcopy(pb)
+    summ = ceres_tr.solve(ref)
+    flags = [bool(it.get('successful', False)) for it in summ.iterations]
+    pattern = ''.join('A' if f else 'r' for f in flags)
+    assert 'rrA' in pattern and sum(flags) >= 10, pattern           # the case is what the docstring says
+    out = bridge.solve_problem_cuda(pb)
+    assert int(out['iterations']) == len(summ.iterations)
+    assert int(out['n_successful']) == sum(flags) and int(out['n_unsuccessful']) == len(flags) - sum(flags)
+    trace = np.array([it['cost'] for it in summ.iterations])
+    assert np.allclose(out['cost_trace'][:len(trace)], trace, rtol=1e-6, atol=0)
+    assert abs(out['final_cost'] - summ.final_cost) <= 1e-6 * summ.final_cost
