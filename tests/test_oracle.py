@@ -291,3 +291,33 @@ def test_window_ba_runs_to_the_iteration_limit():
             assert tail[-1]['radius'] < tail[0]['radius'] * 2.0 ** -(len(tail) - 2)   # halved at every rejection
         seen += len(wins)
     assert seen >= 6
+
+
+def test_failed_candidate_evaluation_is_a_rejected_step(monkeypatch):
+    """ADVICE r1: Ceres 1.14 (ComputeCandidatePointAndEvaluateCost) leaves candidate_cost = numeric_limits<double>::max() when the
+    evaluation of a candidate fails, so the step is rejected and the radius halved; it must not end the solve as "function
+    tolerance reached".  Natural inputs do not produce a non-finite candidate (it takes a landmark exactly at depth 0), so the
+    evaluation is stubbed here: the second cost-only evaluation of a recorded sub-window problem returns inf.  The kernel holds the
+    same statement (backend_solve.cu: `if (!isfinite(cand_cost)) cand_cost = DBL_MAX`)."""
+    from oracle import ceres_tr, problem_io
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'backend_problems.npz'))
+    pb = problem_io.problem_from_dict(g, 'localize/pre/')
+    clean = ceres_tr.solve(problem_io.problem_from_dict(g, 'localize/pre/'))
+    real = ceres_tr.evaluate
+    calls = {'n': 0}
+
+    def stub(pb_, lay, states, inv_depth, want_jac):
+        out = real(pb_, lay, states, inv_depth, want_jac)
+        if not want_jac:
+            calls['n'] += 1
+            if calls['n'] == 2:
+                return (float('inf'),) + tuple(out[1:])
+        return out
+    monkeypatch.setattr(ceres_tr, 'evaluate', stub)
+    summ = ceres_tr.solve(pb)
+    its = summ.iterations
+    assert calls['n'] >= 3                                        # the solve went on after the failed evaluation
+    bad = its[2]
+    assert bad['successful'] is False and bad['cost'] == np.finfo(np.float64).max
+    assert len(its) > 3 and its[3]['radius'] == 0.5 * bad['radius']          # rejected: the radius is halved and the loop goes on
+    assert abs(summ.final_cost - clean.final_cost) <= 1e-9 * clean.final_cost
