@@ -319,5 +319,6 @@ def test_failed_candidate_evaluation_is_a_rejected_step(monkeypatch):
     assert calls['n'] >= 3                                        # the solve went on after the failed evaluation
     bad = its[2]
     assert bad['successful'] is False and bad['cost'] == np.finfo(np.float64).max
-    assert len(its) > 3 and its[3]['radius'] == 0.5 * bad['radius']          # rejected: the radius is halved and the loop goes on
+    assert bad['radius'] == 0.5 * its[1]['radius']                 # rejected: the radius (recorded after the update) is halved ...
+    assert len(its) > 3 and summ.termination == clean.termination  # ... and the loop goes on to the same end
     assert abs(summ.final_cost - clean.final_cost) <= 1e-9 * clean.final_cost
