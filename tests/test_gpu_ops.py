@@ -364,3 +364,39 @@ def test_solver_accepts_inside_candidate_batches(xrvio, golden_problems, seed, a
     trace = np.array([it['cost'] for it in summ.iterations])
     assert np.allclose(out['cost_trace'][:len(trace)], trace, rtol=1e-6, atol=0)
     assert abs(out['final_cost'] - summ.final_cost) <= 1e-6 * summ.final_cost
+
+
+def test_preintegration_chunk_boundaries(xrvio):
+    """preint_kernel precomputes the per-sample quantities 32 samples at a time (one per lane) before the sequential recursion:
+    job lengths around the chunk boundaries, many chunks, and a batch of jobs of mixed lengths against the oracle's PreIntegrator."""
+    from oracle.preintegrator import PreIntegrator
+    rng = np.random.default_rng(23)
+    cfg = Config()
+    rig = bridge.rig_from_cfg(cfg)
+    lengths = [2, 31, 32, 33, 63, 64, 65, 100, 200, 5]
+    jobs = np.zeros(len(lengths), xrvio.preint_job_dtype)
+    imu_all, ref = [], []
+    for k, n in enumerate(lengths):
+        t = 0.3 + k
+        data = []
+        for _ in range(n):
+            data.append((t, rng.normal(size=3) * 0.4, np.array([0.1, -0.2, 9.7]) + rng.normal(size=3)))
+            t += 0.005 * (1 + 0.1 * rng.random())
+        t_end = t + 0.002
+        bg, ba = rng.normal(size=3) * 0.01, rng.normal(size=3) * 0.05
+        pre = PreIntegrator(cfg.cov_g, cfg.cov_a, cfg.cov_bg, cfg.cov_ba)
+        pre.data = data
+        pre.integrate(t_end, bg, ba, True, True)
+        jobs[k]['imu_off'], jobs[k]['n'], jobs[k]['t_end'] = len(imu_all), n, t_end
+        jobs[k]['bg'], jobs[k]['ba'], jobs[k]['flags'] = bg, ba, 3
+        imu_all.extend([[d[0]] + list(d[1]) + list(d[2]) for d in data])
+        ref.append(np.concatenate([[pre.t], pre.q, pre.p, pre.v, pre.cov.ravel(), pre.sqrt_inv_cov.ravel(), pre.dq_dbg.ravel(),
+                                   pre.dp_dbg.ravel(), pre.dp_dba.ravel(), pre.dv_dbg.ravel(), pre.dv_dba.ravel()]))
+    out = xrvio.op_preintegrate(rig, jobs, np.array(imu_all))
+    sl = dict(state=slice(0, 11), cov=slice(11, 236), sic=slice(236, 461), jac=slice(461, 506))
+    for k in range(len(lengths)):
+        for name, s in sl.items():
+            scale = np.abs(ref[k][s]).max() + 1e-300
+            tol = 1e-9 if name != 'sic' else 1e-7
+            err = np.abs(out[k][:506][s] - ref[k][s]).max() / scale
+            assert err < tol, (lengths[k], name, err)
