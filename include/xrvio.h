@@ -80,7 +80,7 @@ typedef struct xrvio_rot {        /* rotation prior residual (rotation_factor.h)
 typedef struct xrvio_pre_ref {    /* preintegration residual (preintegration_factor.h) */
     short i, j;
     int prior;                    /* 1: PreIntegrationPriorFactor (frame_i constant) */
-    int block;                    /* index of its result block */
+    int block;                    /* index of its result block in pre_blocks (0 <= block < n_pre_blocks; anything else is XRVIO_ERR_ARG) */
     int pad;
 } xrvio_pre_ref;
 

@@ -400,3 +400,16 @@ def test_preintegration_chunk_boundaries(xrvio):
             tol = 1e-9 if name != 'sic' else 1e-7
             err = np.abs(out[k][:506][s] - ref[k][s]).max() / scale
             assert err < tol, (lengths[k], name, err)
+
+
+def test_solver_rejects_preintegration_block_out_of_range(xrvio, golden_problems):
+    """xrvio_pre_ref::block must index pre_blocks (0 <= block < n_pre_blocks); the negative values the session layer uses internally
+    for blocks that never left the device are not part of the operator API."""
+    pb = problem_io.problem_from_dict(golden_problems, 'window/pre/')
+    for bad in (-1, 10 ** 6):
+        pk = bridge.PackedProblems([pb])
+        assert len(pk.pre) > 0
+        pk.pre[0]['block'] = bad
+        with pytest.raises(Exception) as e:
+            pk.solve(bridge.rig_from_problem(pb))
+        assert 'block index out of range' in str(e.value)

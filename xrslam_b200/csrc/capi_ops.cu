@@ -195,6 +195,9 @@ int xrvio_op_solve(const xrvio_rig *rig, xrvio_solve_desc *desc, int n_problems,
                    int n_pre_blocks, const int *marg_frames, int n_marg_frames, const double *marg,
                    long long n_marg_doubles, xrvio_solve_out *out) {
     if (!rig || !desc || !states || !frame_flags || !out || n_problems <= 0 || n_frames <= 0) return fail_arg("xrvio_op_solve: bad argument");
+    // (a negative block means "still on the device" inside the session layer only; here every block comes from pre_blocks)
+    for (int i = 0; i < n_pre; ++i)
+        if (pre[i].block < 0 || pre[i].block >= n_pre_blocks) return fail_arg("xrvio_op_solve: preintegration block index out of range");
     long long scratch = 0;
     bool large = false;
     for (int p = 0; p < n_problems; ++p) large = large || desc[p].n_active > XRVIO_MAX_ACTIVE;
@@ -261,6 +264,8 @@ int xrvio_op_marginalize(const xrvio_rig *rig, xrvio_marg_desc *desc, int n_prob
                          int n_pre, const double *pre_blocks, int n_pre_blocks, const int *marg_frames, int n_marg_frames,
                          const double *marg, long long n_marg_doubles, double *out, long long n_out_doubles, int *rank_out) {
     if (!rig || !desc || !states || !marg || !out || !rank_out || n_problems <= 0) return fail_arg("xrvio_op_marginalize: bad argument");
+    for (int i = 0; i < n_pre; ++i)
+        if (pre[i].block < 0 || pre[i].block >= n_pre_blocks) return fail_arg("xrvio_op_marginalize: preintegration block index out of range");
     long long scratch = 0;
     for (int p = 0; p < n_problems; ++p) {
         xrvio_marg_desc &d = desc[p];
